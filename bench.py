@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""Headline benchmark: complexes scored per second, EGNN forward.
+
+Workload (BASELINE.json configs[2]): 8-layer / 64-channel `egnn` pose
+classifier with edge + node attention (residual, normalise, tanh on),
+synthetic ~1000-atom complexes with hydrogens-like density, batch 128 per
+GPU.  One step = the hot path over one batch: K1 radius-graph build (CSR +
+tiles) -> embedding -> 8 fused EGNN layers -> mean pool -> head.  Complexes
+are sharded across GPUs with no inter-GPU traffic (weak scaling).
+
+    python bench.py --gpus N --steps K --warmup W          # this framework
+    python bench.py --impl reference ...                   # CPU port of the
+                                                           # reference path
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'complexes scored/sec (EGNN fwd, 8 layers x 64 ch, ~1k-atom complexes)'
+UNIT = 'complexes/s'
+MODEL_KW = dict(dim_input=13, dim_output=1, k=64, num_layers=8,
+                edge_attention=True, node_attention=True, residual=True,
+                normalize=True, tanh=True, graphnorm=False)
+EDGE_RADIUS = 4.0
+# algorithmic FLOPs (2 x MAC, dense formulation of the
+# reference) and compulsory HBM bytes
+FLOP_PER_EDGE_LAYER = 2 * (4 * 64 * 64 + 6 * 64)      # 33 536
+FLOP_PER_NODE_LAYER = 2 * (3 * 64 * 64 + 64)          # 24 704
+BYTES_PER_COMPLEX_FWD = 4.94e6
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=128,
+                    help='complexes per GPU per step')
+    ap.add_argument('--atoms', type=int, default=1000)
+    ap.add_argument('--math', default=os.environ.get('PVS_MATH', 'fp32'),
+                    choices=['fp32', 'bf16x3', 'bf16'])
+    ap.add_argument('--input-sets', type=int, default=3,
+                    help='distinct input batches rotated through the steps')
+    ap.add_argument('--cpu-sample', type=int, default=16,
+                    help='complexes in the CPU-baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed
+    region (pynvml; same fields as the nvidia-smi query in the recipe)."""
+
+    REASONS = {
+        0x0000000000000004: 'sw_power_cap',
+        0x0000000000000008: 'hw_slowdown',
+        0x0000000000000020: 'sw_thermal_slowdown',
+        0x0000000000000040: 'hw_thermal_slowdown',
+        0x0000000000000080: 'hw_power_brake_slowdown',
+    }
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(
+                self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:   # noqa: BLE001 - NVML missing: report nulls
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(
+                    self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:   # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.ok:
+            self.join(timeout=2)
+        return {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
+                'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------
+# CPU leg: the oracle port of the reference path (test infrastructure; this is
+# the one place bench.py executes oracle/)
+# ---------------------------------------------------------------------------
+def cpu_reference_step(sd, complexes):
+    """Reference path on the host for a list of complexes: generate_edges
+    restatement (numpy, cdist-style O(N^2)) + PyG-style collate + EGNN fwd."""
+    import torch
+    from oracle import egnn_oracle, radius_graph as rg
+    rows, cols, attrs, feats, pos, batch = [], [], [], [], [], []
+    off = 0
+    t0 = time.perf_counter()
+    for b, (coords, bp, f) in enumerate(complexes):
+        _, r, c, a = rg.radius_graph(coords, bp, EDGE_RADIUS, EDGE_RADIUS)
+        rows.append(r + off), cols.append(c + off), attrs.append(a)
+        feats.append(f), pos.append(coords.astype(np.float32))
+        batch.append(np.full(len(coords), b, dtype=np.int64))
+        off += len(coords)
+    t_graph = time.perf_counter() - t0
+    ei = torch.from_numpy(np.vstack([np.concatenate(rows),
+                                     np.concatenate(cols)]))
+    ea = torch.nn.functional.one_hot(
+        torch.from_numpy(np.concatenate(attrs)).long(), 3)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        out, _ = egnn_oracle.model_forward(
+            sd, torch.from_numpy(np.concatenate(feats)), ei,
+            torch.from_numpy(np.concatenate(pos)), ea,
+            torch.from_numpy(np.concatenate(batch)),
+            num_layers=MODEL_KW['num_layers'],
+            **{k: v for k, v in MODEL_KW.items() if k not in (
+                'dim_input', 'dim_output', 'k', 'num_layers')})
+    t_model = time.perf_counter() - t0
+    return out, ei.shape[1], t_graph, t_model
+
+
+def reference_state_dict():
+    """Random-init weights of the architecture (seed 0), built on the CPU by
+    the host-side module (parameter containers only; no kernels involved)."""
+    import torch
+    from pathlib import Path
+    import pointvs_b200 as pv
+    torch.manual_seed(0)
+    model = pv.SartorrasEGNN(Path('/tmp/pvs_bench'), 0, 0, None, None,
+                             silent=True, **MODEL_KW)
+    return {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (the
+    oracle port; the reference itself is Python that cannot travel to the
+    GPU box), all host threads, rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    from pointvs_b200.synthetic import synthetic_complex
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = reference_state_dict()
+    sample = max(1, min(args.cpu_sample, args.batch))
+    sets = [[synthetic_complex(1000 * s + i, args.atoms, 30)
+             for i in range(sample)] for s in range(2)]
+    for w in range(max(1, min(args.warmup, 1))):
+        cpu_reference_step(sd, sets[w % 2])
+    t0 = time.perf_counter()
+    edges = 0
+    steps = max(1, min(args.steps, 5))
+    for s in range(steps):
+        _, e, _, _ = cpu_reference_step(sd, sets[s % 2])
+        edges += e
+    dt = time.perf_counter() - t0
+    value = steps * sample / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': steps, 'warmup': 1,
+        'ms_per_step': 1e3 * dt / steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': workload_config(args, sample_per_step=sample),
+        'edges_per_s': edges / dt,
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores,
+                         'kind': 'port',
+                         'sample': f'{sample} complexes x {args.atoms} atoms '
+                                   f'per step, {steps} steps (graph build + '
+                                   'EGNN fwd, torch CPU)'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, sample_per_step=None):
+    return {
+        'workload': 'BASELINE configs[2]: egnn 8 layers x 64 channels, '
+                    'edge+node attention, residual, normalise, tanh, '
+                    f'~{args.atoms}-atom synthetic complexes (density 0.065/A^3, '
+                    f'edge_radius {EDGE_RADIUS}), batch {args.batch}/GPU; step = '
+                    'radius-graph build + forward + score',
+        'complexes_per_step_per_gpu': sample_per_step or args.batch,
+        'atoms_per_complex': args.atoms,
+        'math': args.math if args.impl == 'ours' else 'fp32-cpu',
+        'parallelism': f'complex-sharded x{args.gpus}, no inter-GPU traffic',
+        'l2': 'per-step working set (P,Q,M,h,x,CSR ~ 0.2 GB) exceeds the '
+              f'126 MB L2; {args.input_sets} distinct input batches rotate',
+    }
+
+
+# ---------------------------------------------------------------------------
+# GPU leg
+# ---------------------------------------------------------------------------
+class StageTimer:
+    """CUDA events around the stages of every layer call (stage 2 = the edge
+    kernel), recorded on the launching stream inside the timed region."""
+
+    def __init__(self, torch):
+        self.torch = torch
+        self.pairs = {1: [], 2: [], 4: []}
+        self._open = None
+
+    def begin(self, stage):
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._open = ev
+
+    def end(self, stage):
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.pairs[stage].append((self._open, ev))
+
+    def totals_ms(self):
+        return {s: (sum(a.elapsed_time(b) for a, b in p), len(p))
+                for s, p in self.pairs.items()}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pathlib import Path
+    import pointvs_b200 as pv
+    from pointvs_b200 import _cabi, egnn as egnn_mod
+    from pointvs_b200.synthetic import synthetic_batch
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl ours needs a CUDA device '
+                         '(no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    n_gpus = world
+
+    torch.manual_seed(0)
+    model = pv.SartorrasEGNN(Path('/tmp/pvs_bench'), 0, 0, None, None,
+                             silent=True, **MODEL_KW).to(dev).eval()
+    model.set_math(args.math)
+    model.set_record_side_channels(False)
+    model.record_embed_coords = False
+
+    # distinct complexes per rank and per input set
+    host_sets, dev_sets = [], []
+    for s in range(args.input_sets):
+        coords, bp, feats, cptr = synthetic_batch(
+            1_000_000 * rank + 10_000 * s, args.batch, args.atoms, 30)
+        host = (torch.from_numpy(coords).pin_memory(),
+                torch.from_numpy(bp).pin_memory(),
+                torch.from_numpy(feats).pin_memory(), cptr)
+        host_sets.append(host)
+        dev_sets.append((host[0].to(dev), host[1].to(dev), host[2].to(dev), cptr))
+
+    def step_device(i):
+        coords, bp, feats, cptr = dev_sets[i % args.input_sets]
+        batch = pv.PackedBatch.from_arrays(coords, bp, feats, cptr,
+                                           EDGE_RADIUS, EDGE_RADIUS, device=dev)
+        with torch.no_grad():
+            return model(batch), batch.pvs_csr.n_edges
+
+    def step_e2e(i):
+        coords, bp, feats, cptr = host_sets[i % args.input_sets]
+        batch = pv.PackedBatch.from_arrays(
+            coords.to(dev, non_blocking=True), bp.to(dev, non_blocking=True),
+            feats.to(dev, non_blocking=True), cptr, EDGE_RADIUS, EDGE_RADIUS,
+            device=dev)
+        with torch.no_grad():
+            scores = model(batch)
+        return scores.cpu(), batch.pvs_csr.n_edges
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident measurement (the `value`) ----
+    for i in range(args.warmup):
+        step_device(i)
+    sampler = ClockSampler(local_rank)
+    timer = StageTimer(torch)
+    launches0 = _cabi.lib().pvs_launch_count()
+    barrier()
+    sampler.start() if sampler.ok else None
+    egnn_mod.STAGE_TIMER = timer
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    edges = 0
+    for i in range(args.steps):
+        _, e = step_device(args.warmup + i)
+        edges += e
+    ev1.record()
+    barrier()
+    egnn_mod.STAGE_TIMER = None
+    clocks = sampler.stop()
+    launches = _cabi.lib().pvs_launch_count() - launches0
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    total_complexes = args.batch * args.steps * n_gpus
+    total_edges = sum_over_ranks(edges)
+    value = total_complexes / (ms_total * 1e-3)
+
+    # ---- end to end through the public API, host buffers ----
+    for i in range(args.warmup):
+        step_e2e(i)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        scores, _ = step_e2e(args.warmup + i)
+    ev1.record()
+    barrier()
+    ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
+    h2d = sum(t.numel() * t.element_size() for t in host_sets[0][:3])
+    d2h = scores.numel() * scores.element_size()
+
+    # ---- roofline of the dominant kernel (edge kernel, stage 2) ----
+    stage = timer.totals_ms()
+    edge_ms, edge_calls = stage[2]
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak_tf = peaks.get('bf16_tflops_sustained')
+    peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)'
+    if peak_tf is None:
+        peak_tf, peak_src = 1590.0, 'B200_PROFILING.md fallback (of fallback)'
+    k = MODEL_KW['k']
+    flop_per_launch = (edges / max(1, args.steps)) * (2 * (4 * k * k + 6 * k))
+    avg_launch_s = (edge_ms / max(1, edge_calls)) * 1e-3
+    achieved_tf = flop_per_launch / avg_launch_s / 1e12 if avg_launch_s > 0 else 0.0
+    roofline = {
+        'kernel': 'egnn_edge_fwd (per-layer edge MLP + attention + segment reduce)',
+        'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf,
+        'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf, 'traffic': None,
+        'peak_source': peak_src,
+        'algorithmic_flop_per_launch': flop_per_launch,
+        'avg_launch_ms': avg_launch_s * 1e3,
+        'share_of_step': edge_ms / max(1e-9, ms_total),
+        'stage_ms_per_step': {
+            'node_pre': stage[1][0] / args.steps,
+            'edge': stage[2][0] / args.steps,
+            'node': stage[4][0] / args.steps},
+        'hbm_algorithmic_gbs': value / n_gpus * BYTES_PER_COMPLEX_FWD / 1e9,
+        'hbm_peak_gbs': peaks.get('hbm_gbs'),
+    }
+
+    cpu_baseline = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        from pointvs_b200.synthetic import synthetic_complex
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd = {k_: v.detach().cpu() for k_, v in model.state_dict().items()}
+        sample = [synthetic_complex(i, args.atoms, 30)
+                  for i in range(args.cpu_sample)]
+        cpu_reference_step(sd, sample[:2])   # warm-up
+        best, tg, tm = None, 0.0, 0.0
+        for _ in range(3):
+            t0 = time.perf_counter()
+            cpu_out, _, t_graph, t_model = cpu_reference_step(sd, sample)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best:
+                best, tg, tm = dt, t_graph, t_model
+        cpu_baseline = {
+            'value': args.cpu_sample / best, 'unit': UNIT, 'cores': cores,
+            'kind': 'port',
+            'sample': f'{args.cpu_sample} complexes x {args.atoms} atoms, '
+                      'best of 3 (oracle port of generate_edges + EGNN fwd, '
+                      'torch CPU fp32)',
+            'graph_build_s': tg, 'model_fwd_s': tm}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': n_gpus,
+            'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None,
+            'dtype': {'fp32': 'f32', 'bf16x3': 'bf16x3 (fp32-class)',
+                      'bf16': 'bf16'}[args.math],
+            'data': 'synthetic',
+            'config': workload_config(args),
+            'edges_per_s': total_edges / (ms_total * 1e-3),
+            'clocks': clocks,
+            'e2e': {'value': total_complexes / (ms_e2e * 1e-3), 'unit': UNIT,
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': int(launches),
+            'roofline': roofline,
+            'cpu_baseline': cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

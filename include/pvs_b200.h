@@ -1,0 +1,259 @@
+/*
+ * pvs_b200.h -- C ABI of the B200-native PointVS EGNN hot path.
+ *
+ * The reference (jscant/PointVS) is pure Python/PyTorch and has no FFI of its
+ * own; each entry point below names the reference function it replaces
+ * (file:line under /root/reference).  The host-side mirror of the reference's
+ * Python API (pointvs_b200/*.py) binds these with ctypes; INTEGRATION.md shows
+ * the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns and allocates all outputs and workspaces;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as
+ *     void*), never synchronises and keeps no mutable global state;
+ *   - the return value is a pvs_status (0 = ok).  Argument errors are
+ *     reported before anything is launched; launch errors come back as
+ *     PVS_ERR_CUDA (pvs_last_cuda_error() has the cudaError_t);
+ *   - feature matrices are row-major fp32; parameters are passed in the
+ *     layout nn.Linear stores them ([out][in], row-major), so a PyTorch
+ *     state_dict is usable without re-packing.
+ */
+#ifndef PVS_B200_H
+#define PVS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVS_VERSION 100 /* 0.1.0 */
+
+typedef enum pvs_status {
+    PVS_OK = 0,
+    PVS_ERR_INVALID_ARG = 1,   /* null pointer, negative size, bad enum */
+    PVS_ERR_UNSUPPORTED_K = 2, /* hidden width outside 1..PVS_MAX_K */
+    PVS_ERR_TOO_LARGE = 3,     /* one complex does not fit the cell-list smem */
+    PVS_ERR_CUDA = 4,          /* a CUDA call failed: pvs_last_cuda_error() */
+    PVS_ERR_WORKSPACE = 5      /* workspace smaller than *_workspace_bytes */
+} pvs_status;
+
+#define PVS_MAX_K 64          /* widest hidden size (--channels) supported */
+#define PVS_MAX_EDGE_CLASSES 8
+#define PVS_TILE_EDGES 128    /* edges per work tile (one tcgen05 M=128 tile) */
+#define PVS_TILE_NODES 128    /* node cap per work tile */
+
+/* capability bits returned by pvs_capabilities() */
+#define PVS_CAP_FWD_FP32 1u      /* FFMA forward                              */
+#define PVS_CAP_FWD_TCGEN05 2u   /* tcgen05 edge-MLP tiles (bf16x3 / bf16)    */
+#define PVS_CAP_BWD_FP32 4u      /* backward kernels                          */
+
+/* pvs_layer_config.flags -- EGNNLayer.__init__ (egnn_satorras.py:26-46) */
+#define PVS_F_RESIDUAL 0x001u
+#define PVS_F_EDGE_RESIDUAL 0x002u
+#define PVS_F_EDGE_ATTENTION 0x004u
+#define PVS_F_NORMALIZE 0x008u
+#define PVS_F_TANH 0x010u
+#define PVS_F_GRAPHNORM 0x020u
+#define PVS_F_UPDATE_COORDS 0x040u
+#define PVS_F_PERM_INVARIANT 0x080u
+#define PVS_F_NODE_ATTENTION 0x100u
+#define PVS_F_GATED_RESIDUAL 0x200u
+#define PVS_F_REZERO 0x400u
+#define PVS_F_SOFTMAX_ATTENTION 0x800u
+
+/* attention / head activations (egnn_satorras.py:66-73) */
+typedef enum pvs_act {
+    PVS_ACT_NONE = 0,
+    PVS_ACT_SIGMOID = 1,
+    PVS_ACT_TANH = 2,
+    PVS_ACT_RELU = 3,
+    PVS_ACT_SILU = 4,
+    PVS_ACT_SOFTPLUS = 5
+} pvs_act;
+
+/* arithmetic used for the two per-edge 64x64 contractions */
+typedef enum pvs_math {
+    PVS_MATH_FP32 = 0,   /* FFMA, fp32 throughout                            */
+    PVS_MATH_BF16X3 = 1, /* tcgen05, error-compensated bf16 split (fp32-class) */
+    PVS_MATH_BF16 = 2    /* tcgen05, single bf16 pass (fast mode)            */
+} pvs_math;
+
+/* Destination-sorted CSR of one packed batch plus its work-tile partition. */
+typedef struct pvs_graph {
+    int32_t n_nodes;
+    int32_t n_edges;
+    const int32_t *row_ptr;  /* [n_nodes+1] edges of node i (the RECEIVER,
+                                edge_index[0]) are [row_ptr[i], row_ptr[i+1]) */
+    const int32_t *col;      /* [n_edges] neighbour j (edge_index[1])         */
+    const uint8_t *attr;     /* [n_edges] edge class (argmax of the one-hot
+                                edge_attr) or NULL when edges_in_d == 0       */
+    const int32_t *tile_ptr; /* [n_tiles+1] node boundaries of work tiles     */
+    const int32_t *n_tiles;  /* device scalar written by pvs_build_tiles      */
+    int32_t n_tiles_cap;     /* capacity of tile_ptr minus one                */
+} pvs_graph;
+
+typedef struct pvs_layer_config {
+    int32_t k;              /* hidden_nf == input_nf == output_nf            */
+    int32_t n_edge_classes; /* edges_in_d (3 in every PointVS model, or 0)   */
+    uint32_t flags;         /* PVS_F_*                                        */
+    int32_t att_act;        /* pvs_act for att_mlp / node_att_mlp            */
+    int32_t math;           /* pvs_math                                       */
+    int32_t stages;         /* PVS_STAGE_* mask; 0 = all.  Lets a profiler put
+                               events between the three launches of a layer;
+                               the workspace carries state between calls.     */
+} pvs_layer_config;
+
+#define PVS_STAGE_NODE_PRE 1 /* P = h W1a^T + b1, Q = h W1b^T                 */
+#define PVS_STAGE_EDGE 2     /* edge MLP, attention, coordinate + message reduce */
+#define PVS_STAGE_NODE 4     /* node MLP, node attention, residual            */
+#define PVS_STAGE_ALL 7
+
+/* Parameters of one EGNNLayer in state_dict layout (egnn_satorras.py:76-121).
+ * Unused blocks are NULL. */
+typedef struct pvs_layer_params {
+    const float *edge_w1;  /* edge_mlp.0.weight [k][in_e], in_e =
+                              (perm_invariant ? k : 2k) + 1 + n_edge_classes */
+    const float *edge_b1;  /* edge_mlp.0.bias   [k]     */
+    const float *edge_w2;  /* edge_mlp.2.weight [k][k]  */
+    const float *edge_b2;  /* edge_mlp.2.bias   [k]     */
+    const float *coord_w1; /* coord_mlp.0.weight [k][k] */
+    const float *coord_b1; /* coord_mlp.0.bias   [k]    */
+    const float *coord_w2; /* coord_mlp.2.weight [1][k] (no bias) */
+    const float *att_w;    /* att_mlp.0.weight   [1][k] */
+    const float *att_b;    /* att_mlp.0.bias     [1]    */
+    const float *node_w1;  /* node_mlp.0.weight  [k][2k] */
+    const float *node_b1;  /* node_mlp.0.bias    [k]    */
+    const float *gn_weight;     /* node_mlp.1.weight     [k] (GraphNorm)     */
+    const float *gn_bias;       /* node_mlp.1.bias       [k]                 */
+    const float *gn_mean_scale; /* node_mlp.1.mean_scale [k]                 */
+    const float *node_w2;  /* node_mlp.3.weight  [k][k] */
+    const float *node_b2;  /* node_mlp.3.bias    [k]    */
+    const float *natt_w;   /* node_att_mlp.0.weight [1][k] */
+    const float *natt_b;   /* node_att_mlp.0.bias   [1]    */
+    const float *edge_gate; /* edge_gate_parameter [1] */
+    const float *node_gate; /* node_gate_parameter [1] */
+} pvs_layer_params;
+
+/* Gradients of pvs_layer_params, same shapes; accumulated into (+=). */
+typedef struct pvs_layer_grads {
+    float *edge_w1, *edge_b1, *edge_w2, *edge_b2;
+    float *coord_w1, *coord_b1, *coord_w2;
+    float *att_w, *att_b;
+    float *node_w1, *node_b1, *node_w2, *node_b2;
+    float *natt_w, *natt_b;
+    float *edge_gate, *node_gate;
+} pvs_layer_grads;
+
+int pvs_version(void);
+uint32_t pvs_capabilities(void);
+const char *pvs_status_string(int status);
+int pvs_last_cuda_error(void);
+/* kernels launched by this library on the calling thread since load */
+int64_t pvs_launch_count(void);
+
+/* ---- K1: radius graph --------------------------------------------------
+ * Replaces generate_edges (point_vs/preprocessing/preprocessing.py:68-155)
+ * for a packed batch of complexes.  Per-complex cell list; fp64 distances
+ * sqrt((dx*dx+dy*dy)+dz*dz) without FMA contraction, tests d < radius and
+ * d > 1e-7 exactly as :108-121.  Output is the destination-sorted CSR of
+ * the reference edge list: within a row, the inter-molecular edges in
+ * ascending col, then the intra list in ascending col (the stable sort by
+ * row of the reference's [inter | intra] output).
+ *
+ * Two passes so the caller can size col/attr:
+ *   count: deg[N] = edges per node, n_inter[N] = of which inter edges,
+ *          row_ptr[N+1] = exclusive scan of deg (row_ptr[N] = total edges).
+ *   fill:  col / attr, and optionally ref_pos[E] = index of each CSR edge in
+ *          the reference's (PyG-collated) edge order.
+ * coords: fp64 [N][3]; bp: int32 [N] (0 ligand, 1 receptor; :106);
+ * complex_ptr: int32 [B+1] node offsets.  scratch: pvs_scan_scratch_bytes(N). */
+int pvs_radius_graph_count(const double *coords, const int32_t *bp,
+                           const int32_t *complex_ptr, int32_t n_complexes,
+                           int32_t n_nodes, int32_t max_complex_nodes,
+                           double inter_radius, double intra_radius,
+                           int32_t *deg, int32_t *n_inter, int32_t *row_ptr,
+                           void *scratch, void *stream);
+int pvs_radius_graph_fill(const double *coords, const int32_t *bp,
+                          const int32_t *complex_ptr, int32_t n_complexes,
+                          int32_t n_nodes, int32_t max_complex_nodes,
+                          double inter_radius, double intra_radius,
+                          const int32_t *n_inter, const int32_t *row_ptr,
+                          int32_t *col, uint8_t *attr, int32_t *ref_pos,
+                          void *stream);
+/* Connected-component mask for `prune` (preprocessing.py:144-153): keep[i]=1
+ * iff node i is reachable from the row of its complex's first inter edge
+ * (or every node of a complex that has no inter edge). */
+int pvs_prune_mask(const int32_t *row_ptr, const int32_t *col,
+                   const int32_t *n_inter, const int32_t *complex_ptr,
+                   int32_t n_complexes, int32_t n_nodes, uint8_t *keep,
+                   void *stream);
+
+int64_t pvs_scan_scratch_bytes(int32_t n);
+/* row_ptr[0..n] = exclusive scan of deg[0..n-1] */
+int pvs_exclusive_scan(const int32_t *deg, int32_t n, int32_t *row_ptr,
+                       void *scratch, void *stream);
+
+/* Greedy partition of the node range into work tiles: consecutive nodes
+ * whose edges total <= PVS_TILE_EDGES (a node with more edges gets a tile of
+ * its own) and at most PVS_TILE_NODES nodes.  tile_ptr needs
+ * pvs_tiles_capacity(n_nodes, n_edges)+1 ints; scratch the same amount of
+ * ints again + pvs_scan_scratch_bytes of that. */
+int32_t pvs_tiles_capacity(int32_t n_nodes, int32_t n_edges);
+int64_t pvs_tiles_scratch_bytes(int32_t n_nodes);
+int pvs_build_tiles(const int32_t *row_ptr, int32_t n_nodes, int32_t *tile_ptr,
+                    int32_t *n_tiles, void *scratch, void *stream);
+
+/* Arbitrary-order edge_index (PyG [2][E] int64, edge_attr one-hot int64
+ * [E][n_classes] or NULL) -> destination-sorted CSR, stable in the caller's
+ * order.  perm[p] = caller's edge index stored at CSR slot p.  For callers
+ * that bring their own graph (attribution, reference data loaders;
+ * pnn_geometric_base.py:55-58).  bad_index (device int) is set non-zero if
+ * any index is outside [0, n_nodes).  scratch: n_nodes ints +
+ * pvs_scan_scratch_bytes(n_nodes). */
+int pvs_edge_index_to_csr(const int64_t *edge_index, int64_t n_edges,
+                          const int64_t *edge_attr_onehot, int32_t n_classes,
+                          int32_t n_nodes, int32_t *deg, int32_t *row_ptr,
+                          int32_t *col, uint8_t *attr, int32_t *perm,
+                          int32_t *bad_index, void *scratch, void *stream);
+
+/* batch [N] int64 non-decreasing -> graph_ptr [B+1]
+ * (pnn_geometric_base.py:27 derives B = max(batch)+1) */
+int pvs_batch_to_ptr(const int64_t *batch, int32_t n_nodes, int32_t n_graphs,
+                     int32_t *graph_ptr, void *stream);
+
+/* ---- dense helpers ------------------------------------------------------
+ * out[r][0..ko) = act(in[r][0..ki) . W[ko][ki]^T + b).  Embedding
+ * (PygLinearPass, pnn_geometric_base.py:83-94), heads
+ * (egnn_satorras.py:304-317, egnn_multitask.py:141-146).  ki, ko <= 128. */
+int pvs_linear_fwd(const float *in, int32_t ld_in, int32_t rows, int32_t ki,
+                   const float *w, int32_t ld_w, const float *b, int32_t ko,
+                   int32_t act, float *out, int32_t ld_out, void *stream);
+/* global_mean_pool (pnn_geometric_base.py:29-33): pooled[b] = mean of h rows
+ * [graph_ptr[b], graph_ptr[b+1]) (0 for an empty graph). */
+int pvs_mean_pool_fwd(const float *h, const int32_t *graph_ptr,
+                      int32_t n_graphs, int32_t k, float *pooled, void *stream);
+
+/* ---- K2: one EGNN layer, forward ----------------------------------------
+ * Replaces EGNNLayer.forward (egnn_satorras.py:189-206 and :123-187).
+ *   h_in [N][k], x_in [N][3] -> h_out [N][k], x_out [N][3] (x_out may not
+ *   alias x_in; the Python wrapper copies back to keep the reference's
+ *   in-place `coord += agg`, :174).
+ *   m_prev [E][k] (CSR order) or NULL: previous layer's messages, read only
+ *   with PVS_F_EDGE_RESIDUAL.  m_out [E][k], att_out [E], natt_out [N] are
+ *   optional outputs (NULL to skip) in CSR order.
+ * workspace: pvs_egnn_layer_workspace_bytes(). */
+int64_t pvs_egnn_layer_workspace_bytes(int32_t n_nodes, int32_t n_edges,
+                                       const pvs_layer_config *cfg);
+int pvs_egnn_layer_fwd(const pvs_graph *graph, const pvs_layer_config *cfg,
+                       const pvs_layer_params *params, const float *h_in,
+                       const float *x_in, const float *m_prev, float *h_out,
+                       float *x_out, float *m_out, float *att_out,
+                       float *natt_out, void *workspace,
+                       int64_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVS_B200_H */

@@ -1,0 +1,123 @@
+"""ctypes binding of include/pvs_b200.h.
+
+The CUDA library is the product path: if it is missing this module raises on
+first use (there is no CPU or PyTorch fallback).
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, '_C', 'libpvs_b200.so')
+
+# flags / enums (mirror include/pvs_b200.h)
+F_RESIDUAL = 0x001
+F_EDGE_RESIDUAL = 0x002
+F_EDGE_ATTENTION = 0x004
+F_NORMALIZE = 0x008
+F_TANH = 0x010
+F_GRAPHNORM = 0x020
+F_UPDATE_COORDS = 0x040
+F_PERM_INVARIANT = 0x080
+F_NODE_ATTENTION = 0x100
+F_GATED_RESIDUAL = 0x200
+F_REZERO = 0x400
+F_SOFTMAX_ATTENTION = 0x800
+
+ACT = {'none': 0, 'sigmoid': 1, 'tanh': 2, 'relu': 3, 'silu': 4, 'softplus': 5}
+MATH = {'fp32': 0, 'bf16x3': 1, 'bf16': 2}
+MAX_K = 64
+TILE_EDGES = 128
+
+CAP_FWD_FP32 = 1
+CAP_FWD_TCGEN05 = 2
+CAP_BWD_FP32 = 4
+
+_fp = C.c_void_p
+
+
+class Graph(C.Structure):
+    _fields_ = [('n_nodes', C.c_int32), ('n_edges', C.c_int32),
+                ('row_ptr', _fp), ('col', _fp), ('attr', _fp),
+                ('tile_ptr', _fp), ('n_tiles', _fp), ('n_tiles_cap', C.c_int32)]
+
+
+class LayerConfig(C.Structure):
+    _fields_ = [('k', C.c_int32), ('n_edge_classes', C.c_int32),
+                ('flags', C.c_uint32), ('att_act', C.c_int32),
+                ('math', C.c_int32), ('stages', C.c_int32)]
+
+
+PARAM_FIELDS = ('edge_w1', 'edge_b1', 'edge_w2', 'edge_b2', 'coord_w1',
+                'coord_b1', 'coord_w2', 'att_w', 'att_b', 'node_w1', 'node_b1',
+                'gn_weight', 'gn_bias', 'gn_mean_scale', 'node_w2', 'node_b2',
+                'natt_w', 'natt_b', 'edge_gate', 'node_gate')
+GRAD_FIELDS = ('edge_w1', 'edge_b1', 'edge_w2', 'edge_b2', 'coord_w1',
+               'coord_b1', 'coord_w2', 'att_w', 'att_b', 'node_w1', 'node_b1',
+               'node_w2', 'node_b2', 'natt_w', 'natt_b', 'edge_gate',
+               'node_gate')
+
+
+class LayerParams(C.Structure):
+    _fields_ = [(n, _fp) for n in PARAM_FIELDS]
+
+
+class LayerGrads(C.Structure):
+    _fields_ = [(n, _fp) for n in GRAD_FIELDS]
+
+
+class PvsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; raise loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PvsError(
+                f'{LIB_PATH} not found: build it with '
+                '`python -m pointvs_b200.build` (or __graft_entry__.build()). '
+                'There is no CPU fallback.')
+        handle = C.CDLL(LIB_PATH)
+        handle.pvs_status_string.restype = C.c_char_p
+        handle.pvs_capabilities.restype = C.c_uint32
+        handle.pvs_launch_count.restype = C.c_int64
+        for name in ('pvs_scan_scratch_bytes', 'pvs_tiles_scratch_bytes',
+                     'pvs_egnn_layer_workspace_bytes',
+                     'pvs_egnn_layer_bwd_workspace_bytes'):
+            if hasattr(handle, name):
+                getattr(handle, name).restype = C.c_int64
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        h = lib()
+        msg = h.pvs_status_string(int(rc)).decode()
+        if rc == 4:
+            msg += f' [cudaError {h.pvs_last_cuda_error()}]'
+        raise PvsError(f'{what or "pvs call"} failed: {msg} (status {rc})')
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise PvsError('pointvs_b200 kernels need CUDA tensors; there is '
+                           'no CPU fallback')

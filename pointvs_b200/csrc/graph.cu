@@ -1,0 +1,751 @@
+// K1 and friends: radius-graph construction (per-complex cell list -> dst-sorted
+// CSR), work-tile partition, caller-order edge_index -> CSR, CSC transpose,
+// prune mask.  All integer / fp64-compare work: bit-exact by construction.
+//
+// Replaces /root/reference/point_vs/preprocessing/preprocessing.py:68-155
+// (generate_edges) and the PyG collate offsets (data_loaders.py:517-520).
+#include "pvs_common.cuh"
+
+namespace pvs {
+
+// ---------------------------------------------------------------------------
+// exclusive scan of int32 (three small launches; n is a node count)
+// ---------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+// exclusive scan of one value per thread across the block; returns prefix,
+// writes the block total to *total (all threads see it after the call).
+__device__ int block_scan_excl(int v, int *total, int *warp_buf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+    int incl = warp_scan_incl(v, lane);
+    if (lane == 31) warp_buf[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < nwarps ? warp_buf[lane] : 0;
+        int wi = warp_scan_incl(w, lane);
+        warp_buf[lane] = wi - w;
+        if (lane == 31) warp_buf[32] = wi;
+    }
+    __syncthreads();
+    int prefix = warp_buf[warp] + incl - v;
+    *total = warp_buf[32];
+    __syncthreads();
+    return prefix;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_local_kernel(const int32_t *__restrict__ in, int n,
+                  int32_t *__restrict__ out, int32_t *__restrict__ block_sums) {
+    __shared__ int warp_buf[33];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0;
+        s += v[i];
+    }
+    int total;
+    int prefix = block_scan_excl(s, &total, warp_buf);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = prefix;
+        prefix += v[i];
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_sums_kernel(int32_t *__restrict__ block_sums, int nb,
+                 int32_t *__restrict__ total_out) {
+    __shared__ int warp_buf[33];
+    int carry = 0;
+    for (int b0 = 0; b0 < nb; b0 += SCAN_THREADS) {
+        int i = b0 + threadIdx.x;
+        int v = i < nb ? block_sums[i] : 0;
+        int total;
+        int prefix = block_scan_excl(v, &total, warp_buf);
+        if (i < nb) block_sums[i] = carry + prefix;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_add_kernel(int32_t *__restrict__ out, int n,
+                const int32_t *__restrict__ block_sums) {
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    const int add = block_sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (base + i < n) out[base + i] += add;
+}
+
+static int exclusive_scan(const int32_t *deg, int n, int32_t *row_ptr,
+                          void *scratch, cudaStream_t st) {
+    if (n == 0) {
+        return cuda_call(cudaMemsetAsync(row_ptr, 0, sizeof(int32_t), st));
+    }
+    int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    int32_t *sums = (int32_t *)scratch;
+    scan_local_kernel<<<nb, SCAN_THREADS, 0, st>>>(deg, n, row_ptr, sums);
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(sums, nb, row_ptr + n);
+    if (nb > 1) scan_add_kernel<<<nb, SCAN_THREADS, 0, st>>>(row_ptr, n, sums);
+    return check_launch(nb > 1 ? 3 : 2);
+}
+
+// in-place exclusive scan of a shared-memory array of any length
+__device__ int smem_scan_excl(int *data, int n, int *warp_buf) {
+    const int T = blockDim.x;
+    const int per = (n + T - 1) / T;
+    const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += data[i];
+    int total;
+    int prefix = block_scan_excl(s, &total, warp_buf);
+    for (int i = lo; i < hi; ++i) {
+        int v = data[i];
+        data[i] = prefix;
+        prefix += v;
+    }
+    __syncthreads();
+    return total;
+}
+
+// ---------------------------------------------------------------------------
+// K1: radius graph.  One CTA per complex.
+// ---------------------------------------------------------------------------
+constexpr int RG_THREADS = 256;
+constexpr int RG_WARPS = RG_THREADS / 32;
+constexpr int RG_MAX_DIM = 16;
+constexpr int RG_MAX_CELLS = RG_MAX_DIM * RG_MAX_DIM * RG_MAX_DIM;
+
+struct RgSmem {
+    int cell_start[RG_MAX_CELLS + 1];
+    int cell_fill[RG_MAX_CELLS];
+    double red[6][RG_WARPS];
+    double box[6];
+    int warp_buf[33];
+    int misc[4];
+};
+
+static size_t rg_smem_bytes(int max_n, bool with_prefix) {
+    size_t words = (size_t)(max_n + 31) / 32;
+    size_t b = sizeof(RgSmem);
+    b += (size_t)max_n * sizeof(int);                 // sorted_idx
+    b += (size_t)RG_WARPS * 2 * words * sizeof(int);  // per-warp bit masks
+    if (with_prefix) b += (size_t)max_n * sizeof(int);
+    return b;
+}
+
+__device__ __forceinline__ int cell_coord(double v, double lo, double cs, int dim) {
+    int c = (int)floor(__ddiv_rn(__dsub_rn(v, lo), cs));
+    return max(0, min(dim - 1, c));
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(RG_THREADS)
+radius_graph_kernel(const double *__restrict__ coords,
+                    const int32_t *__restrict__ bp,
+                    const int32_t *__restrict__ complex_ptr, double r_inter,
+                    double r_intra, int32_t *__restrict__ deg,
+                    int32_t *__restrict__ n_inter_out,
+                    const int32_t *__restrict__ n_inter_in,
+                    const int32_t *__restrict__ row_ptr,
+                    int32_t *__restrict__ col, uint8_t *__restrict__ attr,
+                    int32_t *__restrict__ ref_pos, int max_n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RgSmem &S = *reinterpret_cast<RgSmem *>(smem_raw);
+    const int n0 = complex_ptr[blockIdx.x];
+    const int n = complex_ptr[blockIdx.x + 1] - n0;
+    if (n <= 0 || n > max_n) return;   // host sizes smem from max_n
+    const int words = (max_n + 31) / 32;
+    int *sorted_idx = reinterpret_cast<int *>(smem_raw + sizeof(RgSmem));
+    unsigned *masks = reinterpret_cast<unsigned *>(sorted_idx + max_n);
+    int *prefix_inter = reinterpret_cast<int *>(masks + (size_t)RG_WARPS * 2 * words);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *cx = coords + 3 * (size_t)n0;
+    const int32_t *cbp = bp + n0;
+
+    // ---- bounding box ----
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = tid; i < n; i += RG_THREADS) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double v = cx[3 * i + a];
+            lo[a] = fmin(lo[a], v);
+            hi[a] = fmax(hi[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) {
+            S.red[a][warp] = lo[a];
+            S.red[3 + a][warp] = hi[a];
+        }
+    }
+    __syncthreads();
+    if (tid < 3) {
+        double l = S.red[tid][0], h = S.red[3 + tid][0];
+        for (int w = 1; w < RG_WARPS; ++w) {
+            l = fmin(l, S.red[tid][w]);
+            h = fmax(h, S.red[3 + tid][w]);
+        }
+        S.box[tid] = l;
+        S.box[3 + tid] = h;
+    }
+    __syncthreads();
+    // cell edge >= r_max * (1 + 1e-6): two atoms closer than r_max are at most
+    // one cell apart on every axis even after rounding of the cell coordinate.
+    const double r_max = fmax(r_inter, r_intra);
+    const double cs0 = fmax(r_max * (1.0 + 1e-6), 1e-9);
+    int dim[3];
+    double cs[3], blo[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        blo[a] = S.box[a];
+        double ext = S.box[3 + a] - S.box[a];
+        double q = ext / cs0;
+        if (q + 1.0 > (double)RG_MAX_DIM) {
+            dim[a] = RG_MAX_DIM;
+            cs[a] = ext / RG_MAX_DIM * (1.0 + 1e-6);
+        } else {
+            dim[a] = (int)q + 1;
+            cs[a] = cs0;
+        }
+    }
+    const int ncell = dim[0] * dim[1] * dim[2];
+
+    // ---- counting sort of atoms by cell (x fastest) ----
+    for (int c = tid; c < ncell; c += RG_THREADS) {
+        S.cell_start[c] = 0;
+        S.cell_fill[c] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += RG_THREADS) {
+        int c = cell_coord(cx[3 * i], blo[0], cs[0], dim[0]) +
+                dim[0] * (cell_coord(cx[3 * i + 1], blo[1], cs[1], dim[1]) +
+                          dim[1] * cell_coord(cx[3 * i + 2], blo[2], cs[2], dim[2]));
+        atomicAdd(&S.cell_start[c], 1);
+    }
+    __syncthreads();
+    int total = smem_scan_excl(S.cell_start, ncell, S.warp_buf);
+    if (tid == 0) S.cell_start[ncell] = total;
+    __syncthreads();
+    for (int i = tid; i < n; i += RG_THREADS) {
+        int c = cell_coord(cx[3 * i], blo[0], cs[0], dim[0]) +
+                dim[0] * (cell_coord(cx[3 * i + 1], blo[1], cs[1], dim[1]) +
+                          dim[1] * cell_coord(cx[3 * i + 2], blo[2], cs[2], dim[2]));
+        int p = atomicAdd(&S.cell_fill[c], 1);
+        sorted_idx[S.cell_start[c] + p] = i;
+    }
+    int e_base_c = 0, total_inter_c = 0;
+    if (FILL && ref_pos != nullptr) {
+        for (int i = tid; i < n; i += RG_THREADS) prefix_inter[i] = n_inter_in[n0 + i];
+        __syncthreads();
+        total_inter_c = smem_scan_excl(prefix_inter, n, S.warp_buf);
+        e_base_c = row_ptr[n0];
+    }
+    __syncthreads();
+
+    // ---- one warp per destination node ----
+    unsigned *m_inter = masks + (size_t)warp * 2 * words;
+    unsigned *m_intra = m_inter + words;
+    const int nw = (n + 31) / 32;
+    for (int i = warp; i < n; i += RG_WARPS) {
+        for (int w = lane; w < nw; w += 32) {
+            m_inter[w] = 0u;
+            m_intra[w] = 0u;
+        }
+        __syncwarp();
+        const double xi = cx[3 * i], yi = cx[3 * i + 1], zi = cx[3 * i + 2];
+        const int bi = cbp[i];
+        const int ci0 = cell_coord(xi, blo[0], cs[0], dim[0]);
+        const int ci1 = cell_coord(yi, blo[1], cs[1], dim[1]);
+        const int ci2 = cell_coord(zi, blo[2], cs[2], dim[2]);
+        const int x_lo = max(ci0 - 1, 0), x_hi = min(ci0 + 1, dim[0] - 1);
+        for (int dz = -1; dz <= 1; ++dz) {
+            int c2 = ci2 + dz;
+            if (c2 < 0 || c2 >= dim[2]) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                int c1 = ci1 + dy;
+                if (c1 < 0 || c1 >= dim[1]) continue;
+                int cb = dim[0] * (c1 + dim[1] * c2);
+                int p_end = S.cell_start[cb + x_hi + 1];
+                for (int p = S.cell_start[cb + x_lo] + lane; p < p_end; p += 32) {
+                    int j = sorted_idx[p];
+                    // scipy cdist (preprocessing.py:108):
+                    // sqrt((dx*dx + dy*dy) + dz*dz), no FMA contraction
+                    double ddx = __dsub_rn(xi, cx[3 * j]);
+                    double ddy = __dsub_rn(yi, cx[3 * j + 1]);
+                    double ddz = __dsub_rn(zi, cx[3 * j + 2]);
+                    double d = __dsqrt_rn(__dadd_rn(
+                        __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)),
+                        __dmul_rn(ddz, ddz)));
+                    bool pos = d > 1e-7;
+                    unsigned bit = 1u << (j & 31);
+                    if (pos && d < r_inter && cbp[j] != bi)
+                        atomicOr(&m_inter[j >> 5], bit);   // :110-117
+                    if (pos && d < r_intra)
+                        atomicOr(&m_intra[j >> 5], bit);   // :119-121
+                }
+            }
+        }
+        __syncwarp();
+        if (!FILL) {
+            int ci = 0, ca = 0;
+            for (int w = lane; w < nw; w += 32) {
+                ci += __popc(m_inter[w]);
+                ca += __popc(m_intra[w]);
+            }
+            ci = warp_sum_int(ci);
+            ca = warp_sum_int(ca);
+            if (lane == 0) {
+                deg[n0 + i] = ci + ca;
+                n_inter_out[n0 + i] = ci;
+            }
+        } else {
+            const int e_row = row_ptr[n0 + i];
+            int run = e_row;
+            int pi = 0;
+            if (ref_pos != nullptr) pi = prefix_inter[i];
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const unsigned *mk = pass == 0 ? m_inter : m_intra;
+                const int pass_base = run;
+                for (int w0 = 0; w0 < nw; w0 += 32) {
+                    int w = w0 + lane;
+                    unsigned bits = w < nw ? mk[w] : 0u;
+                    int cnt = __popc(bits);
+                    int incl = warp_scan_incl(cnt, lane);
+                    int off = run + incl - cnt;
+                    while (bits) {
+                        int b = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        int j = w * 32 + b;
+                        int bj = cbp[j];
+                        col[off] = n0 + j;
+                        uint8_t a;
+                        if (pass == 0)   // :129-133
+                            a = ((bi == 0 && bj == 1) || (bi == 1 && bj == 0)) ? 1 : 0;
+                        else             // :135
+                            a = (bi == 1 && bj == 1) ? 2 : 0;
+                        attr[off] = a;
+                        if (ref_pos != nullptr) {
+                            int q = off - pass_base;
+                            int local_row = e_row - e_base_c;   // edges before node i
+                            ref_pos[off] = pass == 0
+                                ? e_base_c + pi + q
+                                : e_base_c + total_inter_c + (local_row - pi) + q;
+                        }
+                        ++off;
+                    }
+                    run += __shfl_sync(0xffffffffu, incl, 31);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// prune mask: component reachable from the first inter edge's row
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prune_mask_kernel(const int32_t *__restrict__ row_ptr,
+                  const int32_t *__restrict__ col,
+                  const int32_t *__restrict__ n_inter,
+                  const int32_t *__restrict__ complex_ptr,
+                  uint8_t *__restrict__ keep) {
+    __shared__ int start;
+    const int n0 = complex_ptr[blockIdx.x];
+    const int n = complex_ptr[blockIdx.x + 1] - n0;
+    if (n <= 0) return;
+    if (threadIdx.x == 0) start = 0x7fffffff;
+    __syncthreads();
+    int first = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (n_inter[n0 + i] > 0) { first = i; break; }
+    if (first != 0x7fffffff) atomicMin(&start, first);
+    __syncthreads();
+    const int s = start;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        keep[n0 + i] = (s == 0x7fffffff || i == s) ? 1 : 0;
+    if (s == 0x7fffffff) return;   // no inter edge: reference keeps everything
+    __syncthreads();
+    for (;;) {
+        int changed = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            if (keep[n0 + i]) continue;
+            for (int e = row_ptr[n0 + i]; e < row_ptr[n0 + i + 1]; ++e) {
+                if (keep[col[e]]) {
+                    keep[n0 + i] = 1;
+                    changed = 1;
+                    break;
+                }
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// work tiles
+// ---------------------------------------------------------------------------
+constexpr int TILE_CHUNK = 1024;
+
+__global__ void __launch_bounds__(256)
+tiles_walk_kernel(const int32_t *__restrict__ row_ptr, int n_nodes,
+                  int32_t *__restrict__ tmp, int32_t *__restrict__ chunk_count) {
+    __shared__ int rp[TILE_CHUNK + 1];
+    const int c0 = blockIdx.x * TILE_CHUNK;
+    const int cn = min(TILE_CHUNK, n_nodes - c0);
+    for (int i = threadIdx.x; i <= cn; i += blockDim.x) rp[i] = row_ptr[c0 + i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int count = 0;
+        int start = 0;
+        while (start < cn) {
+            tmp[c0 + count++] = c0 + start;
+            int end = start + 1;   // a tile always holds at least one node
+            while (end < cn && end - start < PVS_TILE_NODES &&
+                   rp[end + 1] - rp[start] <= PVS_TILE_EDGES)
+                ++end;
+            start = end;
+        }
+        chunk_count[blockIdx.x] = count;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tiles_compact_kernel(const int32_t *__restrict__ tmp,
+                     const int32_t *__restrict__ chunk_count,
+                     const int32_t *__restrict__ chunk_off, int n_nodes,
+                     int n_chunks, int32_t *__restrict__ tile_ptr,
+                     int32_t *__restrict__ n_tiles) {
+    const int c0 = blockIdx.x * TILE_CHUNK;
+    const int cnt = chunk_count[blockIdx.x];
+    const int off = chunk_off[blockIdx.x];
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) tile_ptr[off + i] = tmp[c0 + i];
+    if (blockIdx.x == n_chunks - 1 && threadIdx.x == 0) {
+        tile_ptr[off + cnt] = n_nodes;
+        *n_tiles = off + cnt;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// group edges by an integer key (row for CSR, col for CSC), stable
+// ---------------------------------------------------------------------------
+template <typename KeyT>
+__global__ void key_count_kernel(const KeyT *__restrict__ keys, int64_t n_edges,
+                                 int n_nodes, int32_t *__restrict__ deg,
+                                 int32_t *__restrict__ bad) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    int64_t k = (int64_t)keys[e];
+    if (k < 0 || k >= n_nodes) {
+        if (bad) *bad = 1;
+        return;
+    }
+    atomicAdd(&deg[k], 1);
+}
+
+template <typename KeyT>
+__global__ void key_place_kernel(const KeyT *__restrict__ keys, int64_t n_edges,
+                                 int n_nodes, const int32_t *__restrict__ ptr,
+                                 int32_t *__restrict__ cursor,
+                                 int32_t *__restrict__ perm) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    int64_t k = (int64_t)keys[e];
+    if (k < 0 || k >= n_nodes) return;
+    int p = atomicAdd(&cursor[k], 1);
+    perm[ptr[k] + p] = (int32_t)e;
+}
+
+// restore the caller's order inside every group (=> stable sort by key)
+__global__ void segment_sort_kernel(const int32_t *__restrict__ ptr, int n_nodes,
+                                    int32_t *__restrict__ perm) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const int lo = ptr[i], hi = ptr[i + 1];
+    for (int a = lo + 1; a < hi; ++a) {
+        int v = perm[a];
+        int b = a - 1;
+        while (b >= lo && perm[b] > v) {
+            perm[b + 1] = perm[b];
+            --b;
+        }
+        perm[b + 1] = v;
+    }
+}
+
+__global__ void csr_gather_kernel(const int64_t *__restrict__ edge_col,
+                                  const int64_t *__restrict__ onehot,
+                                  int n_classes, const int32_t *__restrict__ perm,
+                                  int64_t n_edges, int n_nodes,
+                                  int32_t *__restrict__ col,
+                                  uint8_t *__restrict__ attr,
+                                  int32_t *__restrict__ bad) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_edges) return;
+    const int e = perm[p];
+    int64_t c = edge_col[e];
+    if (c < 0 || c >= n_nodes) {
+        if (bad) *bad = 1;
+        c = 0;
+    }
+    col[p] = (int32_t)c;
+    if (attr != nullptr) {
+        int cls = 0;
+        if (onehot != nullptr)
+            for (int d = 0; d < n_classes; ++d)
+                if (onehot[(int64_t)e * n_classes + d] != 0) cls = d;
+        attr[p] = (uint8_t)cls;
+    }
+}
+
+__global__ void batch_to_ptr_kernel(const int64_t *__restrict__ batch, int n_nodes,
+                                    int n_graphs, int32_t *__restrict__ ptr) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_nodes) return;
+    int64_t prev = i == 0 ? -1 : batch[i - 1];
+    int64_t cur = i == n_nodes ? (int64_t)n_graphs : batch[i];
+    if (cur > n_graphs) cur = n_graphs;
+    for (int64_t g = prev + 1; g <= cur; ++g)
+        if (g >= 0 && g <= n_graphs) ptr[g] = i;
+}
+
+}  // namespace pvs
+
+using namespace pvs;
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int64_t pvs_scan_scratch_bytes(int32_t n) {
+    int64_t nb = ((int64_t)n + SCAN_TILE - 1) / SCAN_TILE + 1;
+    return align_up(nb * (int64_t)sizeof(int32_t), 256);
+}
+
+int pvs_exclusive_scan(const int32_t *deg, int32_t n, int32_t *row_ptr,
+                       void *scratch, void *stream) {
+    if (n < 0 || row_ptr == nullptr || (n > 0 && (deg == nullptr || scratch == nullptr)))
+        return PVS_ERR_INVALID_ARG;
+    return exclusive_scan(deg, n, row_ptr, scratch, (cudaStream_t)stream);
+}
+
+static int rg_check(const double *coords, const int32_t *bp,
+                    const int32_t *complex_ptr, int32_t n_complexes,
+                    int32_t n_nodes, int32_t max_n, double r1, double r2) {
+    if (n_complexes < 0 || n_nodes < 0 || max_n < 0) return PVS_ERR_INVALID_ARG;
+    if (!(r1 >= 0.0) || !(r2 >= 0.0)) return PVS_ERR_INVALID_ARG;
+    if (n_complexes > 0 && complex_ptr == nullptr) return PVS_ERR_INVALID_ARG;
+    if (n_nodes > 0 && (coords == nullptr || bp == nullptr)) return PVS_ERR_INVALID_ARG;
+    return PVS_OK;
+}
+
+int pvs_radius_graph_count(const double *coords, const int32_t *bp,
+                           const int32_t *complex_ptr, int32_t n_complexes,
+                           int32_t n_nodes, int32_t max_complex_nodes,
+                           double inter_radius, double intra_radius,
+                           int32_t *deg, int32_t *n_inter, int32_t *row_ptr,
+                           void *scratch, void *stream) {
+    int rc = rg_check(coords, bp, complex_ptr, n_complexes, n_nodes,
+                      max_complex_nodes, inter_radius, intra_radius);
+    if (rc) return rc;
+    if (row_ptr == nullptr || (n_nodes > 0 && (!deg || !n_inter || !scratch)))
+        return PVS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_nodes > 0 && n_complexes > 0) {
+        size_t smem = rg_smem_bytes(max_complex_nodes, false);
+        if (smem > (size_t)max_optin_smem()) return PVS_ERR_TOO_LARGE;
+        rc = cuda_call(cudaFuncSetAttribute(
+            radius_graph_kernel<false>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (rc) return rc;
+        radius_graph_kernel<false><<<n_complexes, RG_THREADS, smem, st>>>(
+            coords, bp, complex_ptr, inter_radius, intra_radius, deg, n_inter,
+            nullptr, nullptr, nullptr, nullptr, nullptr, max_complex_nodes);
+        rc = check_launch();
+        if (rc) return rc;
+    }
+    return exclusive_scan(deg, n_nodes, row_ptr, scratch, st);
+}
+
+int pvs_radius_graph_fill(const double *coords, const int32_t *bp,
+                          const int32_t *complex_ptr, int32_t n_complexes,
+                          int32_t n_nodes, int32_t max_complex_nodes,
+                          double inter_radius, double intra_radius,
+                          const int32_t *n_inter, const int32_t *row_ptr,
+                          int32_t *col, uint8_t *attr, int32_t *ref_pos,
+                          void *stream) {
+    int rc = rg_check(coords, bp, complex_ptr, n_complexes, n_nodes,
+                      max_complex_nodes, inter_radius, intra_radius);
+    if (rc) return rc;
+    if (n_nodes == 0 || n_complexes == 0) return PVS_OK;
+    if (!n_inter || !row_ptr || !col || !attr) return PVS_ERR_INVALID_ARG;
+    size_t smem = rg_smem_bytes(max_complex_nodes, ref_pos != nullptr);
+    if (smem > (size_t)max_optin_smem()) return PVS_ERR_TOO_LARGE;
+    rc = cuda_call(cudaFuncSetAttribute(
+        radius_graph_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        (int)smem));
+    if (rc) return rc;
+    radius_graph_kernel<true><<<n_complexes, RG_THREADS, smem,
+                                (cudaStream_t)stream>>>(
+        coords, bp, complex_ptr, inter_radius, intra_radius, nullptr, nullptr,
+        n_inter, row_ptr, col, attr, ref_pos, max_complex_nodes);
+    return check_launch();
+}
+
+int pvs_prune_mask(const int32_t *row_ptr, const int32_t *col,
+                   const int32_t *n_inter, const int32_t *complex_ptr,
+                   int32_t n_complexes, int32_t n_nodes, uint8_t *keep,
+                   void *stream) {
+    if (n_complexes < 0 || n_nodes < 0) return PVS_ERR_INVALID_ARG;
+    if (n_complexes == 0 || n_nodes == 0) return PVS_OK;
+    if (!row_ptr || !n_inter || !complex_ptr || !keep) return PVS_ERR_INVALID_ARG;
+    prune_mask_kernel<<<n_complexes, 256, 0, (cudaStream_t)stream>>>(
+        row_ptr, col, n_inter, complex_ptr, keep);
+    return check_launch();
+}
+
+int32_t pvs_tiles_capacity(int32_t n_nodes, int32_t n_edges) {
+    int64_t chunks = ((int64_t)n_nodes + TILE_CHUNK - 1) / TILE_CHUNK;
+    int64_t cap = (int64_t)n_edges / (PVS_TILE_EDGES / 2) +
+                  (int64_t)n_nodes / PVS_TILE_NODES + 2 * chunks + 2;
+    if (cap > n_nodes) cap = n_nodes;   // never more tiles than nodes
+    return (int32_t)(cap < 1 ? 1 : cap);
+}
+
+int64_t pvs_tiles_scratch_bytes(int32_t n_nodes) {
+    int64_t chunks = ((int64_t)n_nodes + TILE_CHUNK - 1) / TILE_CHUNK;
+    return align_up((int64_t)n_nodes * 4, 256) +
+           2 * align_up((chunks + 1) * 4, 256) +
+           pvs_scan_scratch_bytes((int32_t)chunks);
+}
+
+int pvs_build_tiles(const int32_t *row_ptr, int32_t n_nodes, int32_t *tile_ptr,
+                    int32_t *n_tiles, void *scratch, void *stream) {
+    if (n_nodes < 0 || !tile_ptr || !n_tiles) return PVS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_nodes == 0) {
+        int rc = cuda_call(cudaMemsetAsync(n_tiles, 0, sizeof(int32_t), st));
+        if (rc) return rc;
+        return cuda_call(cudaMemsetAsync(tile_ptr, 0, sizeof(int32_t), st));
+    }
+    if (!row_ptr || !scratch) return PVS_ERR_INVALID_ARG;
+    int chunks = (n_nodes + TILE_CHUNK - 1) / TILE_CHUNK;
+    char *p = (char *)scratch;
+    int32_t *tmp = (int32_t *)p;
+    p += align_up((int64_t)n_nodes * 4, 256);
+    int32_t *cnt = (int32_t *)p;
+    p += align_up(((int64_t)chunks + 1) * 4, 256);
+    int32_t *off = (int32_t *)p;
+    p += align_up(((int64_t)chunks + 1) * 4, 256);
+    tiles_walk_kernel<<<chunks, 256, 0, st>>>(row_ptr, n_nodes, tmp, cnt);
+    g_launches += 1;
+    int rc = exclusive_scan(cnt, chunks, off, p, st);
+    if (rc) return rc;
+    tiles_compact_kernel<<<chunks, 256, 0, st>>>(tmp, cnt, off, n_nodes, chunks,
+                                                 tile_ptr, n_tiles);
+    return check_launch();
+}
+
+int pvs_edge_index_to_csr(const int64_t *edge_index, int64_t n_edges,
+                          const int64_t *edge_attr_onehot, int32_t n_classes,
+                          int32_t n_nodes, int32_t *deg, int32_t *row_ptr,
+                          int32_t *col, uint8_t *attr, int32_t *perm,
+                          int32_t *bad_index, void *scratch, void *stream) {
+    if (n_edges < 0 || n_nodes < 0 || n_classes < 0 ||
+        n_classes > PVS_MAX_EDGE_CLASSES || n_edges > 0x7fffffffLL)
+        return PVS_ERR_INVALID_ARG;
+    if (!row_ptr || (n_nodes > 0 && (!deg || !scratch))) return PVS_ERR_INVALID_ARG;
+    if (n_edges > 0 && (!edge_index || !col || !perm)) return PVS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (n_nodes > 0) {
+        rc = cuda_call(cudaMemsetAsync(deg, 0, (size_t)n_nodes * 4, st));
+        if (rc) return rc;
+    }
+    int32_t *cursor = (int32_t *)scratch;
+    void *scan_scratch = (char *)scratch + align_up((int64_t)n_nodes * 4, 256);
+    const int T = 256;
+    const unsigned nb = (unsigned)((n_edges + T - 1) / T);
+    if (n_edges > 0) {
+        key_count_kernel<int64_t><<<nb, T, 0, st>>>(edge_index, n_edges, n_nodes,
+                                                   deg, bad_index);
+        g_launches += 1;
+    }
+    rc = exclusive_scan(deg, n_nodes, row_ptr, scan_scratch, st);
+    if (rc) return rc;
+    if (n_edges > 0 && n_nodes > 0) {
+        rc = cuda_call(cudaMemsetAsync(cursor, 0, (size_t)n_nodes * 4, st));
+        if (rc) return rc;
+        key_place_kernel<int64_t><<<nb, T, 0, st>>>(edge_index, n_edges, n_nodes,
+                                                   row_ptr, cursor, perm);
+        segment_sort_kernel<<<(n_nodes + T - 1) / T, T, 0, st>>>(row_ptr, n_nodes,
+                                                               perm);
+        csr_gather_kernel<<<nb, T, 0, st>>>(edge_index + n_edges,
+                                            edge_attr_onehot, n_classes, perm,
+                                            n_edges, n_nodes, col, attr,
+                                            bad_index);
+        g_launches += 3;
+    }
+    return check_launch(0);
+}
+
+int pvs_csr_transpose(const pvs_graph *g, int32_t *csc_ptr, int32_t *csc_eid,
+                      void *scratch, void *stream) {
+    if (!g || !csc_ptr || g->n_nodes < 0 || g->n_edges < 0) return PVS_ERR_INVALID_ARG;
+    if (g->n_nodes > 0 && !scratch) return PVS_ERR_INVALID_ARG;
+    if (g->n_edges > 0 && (!g->col || !csc_eid)) return PVS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = g->n_nodes;
+    const int64_t E = g->n_edges;
+    // scratch: deg[n] | cursor[n] | scan scratch
+    int32_t *deg = (int32_t *)scratch;
+    int32_t *cursor = (int32_t *)((char *)scratch + align_up((int64_t)n * 4, 256));
+    void *scan_scratch = (char *)cursor + align_up((int64_t)n * 4, 256);
+    int rc;
+    if (n > 0) {
+        rc = cuda_call(cudaMemsetAsync(scratch, 0, 2 * align_up((int64_t)n * 4, 256), st));
+        if (rc) return rc;
+    }
+    const int T = 256;
+    const unsigned nb = (unsigned)((E + T - 1) / T);
+    if (E > 0)
+        key_count_kernel<int32_t><<<nb, T, 0, st>>>(g->col, E, n, deg, nullptr);
+    if (E > 0) g_launches += 1;
+    rc = exclusive_scan(deg, n, csc_ptr, scan_scratch, st);
+    if (rc) return rc;
+    if (E > 0 && n > 0) {
+        key_place_kernel<int32_t><<<nb, T, 0, st>>>(g->col, E, n, csc_ptr, cursor,
+                                                   csc_eid);
+        segment_sort_kernel<<<(n + T - 1) / T, T, 0, st>>>(csc_ptr, n, csc_eid);
+        g_launches += 2;
+    }
+    return check_launch(0);
+}
+
+int pvs_batch_to_ptr(const int64_t *batch, int32_t n_nodes, int32_t n_graphs,
+                     int32_t *graph_ptr, void *stream) {
+    if (n_nodes < 0 || n_graphs < 0 || !graph_ptr) return PVS_ERR_INVALID_ARG;
+    if (n_nodes > 0 && !batch) return PVS_ERR_INVALID_ARG;
+    const int T = 256;
+    batch_to_ptr_kernel<<<(n_nodes + 1 + T - 1) / T, T, 0, (cudaStream_t)stream>>>(
+        batch, n_nodes, n_graphs, graph_ptr);
+    return check_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// Shared device helpers for the PointVS B200 kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pvs_b200.h"
+
+namespace pvs {
+
+extern thread_local int g_last_cuda_error;
+extern thread_local int64_t g_launches;
+
+// call after a group of `n` kernel launches
+inline int check_launch(int n = 1) {
+    g_launches += n;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g_last_cuda_error = (int)e;
+        return PVS_ERR_CUDA;
+    }
+    return PVS_OK;
+}
+
+inline int cuda_call(cudaError_t e) {
+    if (e != cudaSuccess) {
+        g_last_cuda_error = (int)e;
+        return PVS_ERR_CUDA;
+    }
+    return PVS_OK;
+}
+
+int num_sms();
+int max_optin_smem();
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+__device__ __forceinline__ float sigmoidf_(float v) {
+    return __fdividef(1.0f, 1.0f + __expf(-v));
+}
+// SiLU with ex2.approx + rcp.approx (2 MUFU ops, ~2 ulp): fp32-parity mode.
+__device__ __forceinline__ float siluf_(float v) {
+    return __fdividef(v, 1.0f + __expf(-v));
+}
+// d silu / dv given v
+__device__ __forceinline__ float silu_gradf_(float v) {
+    float s = sigmoidf_(v);
+    return s * (1.0f + v * (1.0f - s));
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case PVS_ACT_SIGMOID: return sigmoidf_(v);
+        case PVS_ACT_TANH: return tanhf(v);
+        case PVS_ACT_RELU: return fmaxf(v, 0.0f);
+        case PVS_ACT_SILU: return siluf_(v);
+        case PVS_ACT_SOFTPLUS:
+            // torch.nn.Softplus(beta=1, threshold=20)
+            return v > 20.0f ? v : log1pf(expf(v));
+        default: return v;
+    }
+}
+// derivative of act w.r.t. its input, from input v and output y
+__device__ __forceinline__ float act_grad(float v, float y, int act) {
+    switch (act) {
+        case PVS_ACT_SIGMOID: return y * (1.0f - y);
+        case PVS_ACT_TANH: return 1.0f - y * y;
+        case PVS_ACT_RELU: return v > 0.0f ? 1.0f : 0.0f;
+        case PVS_ACT_SILU: return silu_gradf_(v);
+        case PVS_ACT_SOFTPLUS: return v > 20.0f ? 1.0f : sigmoidf_(v);
+        default: return 1.0f;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// inclusive scan across the warp
+__device__ __forceinline__ int warp_scan_incl(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+}  // namespace pvs

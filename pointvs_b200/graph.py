@@ -1,0 +1,311 @@
+"""Radius graphs and packed batches on the GPU.
+
+Host-side mirror of the reference's graph construction:
+
+* `generate_edges(struct, inter_radius, intra_radius, prune)` -- drop-in for
+  /root/reference/point_vs/preprocessing/preprocessing.py:68-155 (same
+  argument meaning, same return triple, same edge ORDER), computed by the K1
+  cell-list kernel.
+* `radius_graph_batch(...)` -- the packed-batch path: many complexes in one
+  launch, destination-sorted CSR + work tiles, ready for the EGNN kernels.
+* `csr_from_edge_index(...)` -- any caller-supplied PyG `edge_index`
+  (pnn_geometric_base.py:55-58; attribution passes masked, arbitrarily
+  ordered edges) -> the same CSR, remembering the caller's order.
+* `PackedBatch` -- duck-types the PyG `Batch` the models consume
+  (data_loaders.py:381-391, 517-520).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import check, lib, ptr, stream
+
+
+class CSRGraph:
+    """Destination-sorted CSR + work tiles, all on one CUDA device.
+
+    row_ptr [N+1] int32, col [E] int32, attr [E] uint8 (edge class),
+    perm [E] int32 or None: perm[p] = index in the caller's edge order of the
+    edge stored at CSR slot p.
+    """
+
+    def __init__(self, n_nodes, n_edges, row_ptr, col, attr, perm=None,
+                 n_inter=None, ref_pos=None, n_classes=3):
+        self.n_nodes, self.n_edges = int(n_nodes), int(n_edges)
+        self.row_ptr, self.col, self.attr = row_ptr, col, attr
+        self.perm, self.n_inter, self.ref_pos = perm, n_inter, ref_pos
+        self.n_classes = n_classes
+        self.device = row_ptr.device
+        self._inv_perm = None
+        self._csc = None
+        self._build_tiles()
+
+    def _build_tiles(self):
+        h = lib()
+        dev = self.device
+        cap = h.pvs_tiles_capacity(self.n_nodes, self.n_edges)
+        self.n_tiles_cap = int(cap)
+        self.tile_ptr = torch.empty(cap + 1, dtype=torch.int32, device=dev)
+        self.n_tiles = torch.zeros(1, dtype=torch.int32, device=dev)
+        scratch = torch.empty(
+            max(1, int(h.pvs_tiles_scratch_bytes(self.n_nodes))),
+            dtype=torch.uint8, device=dev)
+        check(h.pvs_build_tiles(ptr(self.row_ptr), self.n_nodes,
+                                ptr(self.tile_ptr), ptr(self.n_tiles),
+                                ptr(scratch), stream()), 'pvs_build_tiles')
+
+    def c_struct(self):
+        return _cabi.Graph(self.n_nodes, self.n_edges, ptr(self.row_ptr),
+                           ptr(self.col), ptr(self.attr), ptr(self.tile_ptr),
+                           ptr(self.n_tiles), self.n_tiles_cap)
+
+    # -- orderings -------------------------------------------------------
+    def rows(self):
+        """Destination node of every CSR edge, int64 [E]."""
+        deg = (self.row_ptr[1:] - self.row_ptr[:-1]).long()
+        return torch.repeat_interleave(
+            torch.arange(self.n_nodes, device=self.device), deg,
+            output_size=self.n_edges)
+
+    def inv_perm(self):
+        if self.perm is None:
+            return None
+        if self._inv_perm is None:
+            inv = torch.empty_like(self.perm, dtype=torch.long)
+            inv[self.perm.long()] = torch.arange(
+                self.n_edges, device=self.device)
+            self._inv_perm = inv
+        return self._inv_perm
+
+    def to_caller_order(self, per_edge):
+        """CSR-ordered per-edge tensor -> the caller's edge order."""
+        if self.perm is None:
+            return per_edge
+        return per_edge.index_select(0, self.inv_perm())
+
+    def from_caller_order(self, per_edge):
+        if self.perm is None:
+            return per_edge
+        return per_edge.index_select(0, self.perm.long())
+
+    def csc(self):
+        """(csc_ptr [N+1], csc_eid [E]): CSR edge ids grouped by neighbour."""
+        if self._csc is None:
+            h = lib()
+            dev = self.device
+            csc_ptr = torch.empty(self.n_nodes + 1, dtype=torch.int32, device=dev)
+            csc_eid = torch.empty(max(1, self.n_edges), dtype=torch.int32,
+                                  device=dev)
+            nbytes = 2 * ((self.n_nodes * 4 + 255) // 256 * 256) + \
+                int(h.pvs_scan_scratch_bytes(self.n_nodes)) + 256
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            g = self.c_struct()
+            check(h.pvs_csr_transpose(C.byref(g), ptr(csc_ptr), ptr(csc_eid),
+                                      ptr(scratch), stream()),
+                  'pvs_csr_transpose')
+            self._csc = (csc_ptr, csc_eid)
+        return self._csc
+
+    def edge_index(self, order='csr'):
+        """PyG-style [2,E] int64 edge_index ('csr' or 'reference' order)."""
+        ei = torch.stack([self.rows(), self.col.long()])
+        if order == 'reference':
+            if self.ref_pos is None:
+                raise ValueError('graph was built without ref_pos')
+            out = torch.empty_like(ei)
+            out[:, self.ref_pos.long()] = ei
+            return out
+        return ei
+
+    def edge_attr_onehot(self, order='csr'):
+        a = torch.nn.functional.one_hot(self.attr.long(), self.n_classes)
+        if order == 'reference':
+            out = torch.empty_like(a)
+            out[self.ref_pos.long()] = a
+            return out
+        return a
+
+
+def _as_i32(x, device):
+    return torch.as_tensor(np.asarray(x, dtype=np.int32)).to(device)
+
+
+def radius_graph_batch(coords, bp, complex_ptr, inter_radius=4.0,
+                       intra_radius=2.0, with_ref_pos=False, device=None):
+    """K1 over a packed batch.
+
+    coords: float64 [N,3] (tensor or array), bp: int [N], complex_ptr: int
+    [B+1] host array of node offsets.  Returns a CSRGraph whose within-row
+    order is the stable sort by destination of the reference's edge list.
+    """
+    device = torch.device(device or 'cuda')
+    h = lib()
+    coords = torch.as_tensor(coords, dtype=torch.float64).to(device).contiguous()
+    bp = torch.as_tensor(bp).to(device=device, dtype=torch.int32).contiguous()
+    cptr_host = np.asarray(complex_ptr, dtype=np.int32)
+    n = int(coords.shape[0])
+    n_complexes = len(cptr_host) - 1
+    if n_complexes < 0 or (n_complexes >= 0 and int(cptr_host[-1]) != n):
+        raise ValueError('complex_ptr must end at the number of atoms')
+    max_n = int(np.max(np.diff(cptr_host))) if n_complexes > 0 else 0
+    cptr = torch.from_numpy(cptr_host).to(device)
+    deg = torch.empty(max(1, n), dtype=torch.int32, device=device)
+    n_inter = torch.empty(max(1, n), dtype=torch.int32, device=device)
+    row_ptr = torch.empty(n + 1, dtype=torch.int32, device=device)
+    scratch = torch.empty(int(h.pvs_scan_scratch_bytes(n)) + 256,
+                          dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        check(h.pvs_radius_graph_count(
+            ptr(coords), ptr(bp), ptr(cptr), n_complexes, n, max_n,
+            C.c_double(inter_radius), C.c_double(intra_radius), ptr(deg),
+            ptr(n_inter), ptr(row_ptr), ptr(scratch), stream()),
+            'pvs_radius_graph_count')
+        n_edges = int(row_ptr[-1].item())   # the one host sync: sizes col/attr
+        col = torch.empty(max(1, n_edges), dtype=torch.int32, device=device)
+        attr = torch.empty(max(1, n_edges), dtype=torch.uint8, device=device)
+        ref_pos = torch.empty(max(1, n_edges), dtype=torch.int32,
+                              device=device) if with_ref_pos else None
+        check(h.pvs_radius_graph_fill(
+            ptr(coords), ptr(bp), ptr(cptr), n_complexes, n, max_n,
+            C.c_double(inter_radius), C.c_double(intra_radius), ptr(n_inter),
+            ptr(row_ptr), ptr(col), ptr(attr), ptr(ref_pos), stream()),
+            'pvs_radius_graph_fill')
+        g = CSRGraph(n, n_edges, row_ptr, col[:n_edges], attr[:n_edges],
+                     perm=None, n_inter=n_inter[:n],
+                     ref_pos=None if ref_pos is None else ref_pos[:n_edges])
+    g.complex_ptr = cptr
+    g.complex_ptr_host = cptr_host
+    return g
+
+
+def prune_mask(graph):
+    """keep[i] for `prune=True` (preprocessing.py:144-153)."""
+    h = lib()
+    keep = torch.zeros(max(1, graph.n_nodes), dtype=torch.uint8,
+                       device=graph.device)
+    with torch.cuda.device(graph.device):
+        check(h.pvs_prune_mask(ptr(graph.row_ptr), ptr(graph.col),
+                               ptr(graph.n_inter), ptr(graph.complex_ptr),
+                               len(graph.complex_ptr_host) - 1, graph.n_nodes,
+                               ptr(keep), stream()), 'pvs_prune_mask')
+    return keep[:graph.n_nodes].bool()
+
+
+def generate_edges(struct, inter_radius=4.0, intra_radius=2.0, prune=True,
+                   synthpharm=False, device=None):
+    """Drop-in for the reference's generate_edges (same signature/returns).
+
+    struct: DataFrame with x, y, z, bp columns.  Returns
+    (struct, (row, col), edge_attrs) with numpy int64/int32 arrays in the
+    reference's order ([inter | intra], each half row-major).  As in the
+    reference, `struct` is re-indexed in place and pruned atoms are dropped
+    from it.
+    """
+    struct.reset_index(inplace=True, drop=True)
+    if synthpharm:
+        struct['bp'] = struct['atom_id'].apply(lambda v: int(v <= 2))
+    coords = np.vstack([struct.x.to_numpy(), struct.y.to_numpy(),
+                        struct.z.to_numpy()]).T.astype(np.float64)
+    bp = struct.bp.to_numpy()
+    n = len(coords)
+    g = radius_graph_batch(coords, bp, [0, n], inter_radius, intra_radius,
+                           with_ref_pos=True, device=device)
+    if prune and int(g.n_inter.sum().item()) > 0:
+        keep = prune_mask(g).cpu().numpy()
+        drop = struct.index[~keep]
+        struct.drop(drop, inplace=True)
+        return generate_edges(struct.copy(), inter_radius, intra_radius,
+                              False, device=device)
+    ei = g.edge_index('reference').cpu().numpy()
+    attr = torch.empty_like(g.attr)
+    attr[g.ref_pos.long()] = g.attr
+    return struct, (ei[0], ei[1]), attr.cpu().numpy().astype(np.int32)
+
+
+def csr_from_edge_index(edge_index, edge_attr, n_nodes):
+    """Caller-ordered PyG edge_index [2,E] (+ one-hot edge_attr [E,D] or None)
+    -> CSRGraph with `perm`.  Raises IndexError on out-of-range node ids."""
+    h = lib()
+    device = edge_index.device
+    _cabi.require_cuda(edge_index)
+    ei = edge_index.to(torch.int64).contiguous()
+    n_edges = int(ei.shape[1])
+    n_classes = 0
+    onehot = None
+    if edge_attr is not None:
+        if edge_attr.dim() != 2 or edge_attr.shape[0] != n_edges:
+            raise ValueError('edge_attr must be [E, n_classes] one-hot')
+        n_classes = int(edge_attr.shape[1])
+        onehot = edge_attr.to(device=device, dtype=torch.int64).contiguous()
+    deg = torch.empty(max(1, n_nodes), dtype=torch.int32, device=device)
+    row_ptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=device)
+    col = torch.empty(max(1, n_edges), dtype=torch.int32, device=device)
+    attr = torch.zeros(max(1, n_edges), dtype=torch.uint8, device=device)
+    perm = torch.empty(max(1, n_edges), dtype=torch.int32, device=device)
+    bad = torch.zeros(1, dtype=torch.int32, device=device)
+    nbytes = (n_nodes * 4 + 255) // 256 * 256 + \
+        int(h.pvs_scan_scratch_bytes(n_nodes)) + 256
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        check(h.pvs_edge_index_to_csr(
+            ptr(ei), C.c_int64(n_edges), ptr(onehot), n_classes, n_nodes,
+            ptr(deg), ptr(row_ptr), ptr(col), ptr(attr), ptr(perm), ptr(bad),
+            ptr(scratch), stream()), 'pvs_edge_index_to_csr')
+        g = CSRGraph(n_nodes, n_edges, row_ptr, col[:n_edges], attr[:n_edges],
+                     perm=perm[:n_edges], n_classes=max(n_classes, 1))
+    g._bad = bad
+    return g
+
+
+class PackedBatch:
+    """Variable-size complexes packed for the EGNN kernels; duck-types the PyG
+    `Batch` consumed by `forward(graph)` (x, pos, edge_index, edge_attr,
+    batch, y, lig_fname, rec_fname) and carries the prebuilt CSR as
+    `pvs_csr`, so the model skips the edge sort."""
+
+    def __init__(self, x, pos, csr, batch, y=None, lig_fname=None,
+                 rec_fname=None):
+        self.x, self.pos, self.pvs_csr, self.batch = x, pos, csr, batch
+        self.y = y
+        self.lig_fname = lig_fname if lig_fname is not None else []
+        self.rec_fname = rec_fname if rec_fname is not None else []
+        self._edge_index = None
+        self._edge_attr = None
+
+    @property
+    def edge_index(self):
+        if self._edge_index is None:
+            self._edge_index = self.pvs_csr.edge_index('csr')
+        return self._edge_index
+
+    @property
+    def edge_attr(self):
+        if self._edge_attr is None:
+            self._edge_attr = self.pvs_csr.edge_attr_onehot('csr')
+        return self._edge_attr
+
+    def to(self, device):
+        return self
+
+    @staticmethod
+    def from_arrays(coords, bp, feats, complex_ptr, inter_radius=4.0,
+                    intra_radius=4.0, y=None, device=None, lig_fname=None,
+                    rec_fname=None):
+        """coords f64 [N,3], bp [N], feats f32 [N,F], complex_ptr [B+1]
+        (host arrays, or device tensors for coords/bp/feats)."""
+        device = torch.device(device or 'cuda')
+        coords_d = torch.as_tensor(coords, dtype=torch.float64).to(device)
+        csr = radius_graph_batch(coords_d, bp, complex_ptr, inter_radius,
+                                 intra_radius, device=device)
+        cptr = np.asarray(complex_ptr, dtype=np.int64)
+        sizes = torch.from_numpy(np.diff(cptr)).to(device)
+        batch = torch.repeat_interleave(
+            torch.arange(len(cptr) - 1, device=device), sizes,
+            output_size=int(cptr[-1]))
+        x = torch.as_tensor(feats, dtype=torch.float32).to(device)
+        pb = PackedBatch(x, coords_d.float(), csr, batch, y=y,
+                         lig_fname=lig_fname, rec_fname=rec_fname)
+        pb.graph_ptr = torch.from_numpy(cptr.astype(np.int32)).to(device)
+        return pb
