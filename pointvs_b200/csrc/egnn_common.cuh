@@ -1,0 +1,35 @@
+// Argument block shared by the FFMA and tcgen05 edge kernels.
+#pragma once
+#include "pvs_common.cuh"
+
+namespace pvs {
+
+constexpr int TE = PVS_TILE_EDGES;
+constexpr int TN = PVS_TILE_NODES;
+
+struct EdgeArgs {
+    // graph
+    const int32_t *row_ptr, *col, *tile_ptr, *n_tiles;
+    const uint8_t *attr;
+    // activations
+    const float *P, *Q;      // [N][KP]
+    const float *x_in;       // [N][3]
+    const float *m_prev;     // [E][k] or null
+    float *M;                // [N][KP]
+    float *x_out;            // [N][3] or null
+    float *m_out;            // [E][ld_m] or null
+    int ld_m;
+    float *att_out;          // [E] or null (softmax mode: raw logits)
+    // params
+    const float *edge_w1, *edge_w2, *edge_b2, *coord_w1, *coord_b1, *coord_w2;
+    const float *att_w, *att_b, *edge_gate;
+    int k, in_e, n_classes;
+    uint32_t flags;
+    int att_act;
+};
+
+
+// launches the tcgen05 edge kernel (egnn_edge_tc.cu); mode = pvs_math
+int launch_edge_tc(const EdgeArgs &a, int n_tiles_cap, int mode, cudaStream_t st);
+
+}  // namespace pvs

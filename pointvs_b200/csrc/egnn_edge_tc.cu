@@ -1,0 +1,514 @@
+// K2 edge stage on the 5th-generation tensor cores (PVS_MATH_BF16X3 / BF16).
+//
+// Same dataflow as egnn_edge_fwd_kernel (egnn_fwd.cu) but the two per-edge
+// 64x64 contractions (edge_mlp.2 and coord_mlp.0; reference
+// egnn_satorras.py:76-80, 88-96) run as tcgen05.mma tiles:
+//
+//   tile      : 128 dst-sorted edges (UMMA M = 128, cta_group::1), N = 64, K = 64
+//   A operand : activations written by the CTA's threads into shared memory in
+//               the canonical K-major SWIZZLE_128B layout (one 128-byte row per
+//               edge), as a bf16 hi tile and, for BF16X3, a bf16 lo tile
+//   B operand : nn.Linear weight [out][in] = N x K, K-major, same layout,
+//               split hi/lo once per CTA
+//   D         : fp32 accumulators in tensor memory (2 x 64 columns)
+//   BF16X3    : D = Ahi.Bhi + Alo.Bhi + Ahi.Blo (error ~2^-16, fp32-class);
+//   BF16      : D = Ahi.Bhi
+//   epilogue  : tcgen05.ld 32x32b -- each thread owns one edge row: bias, SiLU,
+//               the 64->1 attention / coordinate heads as in-thread dot
+//               products, and the next GEMM's A tile written straight back to
+//               shared memory; the coordinate GEMM overlaps the message
+//               segment-reduce.
+//
+// 128 threads per CTA, ~74 KB shared memory and 128 TMEM columns per CTA, three
+// CTAs per SM so one CTA's MMA/epilogue overlaps another's gather.
+#include <cuda_bf16.h>
+
+#include "egnn_common.cuh"
+
+namespace pvs {
+
+constexpr int TC_THREADS = 128;
+constexpr int TC_K = 64;          // padded hidden width of the tile
+constexpr uint32_t TC_TMEM_COLS = 128;
+
+struct __align__(1024) TcSmem {
+    // swizzled bf16 tiles, each 1024-byte aligned
+    uint8_t A_hi[TE * 128];
+    uint8_t A_lo[TE * 128];
+    uint8_t W2_hi[TC_K * 128];
+    uint8_t W2_lo[TC_K * 128];
+    uint8_t Wc1_hi[TC_K * 128];
+    uint8_t Wc1_lo[TC_K * 128];
+    float b2[64], bc1[64], wc2[64], wa[64], wr[64];
+    float T[PVS_MAX_EDGE_CLASSES][64];
+    float e_rad[TE], e_dx[TE], e_dy[TE], e_dz[TE], e_z[TE], e_c[TE];
+    int e_rowl[TE], e_col[TE], e_attr[TE];
+    int rp[TN + 1];
+    float xsum[TN][3];
+    uint64_t mbar;
+    uint32_t tmem_base;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// bounded wait: a descriptor bug must fail the launch, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(dst_smem)), "n"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                 ::"r"(taddr), "n"(TC_TMEM_COLS) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]),
+          "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+          "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B, 128-byte rows:
+// start address [0,14) (>>4), LBO [16,30) = 1 (unused for swizzled K-major),
+// SBO [32,46) = 1024 B between 8-row groups, version [46,48) = 1,
+// layout type [61,64) = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// Instruction descriptor (kind::f16): D fp32 [4,6)=1, A bf16 [7,10)=1,
+// B bf16 [10,13)=1, both K-major, N>>3 at [17,23), M>>4 at [24,29).
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) |
+                              ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+// byte offset of 16-byte chunk `c` (8 bf16 = channels 8c..8c+7) of row `r`
+__device__ __forceinline__ uint32_t swz(int r, int c) {
+    return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
+}
+
+// split 8 fp32 into bf16 hi (round-to-nearest) and bf16 lo = bf16(x - hi)
+template <bool WITH_LO>
+__device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        h[i] = *reinterpret_cast<uint32_t *>(&hb);
+        if (WITH_LO) {
+            float r0 = v[2 * i] - __uint_as_float(h[i] << 16);
+            float r1 = v[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
+            __nv_bfloat162 lb = __floats2bfloat162_rn(r0, r1);
+            l[i] = *reinterpret_cast<uint32_t *>(&lb);
+        } else {
+            l[i] = 0u;
+        }
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// W [k][k] fp32 (nn.Linear [out][in]) -> swizzled bf16 hi / lo B tiles
+template <bool WITH_LO>
+__device__ void load_weight_tiles(uint8_t *hi_tile, uint8_t *lo_tile,
+                                  const float *__restrict__ W, int k) {
+    for (int idx = threadIdx.x; idx < TC_K * 8; idx += TC_THREADS) {
+        const int n = idx >> 3, c = idx & 7;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int kk = 8 * c + i;
+            v[i] = (n < k && kk < k) ? W[(size_t)n * k + kk] : 0.0f;
+        }
+        uint4 hi, lo;
+        split8<WITH_LO>(v, hi, lo);
+        *reinterpret_cast<uint4 *>(hi_tile + swz(n, c)) = hi;
+        if (WITH_LO) *reinterpret_cast<uint4 *>(lo_tile + swz(n, c)) = lo;
+    }
+}
+
+// one 128 x 64 x 64 GEMM into TMEM columns [d_col, d_col + 64)
+template <bool X3>
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_base, uint32_t d_col,
+                                           const uint8_t *a_hi, const uint8_t *a_lo,
+                                           const uint8_t *b_hi, const uint8_t *b_lo,
+                                           uint64_t *bar) {
+    const uint64_t ah = make_desc(smem_u32(a_hi)), al = make_desc(smem_u32(a_lo));
+    const uint64_t bh = make_desc(smem_u32(b_hi)), bl = make_desc(smem_u32(b_lo));
+    const uint32_t d = tmem_base + d_col;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int ks = 0; ks < TC_K / 16; ++ks) {
+        const uint64_t adv = (uint64_t)(ks * 2);   // 16 bf16 = 32 B = 2 x 16 B
+        umma_bf16(d, ah + adv, bh + adv, TC_IDESC, acc);
+        acc = 1;
+        if (X3) {
+            umma_bf16(d, al + adv, bh + adv, TC_IDESC, 1);
+            umma_bf16(d, ah + adv, bl + adv, TC_IDESC, 1);
+        }
+    }
+    umma_commit(bar);
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(TC_THREADS, 3)
+egnn_edge_tc_kernel(const EdgeArgs a) {
+    // SWIZZLE_128B tiles need 1024-byte alignment; the kernel has no static
+    // shared memory, so the dynamic window starts at its (aligned) base.
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    TcSmem &S = *reinterpret_cast<TcSmem *>(smem_dyn);
+    if ((smem_u32(smem_dyn) & 1023u) != 0u) __trap();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = a.k;
+    const bool f_att = a.flags & PVS_F_EDGE_ATTENTION;
+    const bool f_softmax = f_att && (a.flags & PVS_F_SOFTMAX_ATTENTION);
+    const bool f_coords = (a.flags & PVS_F_UPDATE_COORDS) && a.x_out != nullptr;
+    const bool f_eres = (a.flags & PVS_F_EDGE_RESIDUAL) && a.m_prev != nullptr;
+
+    // ---- one-time setup ----
+    load_weight_tiles<X3>(S.W2_hi, S.W2_lo, a.edge_w2, k);
+    load_weight_tiles<X3>(S.Wc1_hi, S.Wc1_lo, a.coord_w1, k);
+    const int col_r = (a.flags & PVS_F_PERM_INVARIANT) ? k : 2 * k;
+    for (int n = tid; n < 64; n += TC_THREADS) {
+        const bool ok = n < k;
+        S.b2[n] = ok ? a.edge_b2[n] : 0.0f;
+        S.bc1[n] = ok ? a.coord_b1[n] : 0.0f;
+        S.wc2[n] = ok ? a.coord_w2[n] : 0.0f;
+        S.wa[n] = (ok && a.att_w) ? a.att_w[n] : 0.0f;
+        S.wr[n] = ok ? a.edge_w1[(size_t)n * a.in_e + col_r] : 0.0f;
+        for (int c = 0; c < PVS_MAX_EDGE_CLASSES; ++c)
+            S.T[c][n] = (ok && c < a.n_classes)
+                            ? a.edge_w1[(size_t)n * a.in_e + col_r + 1 + c] : 0.0f;
+    }
+    if (tid == 0) mbar_init(&S.mbar, 1);
+    if (warp == 0) tmem_alloc(&S.tmem_base);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = S.tmem_base;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0;
+    const float att_b = (f_att && a.att_b) ? a.att_b[0] : 0.0f;
+    float gate = 1.0f;
+    if (f_eres && a.edge_gate) gate = a.edge_gate[0];
+    const int n_tiles = *a.n_tiles;
+
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int n0 = a.tile_ptr[t], n1 = a.tile_ptr[t + 1];
+        const int nn = n1 - n0;
+        __syncthreads();
+        for (int i = tid; i <= nn; i += TC_THREADS) S.rp[i] = a.row_ptr[n0 + i];
+        for (int i = tid; i < nn * 3; i += TC_THREADS) (&S.xsum[0][0])[i] = 0.0f;
+        __syncthreads();
+        const int e0 = S.rp[0], e1 = S.rp[nn];
+        const int n_chunks = max(1, (e1 - e0 + TE - 1) / TE);
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            const int c0 = e0 + ch * TE;
+            const int ne = min(TE, e1 - c0);
+            if (ne > 0) {
+                // ---- stage 0: geometry, one thread per edge ----
+                if (tid < ne) {
+                    const int e = c0 + tid;
+                    int lo = 0, hi = nn;
+                    while (hi - lo > 1) {
+                        int mid = (lo + hi) >> 1;
+                        if (S.rp[mid] <= e) lo = mid; else hi = mid;
+                    }
+                    const int i = n0 + lo, j = a.col[e];
+                    float dx = a.x_in[3 * i] - a.x_in[3 * j];
+                    float dy = a.x_in[3 * i + 1] - a.x_in[3 * j + 1];
+                    float dz = a.x_in[3 * i + 2] - a.x_in[3 * j + 2];
+                    float r = dx * dx + dy * dy + dz * dz;
+                    if (a.flags & PVS_F_NORMALIZE) {
+                        float inv = 1.0f / (sqrtf(r) + 1e-8f);
+                        dx *= inv; dy *= inv; dz *= inv;
+                    }
+                    S.e_rowl[tid] = lo;
+                    S.e_col[tid] = j;
+                    S.e_attr[tid] = a.attr ? a.attr[e] : 0;
+                    S.e_rad[tid] = r;
+                    S.e_dx[tid] = dx; S.e_dy[tid] = dy; S.e_dz[tid] = dz;
+                }
+                __syncthreads();
+                // ---- stage 1: s1 = silu(P_i + Q_j + w_r r + T[a]) -> A tile.
+                // 8 lanes per edge row (one 16-byte chunk each), 16 rows a pass:
+                // every LDG.128 warp instruction reads 4 full 256-byte rows.
+                {
+                    const int c = tid & 7, slot = tid >> 3;
+                    float wr8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) wr8[i] = S.wr[8 * c + i];
+#pragma unroll 2
+                    for (int p = 0; p < TE / 16; ++p) {
+                        const int r = p * 16 + slot;
+                        float v[8];
+                        if (r < ne) {
+                            const float4 *pp = reinterpret_cast<const float4 *>(
+                                a.P + (size_t)(n0 + S.e_rowl[r]) * TC_K + 8 * c);
+                            const float4 *qq = reinterpret_cast<const float4 *>(
+                                a.Q + (size_t)S.e_col[r] * TC_K + 8 * c);
+                            const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+                            const float4 q0 = __ldg(qq), q1 = __ldg(qq + 1);
+                            const float rad = S.e_rad[r];
+                            const float *tt = &S.T[S.e_attr[r]][8 * c];
+                            const float pq[8] = {p0.x + q0.x, p0.y + q0.y, p0.z + q0.z,
+                                                 p0.w + q0.w, p1.x + q1.x, p1.y + q1.y,
+                                                 p1.z + q1.z, p1.w + q1.w};
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                v[i] = siluf_(fmaf(wr8[i], rad, pq[i]) + tt[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+                        }
+                        uint4 hi, lo;
+                        split8<X3>(v, hi, lo);
+                        *reinterpret_cast<uint4 *>(S.A_hi + swz(r, c)) = hi;
+                        if (X3) *reinterpret_cast<uint4 *>(S.A_lo + swz(r, c)) = lo;
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                __syncthreads();
+                // ---- GEMM 1: t2 = s1 . W2^T ----
+                if (tid == 0) {
+                    tc_fence_after();
+                    issue_gemm<X3>(tmem_base, 0, S.A_hi, S.A_lo, S.W2_hi, S.W2_lo, &S.mbar);
+                }
+                mbar_wait(&S.mbar, phase);
+                phase ^= 1;
+                tc_fence_after();
+                // ---- epilogue 1: m = silu(t2 + b2) (+ edge residual), the
+                // attention logit, and m back into the A tile for GEMM 2 ----
+                {
+                    const int r = tid;
+                    float dot = 0.0f;
+#pragma unroll 1
+                    for (int q = 0; q < 4; ++q) {
+                        float acc[16];
+                        tmem_ld16(tmem_lane + 16 * q, acc);
+#pragma unroll
+                        for (int hlf = 0; hlf < 2; ++hlf) {
+                            float mv[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int n = 16 * q + 8 * hlf + i;
+                                float m = siluf_(acc[8 * hlf + i] + S.b2[n]);
+                                if (f_eres && r < ne && n < k) {
+                                    float mp = a.m_prev[(size_t)(c0 + r) * k + n];
+                                    if (a.flags & PVS_F_REZERO) m = mp + gate * m;
+                                    else if (a.flags & PVS_F_GATED_RESIDUAL) {
+                                        float g = fmaxf(gate, 0.0f);
+                                        m = g * m + (1.0f - g) * mp;
+                                    } else m = m + mp;
+                                }
+                                if (n >= k || r >= ne) m = 0.0f;
+                                mv[i] = m;
+                                dot = fmaf(S.wa[n], m, dot);
+                            }
+                            uint4 hi, lo;
+                            split8<X3>(mv, hi, lo);
+                            const int c = 2 * q + hlf;
+                            *reinterpret_cast<uint4 *>(S.A_hi + swz(r, c)) = hi;
+                            if (X3) *reinterpret_cast<uint4 *>(S.A_lo + swz(r, c)) = lo;
+                        }
+                    }
+                    // attention value per edge (alpha, or the raw logit when
+                    // a softmax pass follows)
+                    float al = 1.0f;
+                    if (f_att) {
+                        const float z = dot + att_b;
+                        al = f_softmax ? z : apply_act(z, a.att_act);
+                        if (a.att_out && r < ne) a.att_out[c0 + r] = al;
+                    }
+                    S.e_z[r] = al;
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                __syncthreads();
+                // ---- GEMM 2 (coordinate MLP) runs while the messages are
+                // reduced below ----
+                if (f_coords && tid == 0) {
+                    tc_fence_after();
+                    issue_gemm<X3>(tmem_base, 64, S.A_hi, S.A_lo, S.Wc1_hi, S.Wc1_lo,
+                                   &S.mbar);
+                }
+            }
+            // ---- M_i = sum_e alpha_e m_e over dst segments (warp per node) ----
+            if (!f_softmax) {
+                for (int nl = warp; nl < nn; nl += TC_THREADS / 32) {
+                    const int lo = max(S.rp[nl], c0) - c0;
+                    const int hi = min(S.rp[nl + 1], c0 + TE) - c0;
+                    float s0 = 0.0f, s1 = 0.0f;
+                    for (int el = lo; el < hi; ++el) {
+                        const uint32_t off = swz(el, lane >> 2) + ((lane & 3) << 2);
+                        const uint32_t h = *reinterpret_cast<const uint32_t *>(S.A_hi + off);
+                        float m0 = __uint_as_float(h << 16);
+                        float m1 = __uint_as_float(h & 0xffff0000u);
+                        if (X3) {
+                            const uint32_t l = *reinterpret_cast<const uint32_t *>(S.A_lo + off);
+                            m0 += __uint_as_float(l << 16);
+                            m1 += __uint_as_float(l & 0xffff0000u);
+                        }
+                        const float al = S.e_z[el];
+                        s0 = fmaf(al, m0, s0);
+                        s1 = fmaf(al, m1, s1);
+                    }
+                    float2 *dst = reinterpret_cast<float2 *>(
+                        a.M + (size_t)(n0 + nl) * TC_K + 2 * lane);
+                    if (ch == 0) {
+                        *dst = make_float2(s0, s1);
+                    } else if (hi > lo) {
+                        float2 old = *dst;
+                        *dst = make_float2(old.x + s0, old.y + s1);
+                    }
+                }
+            }
+            // ---- messages out (edge residual of the next layer / softmax) ----
+            if (a.m_out != nullptr) {
+                for (int idx = tid; idx < ne * (TC_K / 2); idx += TC_THREADS) {
+                    const int el = idx >> 5, w = idx & 31;
+                    const uint32_t off = swz(el, w >> 2) + ((w & 3) << 2);
+                    const uint32_t h = *reinterpret_cast<const uint32_t *>(S.A_hi + off);
+                    float m0 = __uint_as_float(h << 16);
+                    float m1 = __uint_as_float(h & 0xffff0000u);
+                    if (X3) {
+                        const uint32_t l = *reinterpret_cast<const uint32_t *>(S.A_lo + off);
+                        m0 += __uint_as_float(l << 16);
+                        m1 += __uint_as_float(l & 0xffff0000u);
+                    }
+                    float *dst = a.m_out + (size_t)(c0 + el) * a.ld_m;
+                    if (2 * w < a.ld_m) dst[2 * w] = m0;
+                    if (2 * w + 1 < a.ld_m) dst[2 * w + 1] = m1;
+                }
+            }
+            if (ne > 0 && f_coords) {
+                // ---- epilogue 2: c = [tanh](wc2 . silu(Wc1 m + bc1)) ----
+                mbar_wait(&S.mbar, phase);
+                phase ^= 1;
+                tc_fence_after();
+                float dot = 0.0f;
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {
+                    float acc[16];
+                    tmem_ld16(tmem_lane + 64 + 16 * q, acc);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int n = 16 * q + i;
+                        dot = fmaf(S.wc2[n], siluf_(acc[i] + S.bc1[n]), dot);
+                    }
+                }
+                S.e_c[tid] = (a.flags & PVS_F_TANH) ? tanhf(dot) : dot;
+                tc_fence_before();
+            }
+            __syncthreads();
+            // ---- coordinate messages summed per node ----
+            if (f_coords && tid < nn) {
+                const int lo = max(S.rp[tid], c0) - c0;
+                const int hi = min(S.rp[tid + 1], c0 + TE) - c0;
+                float sx = 0.f, sy = 0.f, sz = 0.f;
+                for (int el = lo; el < hi; ++el) {
+                    const float c = S.e_c[el];
+                    sx = fmaf(S.e_dx[el], c, sx);
+                    sy = fmaf(S.e_dy[el], c, sy);
+                    sz = fmaf(S.e_dz[el], c, sz);
+                }
+                S.xsum[tid][0] += sx;
+                S.xsum[tid][1] += sy;
+                S.xsum[tid][2] += sz;
+            }
+            __syncthreads();
+        }
+        if (a.x_out != nullptr && tid < nn) {
+            const int i = n0 + tid;
+            const int cnt = S.rp[tid + 1] - S.rp[tid];
+            const float inv = 1.0f / (float)(cnt > 0 ? cnt : 1);
+            float ax = 0.f, ay = 0.f, az = 0.f;
+            if (f_coords) {
+                ax = S.xsum[tid][0] * inv;
+                ay = S.xsum[tid][1] * inv;
+                az = S.xsum[tid][2] * inv;
+            }
+            a.x_out[3 * i] = a.x_in[3 * i] + ax;
+            a.x_out[3 * i + 1] = a.x_in[3 * i + 1] + ay;
+            a.x_out[3 * i + 2] = a.x_in[3 * i + 2] + az;
+        }
+    }
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base);
+}
+
+int launch_edge_tc(const EdgeArgs &a, int n_tiles_cap, int mode, cudaStream_t st) {
+    const size_t smem = sizeof(TcSmem);
+    int grid = num_sms() * 3;
+    if (n_tiles_cap < grid) grid = n_tiles_cap;
+    if (grid < 1) grid = 1;
+    int rc;
+    if (mode == PVS_MATH_BF16X3) {
+        rc = cuda_call(cudaFuncSetAttribute(egnn_edge_tc_kernel<true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+        if (rc) return rc;
+        egnn_edge_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(a);
+    } else {
+        rc = cuda_call(cudaFuncSetAttribute(egnn_edge_tc_kernel<false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+        if (rc) return rc;
+        egnn_edge_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(a);
+    }
+    return check_launch();
+}
+
+}  // namespace pvs

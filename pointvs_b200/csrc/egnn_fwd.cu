@@ -17,12 +17,11 @@
 //              residual
 #include "pvs_common.cuh"
 #include "tile_gemm.cuh"
+#include "egnn_common.cuh"
 
 namespace pvs {
 
 constexpr int FWD_THREADS = 256;
-constexpr int TE = PVS_TILE_EDGES;
-constexpr int TN = PVS_TILE_NODES;
 constexpr int NODE_ROWS = 64;
 
 // ---------------------------------------------------------------------------
@@ -103,27 +102,6 @@ mean_pool_kernel(const float *__restrict__ h, const int32_t *__restrict__ ptr,
 // ---------------------------------------------------------------------------
 // edge kernel
 // ---------------------------------------------------------------------------
-struct EdgeArgs {
-    // graph
-    const int32_t *row_ptr, *col, *tile_ptr, *n_tiles;
-    const uint8_t *attr;
-    // activations
-    const float *P, *Q;      // [N][KP]
-    const float *x_in;       // [N][3]
-    const float *m_prev;     // [E][k] or null
-    float *M;                // [N][KP]
-    float *x_out;            // [N][3] or null
-    float *m_out;            // [E][ld_m] or null
-    int ld_m;
-    float *att_out;          // [E] or null (softmax mode: raw logits)
-    // params
-    const float *edge_w1, *edge_w2, *edge_b2, *coord_w1, *coord_b1, *coord_w2;
-    const float *att_w, *att_b, *edge_gate;
-    int k, in_e, n_classes;
-    uint32_t flags;
-    int att_act;
-};
-
 template <int KP>
 struct EdgeSmem {
     static constexpr int LDA = KP + 4;
@@ -729,7 +707,8 @@ int pvs_mean_pool_fwd(const float *h, const int32_t *graph_ptr, int32_t n_graphs
 int64_t pvs_egnn_layer_workspace_bytes(int32_t n_nodes, int32_t n_edges,
                                        const pvs_layer_config *cfg) {
     if (!cfg || cfg->k < 1 || cfg->k > PVS_MAX_K) return -1;
-    const int kp = cfg->k <= 32 ? 32 : 64;
+    if (cfg->math < PVS_MATH_FP32 || cfg->math > PVS_MATH_BF16) return -1;
+    const int kp = (cfg->k <= 32 && cfg->math == PVS_MATH_FP32) ? 32 : 64;
     return carve_workspace(nullptr, n_nodes, n_edges, kp, cfg->flags).bytes + 256;
 }
 
@@ -741,6 +720,7 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
                        void *stream) {
     if (!g || !cfg || !p) return PVS_ERR_INVALID_ARG;
     if (cfg->k < 1 || cfg->k > PVS_MAX_K) return PVS_ERR_UNSUPPORTED_K;
+    if (cfg->math < PVS_MATH_FP32 || cfg->math > PVS_MATH_BF16) return PVS_ERR_INVALID_ARG;
     if (cfg->n_edge_classes < 0 || cfg->n_edge_classes > PVS_MAX_EDGE_CLASSES)
         return PVS_ERR_INVALID_ARG;
     if (g->n_nodes < 0 || g->n_edges < 0) return PVS_ERR_INVALID_ARG;
@@ -768,7 +748,8 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
 
     cudaStream_t st = (cudaStream_t)stream;
     const int k = cfg->k;
-    const int kp = k <= 32 ? 32 : 64;
+    const bool tc = cfg->math != PVS_MATH_FP32;   // tcgen05 tiles are 64 wide
+    const int kp = (k <= 32 && !tc) ? 32 : 64;
     const int n = g->n_nodes, E = g->n_edges;
     const bool perm = f & PVS_F_PERM_INVARIANT;
     const int in_e = (perm ? k : 2 * k) + 1 + cfg->n_edge_classes;
@@ -813,8 +794,9 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
     ea.k = k; ea.in_e = in_e; ea.n_classes = cfg->n_edge_classes;
     ea.flags = f; ea.att_act = cfg->att_act;
     if (stages & PVS_STAGE_EDGE) {
-    rc = kp == 32 ? launch_edge<32>(ea, g->n_tiles_cap, st)
-                  : launch_edge<64>(ea, g->n_tiles_cap, st);
+    if (tc) rc = launch_edge_tc(ea, g->n_tiles_cap, cfg->math, st);
+    else rc = kp == 32 ? launch_edge<32>(ea, g->n_tiles_cap, st)
+                       : launch_edge<64>(ea, g->n_tiles_cap, st);
     if (rc) return rc;
     }
     if (softmax && (stages & PVS_STAGE_EDGE)) {
