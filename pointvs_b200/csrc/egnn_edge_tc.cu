@@ -175,6 +175,11 @@ __device__ void load_weight_tiles(uint8_t *hi_tile, uint8_t *lo_tile,
     }
 }
 
+template <bool X3>
+__device__ __forceinline__ float silu_mode(float v) {
+    return X3 ? siluf_(v) : siluf_fast_(v);
+}
+
 // one 128 x 64 x 64 GEMM into TMEM columns [d_col, d_col + 64)
 template <bool X3>
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_base, uint32_t d_col,
@@ -287,7 +292,7 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                     float wr8[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) wr8[i] = S.wr[8 * c + i];
-#pragma unroll 2
+#pragma unroll 4
                     for (int p = 0; p < TE / 16; ++p) {
                         const int r = p * 16 + slot;
                         float v[8];
@@ -299,13 +304,17 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                             const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
                             const float4 q0 = __ldg(qq), q1 = __ldg(qq + 1);
                             const float rad = S.e_rad[r];
-                            const float *tt = &S.T[S.e_attr[r]][8 * c];
+                            const float4 *t4 = reinterpret_cast<const float4 *>(
+                                &S.T[S.e_attr[r]][8 * c]);
+                            const float4 ta = t4[0], tb = t4[1];
+                            const float tt[8] = {ta.x, ta.y, ta.z, ta.w,
+                                                 tb.x, tb.y, tb.z, tb.w};
                             const float pq[8] = {p0.x + q0.x, p0.y + q0.y, p0.z + q0.z,
                                                  p0.w + q0.w, p1.x + q1.x, p1.y + q1.y,
                                                  p1.z + q1.z, p1.w + q1.w};
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                v[i] = siluf_(fmaf(wr8[i], rad, pq[i]) + tt[i]);
+                                v[i] = silu_mode<X3>(fmaf(wr8[i], rad, pq[i]) + tt[i]);
                         } else {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] = 0.0f;
@@ -338,23 +347,36 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                         tmem_ld16(tmem_lane + 16 * q, acc);
 #pragma unroll
                         for (int hlf = 0; hlf < 2; ++hlf) {
+                            const int nb = 16 * q + 8 * hlf;
+                            const float4 *b4 = reinterpret_cast<const float4 *>(&S.b2[nb]);
+                            const float4 *w4 = reinterpret_cast<const float4 *>(&S.wa[nb]);
+                            const float4 ba = b4[0], bb = b4[1], wa0 = w4[0], wa1 = w4[1];
+                            const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                            const float wat[8] = {wa0.x, wa0.y, wa0.z, wa0.w,
+                                                  wa1.x, wa1.y, wa1.z, wa1.w};
+                            // Padded channels (n >= k) need no masking: their
+                            // weight rows and biases are zero, so m = silu(0) = 0.
+                            // Rows >= ne hold values nobody reads.
                             float mv[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int n = 16 * q + 8 * hlf + i;
-                                float m = siluf_(acc[8 * hlf + i] + S.b2[n]);
-                                if (f_eres && r < ne && n < k) {
-                                    float mp = a.m_prev[(size_t)(c0 + r) * k + n];
-                                    if (a.flags & PVS_F_REZERO) m = mp + gate * m;
-                                    else if (a.flags & PVS_F_GATED_RESIDUAL) {
-                                        float g = fmaxf(gate, 0.0f);
-                                        m = g * m + (1.0f - g) * mp;
-                                    } else m = m + mp;
+                            for (int i = 0; i < 8; ++i)
+                                mv[i] = silu_mode<X3>(acc[8 * hlf + i] + bias[i]);
+                            if (f_eres && r < ne) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const int n = nb + i;
+                                    if (n < k) {
+                                        float mp = a.m_prev[(size_t)(c0 + r) * k + n];
+                                        if (a.flags & PVS_F_REZERO) mv[i] = mp + gate * mv[i];
+                                        else if (a.flags & PVS_F_GATED_RESIDUAL) {
+                                            float g = fmaxf(gate, 0.0f);
+                                            mv[i] = g * mv[i] + (1.0f - g) * mp;
+                                        } else mv[i] = mv[i] + mp;
+                                    }
                                 }
-                                if (n >= k || r >= ne) m = 0.0f;
-                                mv[i] = m;
-                                dot = fmaf(S.wa[n], m, dot);
                             }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) dot = fmaf(wat[i], mv[i], dot);
                             uint4 hi, lo;
                             split8<X3>(mv, hi, lo);
                             const int c = 2 * q + hlf;
@@ -442,9 +464,13 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                     float acc[16];
                     tmem_ld16(tmem_lane + 64 + 16 * q, acc);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int n = 16 * q + i;
-                        dot = fmaf(S.wc2[n], siluf_(acc[i] + S.bc1[n]), dot);
+                    for (int v4 = 0; v4 < 4; ++v4) {
+                        const float4 bb = *reinterpret_cast<const float4 *>(&S.bc1[16 * q + 4 * v4]);
+                        const float4 ww = *reinterpret_cast<const float4 *>(&S.wc2[16 * q + 4 * v4]);
+                        dot = fmaf(ww.x, silu_mode<X3>(acc[4 * v4] + bb.x), dot);
+                        dot = fmaf(ww.y, silu_mode<X3>(acc[4 * v4 + 1] + bb.y), dot);
+                        dot = fmaf(ww.z, silu_mode<X3>(acc[4 * v4 + 2] + bb.z), dot);
+                        dot = fmaf(ww.w, silu_mode<X3>(acc[4 * v4 + 3] + bb.w), dot);
                     }
                 }
                 S.e_c[tid] = (a.flags & PVS_F_TANH) ? tanhf(dot) : dot;

@@ -34,12 +34,36 @@ int max_optin_smem();
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
-__device__ __forceinline__ float sigmoidf_(float v) {
-    return __fdividef(1.0f, 1.0f + __expf(-v));
+// Raw MUFU ops.  __expf / __fdividef wrap these in range-fixup code (~12 SASS
+// instructions per SiLU, 36 % of the edge kernel's issue slots in the first
+// ncu capture); .ftz forms need none: ex2(+big) = inf -> rcp(inf) = 0.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
-// SiLU with ex2.approx + rcp.approx (2 MUFU ops, ~2 ulp): fp32-parity mode.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoidf_(float v) {
+    return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v));
+}
+// SiLU, fp32-class: 2 MUFU (ex2, rcp) + 3 FMA-pipe ops, error ~2 ulp.
 __device__ __forceinline__ float siluf_(float v) {
-    return __fdividef(v, 1.0f + __expf(-v));
+    return v * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v));
+}
+// SiLU for the single-pass bf16 mode: x*sigmoid(x) = h + h*tanh(h), h = x/2.
+// 1 MUFU; tanh.approx error 2^-11 is below the bf16 operand rounding.
+__device__ __forceinline__ float siluf_fast_(float v) {
+    const float h = 0.5f * v;
+    return fmaf(h, tanh_approx(h), h);
 }
 // d silu / dv given v
 __device__ __forceinline__ float silu_gradf_(float v) {
