@@ -36,7 +36,8 @@ typedef enum pvs_status {
     PVS_ERR_UNSUPPORTED_K = 2, /* hidden width outside 1..PVS_MAX_K */
     PVS_ERR_TOO_LARGE = 3,     /* one complex does not fit the cell-list smem */
     PVS_ERR_CUDA = 4,          /* a CUDA call failed: pvs_last_cuda_error() */
-    PVS_ERR_WORKSPACE = 5      /* workspace smaller than *_workspace_bytes */
+    PVS_ERR_WORKSPACE = 5,     /* workspace smaller than *_workspace_bytes */
+    PVS_ERR_UNSUPPORTED = 6    /* valid request the kernels do not cover yet */
 } pvs_status;
 
 #define PVS_MAX_K 64          /* widest hidden size (--channels) supported */
@@ -230,10 +231,24 @@ int pvs_batch_to_ptr(const int64_t *batch, int32_t n_nodes, int32_t n_graphs,
 int pvs_linear_fwd(const float *in, int32_t ld_in, int32_t rows, int32_t ki,
                    const float *w, int32_t ld_w, const float *b, int32_t ko,
                    int32_t act, float *out, int32_t ld_out, void *stream);
+/* Backward of pvs_linear_fwd (recomputes the pre-activation):
+ *   g = d_out * act'(in.W^T + b);  d_in = g . W;  d_w += g^T . in;
+ *   d_b += column sums of g.  d_in / d_w / d_b may be NULL.  ko <= 64. */
+int64_t pvs_linear_bwd_workspace_bytes(int32_t rows, int32_t ki, int32_t ko);
+int pvs_linear_bwd(const float *in, int32_t ld_in, int32_t rows, int32_t ki,
+                   const float *w, int32_t ld_w, const float *b, int32_t ko,
+                   int32_t act, const float *d_out, int32_t ld_dout,
+                   float *d_in, int32_t ld_din, float *d_w, int32_t ld_dw,
+                   float *d_b, void *workspace, int64_t workspace_bytes,
+                   void *stream);
+
 /* global_mean_pool (pnn_geometric_base.py:29-33): pooled[b] = mean of h rows
  * [graph_ptr[b], graph_ptr[b+1]) (0 for an empty graph). */
 int pvs_mean_pool_fwd(const float *h, const int32_t *graph_ptr,
                       int32_t n_graphs, int32_t k, float *pooled, void *stream);
+
+int pvs_mean_pool_bwd(const float *d_pooled, const int32_t *graph_ptr,
+                      int32_t n_graphs, int32_t k, float *d_h, void *stream);
 
 /* ---- K2: one EGNN layer, forward ----------------------------------------
  * Replaces EGNNLayer.forward (egnn_satorras.py:189-206 and :123-187).
@@ -252,6 +267,32 @@ int pvs_egnn_layer_fwd(const pvs_graph *graph, const pvs_layer_config *cfg,
                        float *x_out, float *m_out, float *att_out,
                        float *natt_out, void *workspace,
                        int64_t workspace_bytes, void *stream);
+
+/* ---- K3: one EGNN layer, backward ---------------------------------------
+ * Autograd of pvs_egnn_layer_fwd (PyTorch autograd of
+ * egnn_satorras.py:123-206 in the reference).  Recomputes the layer from
+ * (h_in, x_in, m_prev) instead of saving per-edge activations.
+ *   csc_ptr/csc_eid: the same edges grouped by neighbour (pvs_csr_transpose):
+ *   the scatter over `col` becomes a second atomics-free segment reduce.
+ *   d_h_out [N][k], d_x_out [N][3] (NULL = zero), d_m_out [E][k] (NULL =
+ *   zero): gradients of the layer outputs, CSR order.
+ *   d_h_in [N][k], d_x_in [N][3] are overwritten; d_m_prev [E][k] is
+ *   overwritten when the layer has an edge residual and m_prev != NULL.
+ *   Parameter gradients are ACCUMULATED into `grads` (NULL members skipped).
+ * Returns PVS_ERR_UNSUPPORTED for PVS_F_GRAPHNORM / PVS_F_SOFTMAX_ATTENTION
+ * (their backward is not implemented yet). */
+int pvs_csr_transpose(const pvs_graph *graph, int32_t *csc_ptr,
+                      int32_t *csc_eid, void *scratch, void *stream);
+int64_t pvs_egnn_layer_bwd_workspace_bytes(int32_t n_nodes, int32_t n_edges,
+                                           const pvs_layer_config *cfg);
+int pvs_egnn_layer_bwd(const pvs_graph *graph, const int32_t *csc_ptr,
+                       const int32_t *csc_eid, const pvs_layer_config *cfg,
+                       const pvs_layer_params *params, const float *h_in,
+                       const float *x_in, const float *m_prev,
+                       const float *d_h_out, const float *d_x_out,
+                       const float *d_m_out, float *d_h_in, float *d_x_in,
+                       float *d_m_prev, const pvs_layer_grads *grads,
+                       void *workspace, int64_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

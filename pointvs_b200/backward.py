@@ -1,15 +1,102 @@
-"""Backward passes of the autograd Functions (K3).  Filled in with the
-backward kernels; until then training raises instead of silently falling
-back to PyTorch autograd."""
+"""Backward passes of the autograd Functions (K3 and the dense helpers).
+
+Training goes through the same C ABI as scoring: these functions only marshal
+tensors into pvs_egnn_layer_bwd / pvs_linear_bwd / pvs_mean_pool_bwd.  The
+kernels recompute the layer from its saved inputs; PyTorch autograd is used
+only to chain the layers together (and for the loss and optimiser, as in the
+reference's `backprop`, point_neural_network_base.py:417-429).
+"""
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from ._cabi import check, lib, ptr, stream
+
+
+def _zeros_like_or_none(p):
+    return None if p is None else torch.zeros_like(p, dtype=torch.float32)
 
 
 def egnn_layer_backward(ctx, d_h, d_x, d_m):
-    raise NotImplementedError('pvs_egnn_layer_bwd is not built yet')
+    layer, csr = ctx.layer, ctx.csr
+    h, x, m_prev, *params = ctx.saved_tensors
+    if layer.graphnorm or (layer.edge_attention and layer.softmax_attention):
+        raise NotImplementedError(
+            'backward through GraphNorm / softmax attention is not implemented '
+            'in the CUDA path yet (train with graphnorm=False, '
+            'softmax_attention=False; scoring supports both)')
+    cfg = layer.c_config()
+    n, e, k = csr.n_nodes, csr.n_edges, layer.hidden_nf
+    dev = h.device
+    d_h = torch.zeros_like(h) if d_h is None else d_h.contiguous().float()
+    d_x = None if d_x is None else d_x.contiguous().float()
+    d_m = None if d_m is None else d_m.contiguous().float()
+    csc_ptr, csc_eid = csr.csc()
+
+    pstruct = _cabi.LayerParams(*[
+        ptr(None if p is None else p.detach().contiguous()) for p in params])
+    by_name = dict(zip(_cabi.PARAM_FIELDS, params))
+    grads = {name: _zeros_like_or_none(by_name[name])
+             for name in _cabi.GRAD_FIELDS}
+    gstruct = _cabi.LayerGrads(*[ptr(grads[name]) for name in _cabi.GRAD_FIELDS])
+
+    d_h_in = torch.empty_like(h)
+    d_x_in = torch.empty_like(x)
+    d_m_prev = torch.zeros_like(m_prev) if m_prev is not None else None
+    nbytes = int(lib().pvs_egnn_layer_bwd_workspace_bytes(n, e, C.byref(cfg)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    g = csr.c_struct()
+    with torch.cuda.device(dev):
+        check(lib().pvs_egnn_layer_bwd(
+            C.byref(g), ptr(csc_ptr), ptr(csc_eid), C.byref(cfg),
+            C.byref(pstruct), ptr(h), ptr(x), ptr(m_prev), ptr(d_h), ptr(d_x),
+            ptr(d_m), ptr(d_h_in), ptr(d_x_in), ptr(d_m_prev),
+            C.byref(gstruct), ptr(ws), C.c_int64(ws.numel()), stream()),
+            'pvs_egnn_layer_bwd')
+    # inputs of _EGNNLayerFn.forward: layer, csr, want_m, want_side, h, x,
+    # m_prev, *params
+    param_grads = []
+    for name, p in zip(_cabi.PARAM_FIELDS, params):
+        if p is None or name not in grads or grads[name] is None:
+            param_grads.append(None)   # GraphNorm params: unsupported above
+        else:
+            param_grads.append(grads[name].reshape(p.shape))
+    return (None, None, None, None, d_h_in, d_x_in, d_m_prev, *param_grads)
 
 
 def linear_backward(ctx, d_out):
-    raise NotImplementedError('pvs_linear_bwd is not built yet')
+    inp, w, out = ctx.saved_tensors
+    bias = ctx.bias_ref
+    d_out = d_out.contiguous().float()
+    rows, ki = inp.shape
+    ko = w.shape[0]
+    if ko > 64:
+        raise NotImplementedError('linear backward supports at most 64 '
+                                  'output features')
+    need_in = ctx.needs_input_grad[0]
+    d_in = torch.empty_like(inp) if need_in else None
+    d_w = torch.zeros_like(w)
+    d_b = torch.zeros(ko, dtype=torch.float32, device=inp.device) \
+        if ctx.has_bias else None
+    nbytes = int(lib().pvs_linear_bwd_workspace_bytes(rows, ki, ko))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=inp.device)
+    with torch.cuda.device(inp.device):
+        check(lib().pvs_linear_bwd(
+            ptr(inp), ki, rows, ki, ptr(w), ki, ptr(bias), ko,
+            _cabi.ACT[ctx.act], ptr(d_out), ko, ptr(d_in), ki, ptr(d_w), ki,
+            ptr(d_b), ptr(ws), C.c_int64(ws.numel()), stream()),
+            'pvs_linear_bwd')
+    return d_in, d_w, d_b, None
 
 
 def mean_pool_backward(ctx, d_pooled):
-    raise NotImplementedError('pvs_mean_pool_bwd is not built yet')
+    (graph_ptr,) = ctx.saved_tensors
+    d_pooled = d_pooled.contiguous().float()
+    d_h = torch.zeros((ctx.n_nodes, ctx.k), dtype=torch.float32,
+                      device=d_pooled.device)
+    with torch.cuda.device(d_pooled.device):
+        check(lib().pvs_mean_pool_bwd(ptr(d_pooled), ptr(graph_ptr),
+                                      ctx.n_graphs, ctx.k, ptr(d_h), stream()),
+              'pvs_mean_pool_bwd')
+    return d_h, None, None

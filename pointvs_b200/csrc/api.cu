@@ -44,6 +44,7 @@ const char *pvs_status_string(int status) {
         case PVS_ERR_TOO_LARGE: return "complex too large for the cell-list kernel";
         case PVS_ERR_CUDA: return "CUDA error (see pvs_last_cuda_error)";
         case PVS_ERR_WORKSPACE: return "workspace too small";
+        case PVS_ERR_UNSUPPORTED: return "configuration not supported by the kernels yet";
         default: return "unknown status";
     }
 }

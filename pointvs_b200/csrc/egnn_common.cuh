@@ -31,5 +31,13 @@ struct EdgeArgs {
 
 // launches the tcgen05 edge kernel (egnn_edge_tc.cu); mode = pvs_math
 int launch_edge_tc(const EdgeArgs &a, int n_tiles_cap, int mode, cudaStream_t st);
+// FFMA edge kernel with the 64-wide internal pitch (egnn_fwd.cu)
+int launch_edge_fp32_k64(const EdgeArgs &a, int n_tiles_cap, cudaStream_t st);
+// out = act(in . W^T + b) (w_in_major: out = in . W); accumulate: out += ...
+int launch_linear(const float *in, int ld_in, int rows, int ki, const float *w,
+                  int ld_w, const float *b, int ko, int act, float *out,
+                  int ld_out, cudaStream_t st, int w_in_major = 0,
+                  int accumulate = 0);
+int persistent_grid(int work_items, int blocks_per_sm);
 
 }  // namespace pvs

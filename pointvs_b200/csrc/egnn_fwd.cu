@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(FWD_THREADS)
 linear_fwd_kernel(const float *__restrict__ in, int ld_in, int rows, int ki,
                   const float *__restrict__ W, int ld_w,
                   const float *__restrict__ b, int ko, int act,
-                  float *__restrict__ out, int ld_out) {
+                  float *__restrict__ out, int ld_out, int w_in_major,
+                  int accumulate) {
     extern __shared__ __align__(16) float smem[];
     constexpr int LDW = 64 * NJ4;
     const int KIP = (ki + 3) & ~3;
@@ -40,7 +41,14 @@ linear_fwd_kernel(const float *__restrict__ in, int ld_in, int rows, int ki,
     float *Wt = smem;                  // [KIP][LDW]
     float *A = Wt + KIP * LDW;         // [64][lda]
     float *bias = A + NODE_ROWS * lda; // [LDW]
-    load_wt(Wt, KIP, LDW, W, ld_w, ki, ko);
+    if (w_in_major) {   // W given as [ki][ko] (backward: out = in . W)
+        for (int idx = threadIdx.x; idx < KIP * LDW; idx += blockDim.x) {
+            int kk = idx / LDW, n = idx - kk * LDW;
+            Wt[idx] = (kk < ki && n < ko) ? W[(size_t)kk * ld_w + n] : 0.0f;
+        }
+    } else {
+        load_wt(Wt, KIP, LDW, W, ld_w, ki, ko);
+    }
     for (int n = threadIdx.x; n < LDW; n += blockDim.x)
         bias[n] = (b != nullptr && n < ko) ? b[n] : 0.0f;
     const int rg = threadIdx.x >> 4, cg = threadIdx.x & 15;
@@ -65,9 +73,11 @@ linear_fwd_kernel(const float *__restrict__ in, int ld_in, int rows, int ki,
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int n = 4 * cg + 64 * j + c;
-                    if (n < ko)
-                        out[(size_t)r * ld_out + n] =
-                            apply_act(acc[i][j][c] + bias[n], act);
+                    if (n < ko) {
+                        float v = apply_act(acc[i][j][c] + bias[n], act);
+                        float *dst = &out[(size_t)r * ld_out + n];
+                        *dst = accumulate ? *dst + v : v;
+                    }
                 }
         }
     }
@@ -585,15 +595,16 @@ __global__ void gn_finalize_kernel(const float *__restrict__ partial, int nblock
     }
 }
 
-static int persistent_grid(int work_items, int blocks_per_sm) {
+int persistent_grid(int work_items, int blocks_per_sm) {
     int g = num_sms() * blocks_per_sm;
     if (work_items < g) g = work_items;
     return g < 1 ? 1 : g;
 }
 
-static int launch_linear(const float *in, int ld_in, int rows, int ki,
-                         const float *w, int ld_w, const float *b, int ko,
-                         int act, float *out, int ld_out, cudaStream_t st) {
+int launch_linear(const float *in, int ld_in, int rows, int ki,
+                  const float *w, int ld_w, const float *b, int ko,
+                  int act, float *out, int ld_out, cudaStream_t st,
+                  int w_in_major, int accumulate) {
     if (rows == 0) return PVS_OK;
     const int kip = (ki + 3) & ~3;
     const int nj4 = ko <= 64 ? 1 : 2;
@@ -608,14 +619,16 @@ static int launch_linear(const float *in, int ld_in, int rows, int ki,
                                             (int)smem));
         if (rc) return rc;
         linear_fwd_kernel<1><<<grid, FWD_THREADS, smem, st>>>(
-            in, ld_in, rows, ki, w, ld_w, b, ko, act, out, ld_out);
+            in, ld_in, rows, ki, w, ld_w, b, ko, act, out, ld_out, w_in_major,
+            accumulate);
     } else {
         rc = cuda_call(cudaFuncSetAttribute(linear_fwd_kernel<2>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)smem));
         if (rc) return rc;
         linear_fwd_kernel<2><<<grid, FWD_THREADS, smem, st>>>(
-            in, ld_in, rows, ki, w, ld_w, b, ko, act, out, ld_out);
+            in, ld_in, rows, ki, w, ld_w, b, ko, act, out, ld_out, w_in_major,
+            accumulate);
     }
     return check_launch();
 }
@@ -630,6 +643,10 @@ static int launch_edge(const EdgeArgs &a, int n_tiles_cap, cudaStream_t st) {
     const int grid = persistent_grid(n_tiles_cap, 2);
     egnn_edge_fwd_kernel<KP><<<grid, FWD_THREADS, smem, st>>>(a);
     return check_launch();
+}
+
+int launch_edge_fp32_k64(const EdgeArgs &a, int n_tiles_cap, cudaStream_t st) {
+    return launch_edge<64>(a, n_tiles_cap, st);
 }
 
 template <int KP>

@@ -33,6 +33,7 @@ class _LinearFn(torch.autograd.Function):
                 _cabi.ACT[act], ptr(out), ko, stream()), 'pvs_linear_fwd')
         ctx.act = act
         ctx.has_bias = bias is not None
+        ctx.bias_ref = b
         ctx.save_for_backward(inp, w, out)
         return out
 

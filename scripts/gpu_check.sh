@@ -8,7 +8,10 @@ python -c "import os; print('cpus', os.cpu_count())" >> gpurun_out/nvsmi.txt
 timeout 600 python -m pytest tests/test_gpu_tc.py -m gpu -q --tb=short --timeout 120 -p no:cacheprovider -s > gpurun_out/pytest_tc.log 2>&1
 echo "pytest tc exit $?" >> gpurun_out/pytest_tc.log
 tail -30 gpurun_out/pytest_tc.log
-timeout 1200 python -m pytest tests -m gpu -q --tb=short --timeout 300 -p no:cacheprovider --deselect tests/test_gpu_tc.py > gpurun_out/pytest_gpu.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_backward.py -m gpu -q --tb=short --timeout 120 -p no:cacheprovider > gpurun_out/pytest_bwd.log 2>&1
+echo "pytest bwd exit $?" >> gpurun_out/pytest_bwd.log
+tail -40 gpurun_out/pytest_bwd.log
+timeout 1200 python -m pytest tests -m gpu -q --tb=short --timeout 300 -p no:cacheprovider --deselect tests/test_gpu_tc.py --deselect tests/test_gpu_backward.py > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -15 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1

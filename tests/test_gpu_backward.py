@@ -1,0 +1,157 @@
+"""K3 (backward) on the GPU through the C ABI: parameter and input gradients
+against the reference's own autograd (golden fixtures) and against autograd of
+the CPU oracle on seeded inputs.
+
+Tolerance: max |g - g_ref| <= 2e-4 * max|g_ref| + 2e-6 per parameter tensor
+(fp32 sums over ~1e5 edges in a different order than the reference)."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers
+from tests import gpu_helpers as gh
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, want, name, rtol=2e-4, atol=2e-6):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, name
+    err = float(np.max(np.abs(got - want)))
+    bound = rtol * float(np.max(np.abs(want))) + atol
+    assert err <= bound, f'{name}: err {err:.3e} > {bound:.3e}'
+
+
+@pytest.mark.parametrize('name', ['cfg3_k32', 'alloff_multitask'])
+def test_param_grads_vs_reference_golden(name):
+    model, g = gh.cuda_model(name, 'classification')
+    model.train()
+    graph = gh.cuda_graph(g)
+    out = model(graph).reshape(-1)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(
+        out, graph.y.reshape(-1))
+    loss.backward()
+    assert abs(float(loss) - float(g['grad.loss'][0])) < 1e-5
+    checked = 0
+    for pname, p in model.named_parameters():
+        key = 'grad.' + pname
+        if key not in g:
+            continue
+        assert p.grad is not None, pname
+        _close(p.grad.cpu().numpy(), g[key], pname)
+        checked += 1
+    assert checked > 10
+
+
+VARIANTS = {
+    'cfg3_k64': dict(k=64, num_layers=3, edge_attention=True,
+                     node_attention=True, residual=True, normalize=True,
+                     tanh=True),
+    'k48_relu_att_noresid': dict(k=48, num_layers=2, edge_attention=True,
+                                 node_attention=True, residual=False,
+                                 normalize=False, tanh=False,
+                                 attention_activation_fn='relu'),
+    'edge_residual_plain': dict(k=32, num_layers=3, edge_attention=True,
+                                node_attention=False, residual=True,
+                                edge_residual=True, normalize=True, tanh=True,
+                                attention_activation_fn='tanh'),
+    'rezero': dict(k=32, num_layers=3, edge_attention=False,
+                   node_attention=True, residual=True, edge_residual=True,
+                   rezero=True, normalize=True, tanh=True),
+    'gated': dict(k=32, num_layers=3, edge_attention=True, node_attention=True,
+                  residual=True, edge_residual=True, gated_residual=True,
+                  normalize=True, tanh=False,
+                  attention_activation_fn='silu'),
+    'perminv_static': dict(k=32, num_layers=2, edge_attention=True,
+                           node_attention=False, residual=True,
+                           normalize=True, tanh=True,
+                           permutation_invariance=True, update_coords=False),
+}
+
+
+@pytest.mark.parametrize('vname', sorted(VARIANTS))
+def test_grads_vs_oracle_autograd(vname):
+    kw = dict(dim_input=13, dim_output=1, graphnorm=False, **VARIANTS[vname])
+    model = gh.build_model(kw, seed=7, coord_gain=1.0)
+    gen = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for pname, p in model.named_parameters():
+            if 'gate_parameter' in pname:
+                p.copy_(torch.rand(1, generator=gen).cuda() * 0.8 + 0.1)
+    model.train()
+    radii = (4.0, 2.0) if vname == 'k48_relu_att_noresid' else (4.0, 4.0)
+    graph = gh.synthetic_graph(900, 3, 250, 15, radii=radii, ragged=True)
+    y = torch.tensor([1.0, 0.0, 1.0], device='cuda')
+    pos0 = graph.pos.clone()
+    graph.pos = graph.pos.clone().requires_grad_(True)
+    out = model(graph).reshape(-1)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(out, y)
+    loss.backward()
+
+    # oracle autograd on the CPU with the same weights
+    from oracle import egnn_oracle
+    sd = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point())
+          for k, v in model.state_dict().items()}
+    pos_ref = pos0.cpu().clone().requires_grad_(True)
+    want, _ = egnn_oracle.model_forward(
+        sd, graph.x.cpu(), graph.edge_index.cpu(), pos_ref,
+        graph.edge_attr.cpu(), graph.batch.cpu(), num_layers=kw['num_layers'],
+        **helpers.oracle_kwargs(kw))
+    loss_ref = torch.nn.functional.binary_cross_entropy_with_logits(
+        want.reshape(-1), y.cpu())
+    loss_ref.backward()
+    assert abs(float(loss) - float(loss_ref)) < 1e-5
+    for pname, p in model.named_parameters():
+        ref = sd[pname].grad
+        if ref is None:
+            continue
+        assert p.grad is not None, pname
+        _close(p.grad.cpu().numpy(), ref.numpy(), pname)
+    if pos_ref.grad is not None and kw.get('update_coords', True):
+        _close(graph.pos.grad.cpu().numpy(), pos_ref.grad.numpy(), 'pos')
+    elif pos_ref.grad is not None:
+        _close(graph.pos.grad.cpu().numpy(), pos_ref.grad.numpy(), 'pos')
+
+
+def test_backward_is_deterministic():
+    kw = dict(dim_input=13, dim_output=1, graphnorm=False, **VARIANTS['cfg3_k64'])
+    grads = []
+    for _ in range(2):
+        model = gh.build_model(kw, seed=7, coord_gain=1.0).train()
+        graph = gh.synthetic_graph(900, 2, 400, 15)
+        loss = model(graph).sum()
+        loss.backward()
+        grads.append(torch.cat([p.grad.reshape(-1) for p in model.parameters()
+                                if p.grad is not None]))
+    assert torch.equal(grads[0], grads[1])
+
+
+def test_training_step_reduces_loss():
+    """A few Adam steps through the reference-style backprop()."""
+    kw = dict(dim_input=13, dim_output=1, graphnorm=False, **VARIANTS['cfg3_k64'])
+    import pointvs_b200 as pv
+    from pathlib import Path
+    torch.manual_seed(0)
+    model = pv.SartorrasEGNN(Path('/tmp/pvs_test'), 1e-3, 0, None, None,
+                             silent=True, **kw).cuda().train()
+    graph = gh.synthetic_graph(50, 4, 300, 15)
+    graph.y = torch.tensor([1.0, 0.0, 1.0, 0.0], device='cuda')
+    graph.lig_fname = graph.rec_fname = ['x'] * 4
+    pos = graph.pos.clone()
+    losses = []
+    for _ in range(6):
+        graph.pos = pos.clone()
+        y_pred, y_true, _, _ = model.unpack_input_data_and_predict(graph)
+        losses.append(model.backprop(y_true, y_pred))
+    assert losses[-1] < losses[0]
+
+
+def test_graphnorm_training_fails_loudly():
+    kw = dict(dim_input=13, dim_output=1, k=32, num_layers=1, graphnorm=True)
+    model = gh.build_model(kw).train()
+    out = model(gh.synthetic_graph(1, 2, 100, 10))
+    with pytest.raises(NotImplementedError):
+        out.sum().backward()
