@@ -33,7 +33,7 @@ extern "C" {
 int pvs_version(void) { return PVS_VERSION; }
 
 uint32_t pvs_capabilities(void) {
-    return PVS_CAP_FWD_FP32 | PVS_CAP_FWD_TCGEN05;
+    return PVS_CAP_FWD_FP32 | PVS_CAP_FWD_TCGEN05 | PVS_CAP_BWD_FP32;
 }
 
 const char *pvs_status_string(int status) {

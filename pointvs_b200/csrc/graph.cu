@@ -118,7 +118,7 @@ __device__ int smem_scan_excl(int *data, int n, int *warp_buf) {
 // ---------------------------------------------------------------------------
 // K1: radius graph.  One CTA per complex.
 // ---------------------------------------------------------------------------
-constexpr int RG_THREADS = 256;
+constexpr int RG_THREADS = 512;
 constexpr int RG_WARPS = RG_THREADS / 32;
 constexpr int RG_MAX_DIM = 16;
 constexpr int RG_MAX_CELLS = RG_MAX_DIM * RG_MAX_DIM * RG_MAX_DIM;
@@ -132,12 +132,15 @@ struct RgSmem {
     int misc[4];
 };
 
-static size_t rg_smem_bytes(int max_n, bool with_prefix) {
+static size_t rg_smem_bytes(int max_n, bool with_prefix, bool stage) {
     size_t words = (size_t)(max_n + 31) / 32;
     size_t b = sizeof(RgSmem);
     b += (size_t)max_n * sizeof(int);                 // sorted_idx
     b += (size_t)RG_WARPS * 2 * words * sizeof(int);  // per-warp bit masks
-    if (with_prefix) b += (size_t)max_n * sizeof(int);
+    b += (size_t)max_n * sizeof(int);                 // prefix_inter (fill + ref_pos)
+    (void)with_prefix;
+    b = (b + 7) & ~(size_t)7;
+    if (stage) b += (size_t)max_n * (3 * sizeof(double) + sizeof(int));  // cell-sorted copy
     return b;
 }
 
@@ -156,7 +159,7 @@ radius_graph_kernel(const double *__restrict__ coords,
                     const int32_t *__restrict__ n_inter_in,
                     const int32_t *__restrict__ row_ptr,
                     int32_t *__restrict__ col, uint8_t *__restrict__ attr,
-                    int32_t *__restrict__ ref_pos, int max_n) {
+                    int32_t *__restrict__ ref_pos, int max_n, int stage) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RgSmem &S = *reinterpret_cast<RgSmem *>(smem_raw);
     const int n0 = complex_ptr[blockIdx.x];
@@ -166,6 +169,11 @@ radius_graph_kernel(const double *__restrict__ coords,
     int *sorted_idx = reinterpret_cast<int *>(smem_raw + sizeof(RgSmem));
     unsigned *masks = reinterpret_cast<unsigned *>(sorted_idx + max_n);
     int *prefix_inter = reinterpret_cast<int *>(masks + (size_t)RG_WARPS * 2 * words);
+    // cell-sorted copy of the coordinates / bp: the neighbour loop then reads
+    // contiguous shared-memory ranges instead of chasing sorted_idx into global
+    double *scoord = reinterpret_cast<double *>(
+        (reinterpret_cast<uintptr_t>(prefix_inter + max_n) + 7) & ~(uintptr_t)7);
+    int *sbp = reinterpret_cast<int *>(scoord + 3 * (size_t)max_n);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *cx = coords + 3 * (size_t)n0;
     const int32_t *cbp = bp + n0;
@@ -244,8 +252,14 @@ radius_graph_kernel(const double *__restrict__ coords,
         int c = cell_coord(cx[3 * i], blo[0], cs[0], dim[0]) +
                 dim[0] * (cell_coord(cx[3 * i + 1], blo[1], cs[1], dim[1]) +
                           dim[1] * cell_coord(cx[3 * i + 2], blo[2], cs[2], dim[2]));
-        int p = atomicAdd(&S.cell_fill[c], 1);
-        sorted_idx[S.cell_start[c] + p] = i;
+        int p = S.cell_start[c] + atomicAdd(&S.cell_fill[c], 1);
+        sorted_idx[p] = i;
+        if (stage) {
+            scoord[3 * p] = cx[3 * i];
+            scoord[3 * p + 1] = cx[3 * i + 1];
+            scoord[3 * p + 2] = cx[3 * i + 2];
+            sbp[p] = cbp[i];
+        }
     }
     int e_base_c = 0, total_inter_c = 0;
     if (FILL && ref_pos != nullptr) {
@@ -281,18 +295,27 @@ radius_graph_kernel(const double *__restrict__ coords,
                 int cb = dim[0] * (c1 + dim[1] * c2);
                 int p_end = S.cell_start[cb + x_hi + 1];
                 for (int p = S.cell_start[cb + x_lo] + lane; p < p_end; p += 32) {
-                    int j = sorted_idx[p];
+                    const int j = sorted_idx[p];
+                    double xj, yj, zj;
+                    int bj;
+                    if (stage) {
+                        xj = scoord[3 * p]; yj = scoord[3 * p + 1]; zj = scoord[3 * p + 2];
+                        bj = sbp[p];
+                    } else {
+                        xj = cx[3 * j]; yj = cx[3 * j + 1]; zj = cx[3 * j + 2];
+                        bj = cbp[j];
+                    }
                     // scipy cdist (preprocessing.py:108):
                     // sqrt((dx*dx + dy*dy) + dz*dz), no FMA contraction
-                    double ddx = __dsub_rn(xi, cx[3 * j]);
-                    double ddy = __dsub_rn(yi, cx[3 * j + 1]);
-                    double ddz = __dsub_rn(zi, cx[3 * j + 2]);
+                    double ddx = __dsub_rn(xi, xj);
+                    double ddy = __dsub_rn(yi, yj);
+                    double ddz = __dsub_rn(zi, zj);
                     double d = __dsqrt_rn(__dadd_rn(
                         __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)),
                         __dmul_rn(ddz, ddz)));
                     bool pos = d > 1e-7;
                     unsigned bit = 1u << (j & 31);
-                    if (pos && d < r_inter && cbp[j] != bi)
+                    if (pos && d < r_inter && bj != bi)
                         atomicOr(&m_inter[j >> 5], bit);   // :110-117
                     if (pos && d < r_intra)
                         atomicOr(&m_intra[j >> 5], bit);   // :119-121
@@ -568,7 +591,12 @@ int pvs_radius_graph_count(const double *coords, const int32_t *bp,
         return PVS_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_nodes > 0 && n_complexes > 0) {
-        size_t smem = rg_smem_bytes(max_complex_nodes, false);
+        int stage = 1;
+        size_t smem = rg_smem_bytes(max_complex_nodes, false, true);
+        if (smem > (size_t)max_optin_smem()) {
+            stage = 0;
+            smem = rg_smem_bytes(max_complex_nodes, false, false);
+        }
         if (smem > (size_t)max_optin_smem()) return PVS_ERR_TOO_LARGE;
         rc = cuda_call(cudaFuncSetAttribute(
             radius_graph_kernel<false>,
@@ -576,7 +604,7 @@ int pvs_radius_graph_count(const double *coords, const int32_t *bp,
         if (rc) return rc;
         radius_graph_kernel<false><<<n_complexes, RG_THREADS, smem, st>>>(
             coords, bp, complex_ptr, inter_radius, intra_radius, deg, n_inter,
-            nullptr, nullptr, nullptr, nullptr, nullptr, max_complex_nodes);
+            nullptr, nullptr, nullptr, nullptr, nullptr, max_complex_nodes, stage);
         rc = check_launch();
         if (rc) return rc;
     }
@@ -595,7 +623,12 @@ int pvs_radius_graph_fill(const double *coords, const int32_t *bp,
     if (rc) return rc;
     if (n_nodes == 0 || n_complexes == 0) return PVS_OK;
     if (!n_inter || !row_ptr || !col || !attr) return PVS_ERR_INVALID_ARG;
-    size_t smem = rg_smem_bytes(max_complex_nodes, ref_pos != nullptr);
+    int stage = 1;
+    size_t smem = rg_smem_bytes(max_complex_nodes, ref_pos != nullptr, true);
+    if (smem > (size_t)max_optin_smem()) {
+        stage = 0;
+        smem = rg_smem_bytes(max_complex_nodes, ref_pos != nullptr, false);
+    }
     if (smem > (size_t)max_optin_smem()) return PVS_ERR_TOO_LARGE;
     rc = cuda_call(cudaFuncSetAttribute(
         radius_graph_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -604,7 +637,7 @@ int pvs_radius_graph_fill(const double *coords, const int32_t *bp,
     radius_graph_kernel<true><<<n_complexes, RG_THREADS, smem,
                                 (cudaStream_t)stream>>>(
         coords, bp, complex_ptr, inter_radius, intra_radius, nullptr, nullptr,
-        n_inter, row_ptr, col, attr, ref_pos, max_complex_nodes);
+        n_inter, row_ptr, col, attr, ref_pos, max_complex_nodes, stage);
     return check_launch();
 }
 
