@@ -19,35 +19,52 @@
 //               shared memory; the coordinate GEMM overlaps the message
 //               segment-reduce.
 //
-// 128 threads per CTA, ~74 KB shared memory and 128 TMEM columns per CTA, three
-// CTAs per SM so one CTA's MMA/epilogue overlaps another's gather.
+// One persistent CTA per SM holds G = 5 independent 4-warp groups (640 threads).
+// The groups share the weight tiles and each own an A-tile pair, 64 TMEM columns,
+// an mbarrier and a named barrier; they walk different tiles and drift out of
+// phase, so one group's gather latency hides behind another's MUFU-heavy
+// epilogue (the first version, 3 CTAs x 4 warps per SM, issued on only 38 % of
+// cycles with the gather as the top stall: profiles/r01_c_*).
 #include <cuda_bf16.h>
 
 #include "egnn_common.cuh"
 
 namespace pvs {
 
-constexpr int TC_THREADS = 128;
+constexpr int TC_GROUP_THREADS = 128;
+constexpr int TC_GROUPS = 5;
+constexpr int TC_THREADS = TC_GROUP_THREADS * TC_GROUPS;
 constexpr int TC_K = 64;          // padded hidden width of the tile
-constexpr uint32_t TC_TMEM_COLS = 128;
+constexpr uint32_t TC_TMEM_COLS = 512;   // whole TMEM: one CTA per SM
+constexpr uint32_t TC_GROUP_COLS = 64;   // D1 and D2 alias (never live together)
+
+struct TcGroupMisc {
+    float e_rad[TE], e_dx[TE], e_dy[TE], e_dz[TE], e_z[TE], e_c[TE];
+    int e_col[TE];
+    uint8_t e_rowl[TE], e_attr[TE];
+    int rp[TN + 1];
+    float xsum[TN][3];
+    uint64_t mbar;
+};
 
 struct __align__(1024) TcSmem {
     // swizzled bf16 tiles, each 1024-byte aligned
-    uint8_t A_hi[TE * 128];
-    uint8_t A_lo[TE * 128];
+    uint8_t A_hi[TC_GROUPS][TE * 128];
+    uint8_t A_lo[TC_GROUPS][TE * 128];
     uint8_t W2_hi[TC_K * 128];
     uint8_t W2_lo[TC_K * 128];
     uint8_t Wc1_hi[TC_K * 128];
     uint8_t Wc1_lo[TC_K * 128];
     float b2[64], bc1[64], wc2[64], wa[64], wr[64];
     float T[PVS_MAX_EDGE_CLASSES][64];
-    float e_rad[TE], e_dx[TE], e_dy[TE], e_dz[TE], e_z[TE], e_c[TE];
-    int e_rowl[TE], e_col[TE], e_attr[TE];
-    int rp[TN + 1];
-    float xsum[TN][3];
-    uint64_t mbar;
+    TcGroupMisc grp[TC_GROUPS];
     uint32_t tmem_base;
 };
+
+// barrier among the 128 threads of one group (id 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(TC_GROUP_THREADS) : "memory");
+}
 
 // ---- PTX wrappers -----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -204,25 +221,29 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_base, uint32_t d_col,
 }
 
 template <bool X3>
-__global__ void __launch_bounds__(TC_THREADS, 3)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 egnn_edge_tc_kernel(const EdgeArgs a) {
     // SWIZZLE_128B tiles need 1024-byte alignment; the kernel has no static
     // shared memory, so the dynamic window starts at its (aligned) base.
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     TcSmem &S = *reinterpret_cast<TcSmem *>(smem_dyn);
     if ((smem_u32(smem_dyn) & 1023u) != 0u) __trap();
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = threadIdx.x / TC_GROUP_THREADS;          // group
+    const int tid = threadIdx.x % TC_GROUP_THREADS;        // thread in group
+    const int lane = tid & 31, warp = tid >> 5;            // warp in group
+    TcGroupMisc &Gm = S.grp[g];
+    uint8_t *A_hi = S.A_hi[g], *A_lo = S.A_lo[g];
     const int k = a.k;
     const bool f_att = a.flags & PVS_F_EDGE_ATTENTION;
     const bool f_softmax = f_att && (a.flags & PVS_F_SOFTMAX_ATTENTION);
     const bool f_coords = (a.flags & PVS_F_UPDATE_COORDS) && a.x_out != nullptr;
     const bool f_eres = (a.flags & PVS_F_EDGE_RESIDUAL) && a.m_prev != nullptr;
 
-    // ---- one-time setup ----
+    // ---- one-time setup (whole CTA) ----
     load_weight_tiles<X3>(S.W2_hi, S.W2_lo, a.edge_w2, k);
     load_weight_tiles<X3>(S.Wc1_hi, S.Wc1_lo, a.coord_w1, k);
     const int col_r = (a.flags & PVS_F_PERM_INVARIANT) ? k : 2 * k;
-    for (int n = tid; n < 64; n += TC_THREADS) {
+    for (int n = threadIdx.x; n < 64; n += TC_THREADS) {
         const bool ok = n < k;
         S.b2[n] = ok ? a.edge_b2[n] : 0.0f;
         S.bc1[n] = ok ? a.coord_b1[n] : 0.0f;
@@ -233,28 +254,29 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
             S.T[c][n] = (ok && c < a.n_classes)
                             ? a.edge_w1[(size_t)n * a.in_e + col_r + 1 + c] : 0.0f;
     }
-    if (tid == 0) mbar_init(&S.mbar, 1);
-    if (warp == 0) tmem_alloc(&S.tmem_base);
+    if (tid == 0) mbar_init(&Gm.mbar, 1);
+    if (threadIdx.x < 32) tmem_alloc(&S.tmem_base);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = S.tmem_base;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem_grp = tmem_base + (uint32_t)g * TC_GROUP_COLS;
+    const uint32_t tmem_lane = tmem_grp + ((uint32_t)(warp * 32) << 16);
     uint32_t phase = 0;
     const float att_b = (f_att && a.att_b) ? a.att_b[0] : 0.0f;
     float gate = 1.0f;
     if (f_eres && a.edge_gate) gate = a.edge_gate[0];
     const int n_tiles = *a.n_tiles;
 
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x * TC_GROUPS + g; t < n_tiles; t += gridDim.x * TC_GROUPS) {
         const int n0 = a.tile_ptr[t], n1 = a.tile_ptr[t + 1];
         const int nn = n1 - n0;
-        __syncthreads();
-        for (int i = tid; i <= nn; i += TC_THREADS) S.rp[i] = a.row_ptr[n0 + i];
-        for (int i = tid; i < nn * 3; i += TC_THREADS) (&S.xsum[0][0])[i] = 0.0f;
-        __syncthreads();
-        const int e0 = S.rp[0], e1 = S.rp[nn];
+        group_sync(g);
+        for (int i = tid; i <= nn; i += TC_GROUP_THREADS) Gm.rp[i] = a.row_ptr[n0 + i];
+        for (int i = tid; i < nn * 3; i += TC_GROUP_THREADS) (&Gm.xsum[0][0])[i] = 0.0f;
+        group_sync(g);
+        const int e0 = Gm.rp[0], e1 = Gm.rp[nn];
         const int n_chunks = max(1, (e1 - e0 + TE - 1) / TE);
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int c0 = e0 + ch * TE;
@@ -266,7 +288,7 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                     int lo = 0, hi = nn;
                     while (hi - lo > 1) {
                         int mid = (lo + hi) >> 1;
-                        if (S.rp[mid] <= e) lo = mid; else hi = mid;
+                        if (Gm.rp[mid] <= e) lo = mid; else hi = mid;
                     }
                     const int i = n0 + lo, j = a.col[e];
                     float dx = a.x_in[3 * i] - a.x_in[3 * j];
@@ -277,13 +299,13 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                         float inv = 1.0f / (sqrtf(r) + 1e-8f);
                         dx *= inv; dy *= inv; dz *= inv;
                     }
-                    S.e_rowl[tid] = lo;
-                    S.e_col[tid] = j;
-                    S.e_attr[tid] = a.attr ? a.attr[e] : 0;
-                    S.e_rad[tid] = r;
-                    S.e_dx[tid] = dx; S.e_dy[tid] = dy; S.e_dz[tid] = dz;
+                    Gm.e_rowl[tid] = (uint8_t)lo;
+                    Gm.e_col[tid] = j;
+                    Gm.e_attr[tid] = a.attr ? a.attr[e] : 0;
+                    Gm.e_rad[tid] = r;
+                    Gm.e_dx[tid] = dx; Gm.e_dy[tid] = dy; Gm.e_dz[tid] = dz;
                 }
-                __syncthreads();
+                group_sync(g);
                 // ---- stage 1: s1 = silu(P_i + Q_j + w_r r + T[a]) -> A tile.
                 // 8 lanes per edge row (one 16-byte chunk each), 16 rows a pass:
                 // every LDG.128 warp instruction reads 4 full 256-byte rows.
@@ -298,14 +320,14 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                         float v[8];
                         if (r < ne) {
                             const float4 *pp = reinterpret_cast<const float4 *>(
-                                a.P + (size_t)(n0 + S.e_rowl[r]) * TC_K + 8 * c);
+                                a.P + (size_t)(n0 + Gm.e_rowl[r]) * TC_K + 8 * c);
                             const float4 *qq = reinterpret_cast<const float4 *>(
-                                a.Q + (size_t)S.e_col[r] * TC_K + 8 * c);
+                                a.Q + (size_t)Gm.e_col[r] * TC_K + 8 * c);
                             const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
                             const float4 q0 = __ldg(qq), q1 = __ldg(qq + 1);
-                            const float rad = S.e_rad[r];
+                            const float rad = Gm.e_rad[r];
                             const float4 *t4 = reinterpret_cast<const float4 *>(
-                                &S.T[S.e_attr[r]][8 * c]);
+                                &S.T[Gm.e_attr[r]][8 * c]);
                             const float4 ta = t4[0], tb = t4[1];
                             const float tt[8] = {ta.x, ta.y, ta.z, ta.w,
                                                  tb.x, tb.y, tb.z, tb.w};
@@ -321,19 +343,19 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                         }
                         uint4 hi, lo;
                         split8<X3>(v, hi, lo);
-                        *reinterpret_cast<uint4 *>(S.A_hi + swz(r, c)) = hi;
-                        if (X3) *reinterpret_cast<uint4 *>(S.A_lo + swz(r, c)) = lo;
+                        *reinterpret_cast<uint4 *>(A_hi + swz(r, c)) = hi;
+                        if (X3) *reinterpret_cast<uint4 *>(A_lo + swz(r, c)) = lo;
                     }
                 }
                 fence_proxy_async();
                 tc_fence_before();
-                __syncthreads();
+                group_sync(g);
                 // ---- GEMM 1: t2 = s1 . W2^T ----
                 if (tid == 0) {
                     tc_fence_after();
-                    issue_gemm<X3>(tmem_base, 0, S.A_hi, S.A_lo, S.W2_hi, S.W2_lo, &S.mbar);
+                    issue_gemm<X3>(tmem_grp, 0, A_hi, A_lo, S.W2_hi, S.W2_lo, &Gm.mbar);
                 }
-                mbar_wait(&S.mbar, phase);
+                mbar_wait(&Gm.mbar, phase);
                 phase ^= 1;
                 tc_fence_after();
                 // ---- epilogue 1: m = silu(t2 + b2) (+ edge residual), the
@@ -369,8 +391,8 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                                         float mp = a.m_prev[(size_t)(c0 + r) * k + n];
                                         if (a.flags & PVS_F_REZERO) mv[i] = mp + gate * mv[i];
                                         else if (a.flags & PVS_F_GATED_RESIDUAL) {
-                                            float g = fmaxf(gate, 0.0f);
-                                            mv[i] = g * mv[i] + (1.0f - g) * mp;
+                                            float gg = fmaxf(gate, 0.0f);
+                                            mv[i] = gg * mv[i] + (1.0f - gg) * mp;
                                         } else mv[i] = mv[i] + mp;
                                     }
                                 }
@@ -380,8 +402,8 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                             uint4 hi, lo;
                             split8<X3>(mv, hi, lo);
                             const int c = 2 * q + hlf;
-                            *reinterpret_cast<uint4 *>(S.A_hi + swz(r, c)) = hi;
-                            if (X3) *reinterpret_cast<uint4 *>(S.A_lo + swz(r, c)) = lo;
+                            *reinterpret_cast<uint4 *>(A_hi + swz(r, c)) = hi;
+                            if (X3) *reinterpret_cast<uint4 *>(A_lo + swz(r, c)) = lo;
                         }
                     }
                     // attention value per edge (alpha, or the raw logit when
@@ -392,36 +414,36 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                         al = f_softmax ? z : apply_act(z, a.att_act);
                         if (a.att_out && r < ne) a.att_out[c0 + r] = al;
                     }
-                    S.e_z[r] = al;
+                    Gm.e_z[r] = al;
                 }
                 fence_proxy_async();
                 tc_fence_before();
-                __syncthreads();
-                // ---- GEMM 2 (coordinate MLP) runs while the messages are
+                group_sync(g);
+                // ---- GEMM 2 (coordinate MLP; reuses the D columns, which
+                // epilogue 1 has fully read) runs while the messages are
                 // reduced below ----
                 if (f_coords && tid == 0) {
                     tc_fence_after();
-                    issue_gemm<X3>(tmem_base, 64, S.A_hi, S.A_lo, S.Wc1_hi, S.Wc1_lo,
-                                   &S.mbar);
+                    issue_gemm<X3>(tmem_grp, 0, A_hi, A_lo, S.Wc1_hi, S.Wc1_lo, &Gm.mbar);
                 }
             }
             // ---- M_i = sum_e alpha_e m_e over dst segments (warp per node) ----
             if (!f_softmax) {
-                for (int nl = warp; nl < nn; nl += TC_THREADS / 32) {
-                    const int lo = max(S.rp[nl], c0) - c0;
-                    const int hi = min(S.rp[nl + 1], c0 + TE) - c0;
+                for (int nl = warp; nl < nn; nl += TC_GROUP_THREADS / 32) {
+                    const int lo = max(Gm.rp[nl], c0) - c0;
+                    const int hi = min(Gm.rp[nl + 1], c0 + TE) - c0;
                     float s0 = 0.0f, s1 = 0.0f;
                     for (int el = lo; el < hi; ++el) {
                         const uint32_t off = swz(el, lane >> 2) + ((lane & 3) << 2);
-                        const uint32_t h = *reinterpret_cast<const uint32_t *>(S.A_hi + off);
+                        const uint32_t h = *reinterpret_cast<const uint32_t *>(A_hi + off);
                         float m0 = __uint_as_float(h << 16);
                         float m1 = __uint_as_float(h & 0xffff0000u);
                         if (X3) {
-                            const uint32_t l = *reinterpret_cast<const uint32_t *>(S.A_lo + off);
+                            const uint32_t l = *reinterpret_cast<const uint32_t *>(A_lo + off);
                             m0 += __uint_as_float(l << 16);
                             m1 += __uint_as_float(l & 0xffff0000u);
                         }
-                        const float al = S.e_z[el];
+                        const float al = Gm.e_z[el];
                         s0 = fmaf(al, m0, s0);
                         s1 = fmaf(al, m1, s1);
                     }
@@ -437,14 +459,14 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
             }
             // ---- messages out (edge residual of the next layer / softmax) ----
             if (a.m_out != nullptr) {
-                for (int idx = tid; idx < ne * (TC_K / 2); idx += TC_THREADS) {
+                for (int idx = tid; idx < ne * (TC_K / 2); idx += TC_GROUP_THREADS) {
                     const int el = idx >> 5, w = idx & 31;
                     const uint32_t off = swz(el, w >> 2) + ((w & 3) << 2);
-                    const uint32_t h = *reinterpret_cast<const uint32_t *>(S.A_hi + off);
+                    const uint32_t h = *reinterpret_cast<const uint32_t *>(A_hi + off);
                     float m0 = __uint_as_float(h << 16);
                     float m1 = __uint_as_float(h & 0xffff0000u);
                     if (X3) {
-                        const uint32_t l = *reinterpret_cast<const uint32_t *>(S.A_lo + off);
+                        const uint32_t l = *reinterpret_cast<const uint32_t *>(A_lo + off);
                         m0 += __uint_as_float(l << 16);
                         m1 += __uint_as_float(l & 0xffff0000u);
                     }
@@ -455,14 +477,14 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
             }
             if (ne > 0 && f_coords) {
                 // ---- epilogue 2: c = [tanh](wc2 . silu(Wc1 m + bc1)) ----
-                mbar_wait(&S.mbar, phase);
+                mbar_wait(&Gm.mbar, phase);
                 phase ^= 1;
                 tc_fence_after();
                 float dot = 0.0f;
 #pragma unroll 1
                 for (int q = 0; q < 4; ++q) {
                     float acc[16];
-                    tmem_ld16(tmem_lane + 64 + 16 * q, acc);
+                    tmem_ld16(tmem_lane + 16 * q, acc);
 #pragma unroll
                     for (int v4 = 0; v4 < 4; ++v4) {
                         const float4 bb = *reinterpret_cast<const float4 *>(&S.bc1[16 * q + 4 * v4]);
@@ -473,36 +495,36 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                         dot = fmaf(ww.w, silu_mode<X3>(acc[4 * v4 + 3] + bb.w), dot);
                     }
                 }
-                S.e_c[tid] = (a.flags & PVS_F_TANH) ? tanhf(dot) : dot;
+                Gm.e_c[tid] = (a.flags & PVS_F_TANH) ? tanhf(dot) : dot;
                 tc_fence_before();
             }
-            __syncthreads();
+            group_sync(g);
             // ---- coordinate messages summed per node ----
             if (f_coords && tid < nn) {
-                const int lo = max(S.rp[tid], c0) - c0;
-                const int hi = min(S.rp[tid + 1], c0 + TE) - c0;
+                const int lo = max(Gm.rp[tid], c0) - c0;
+                const int hi = min(Gm.rp[tid + 1], c0 + TE) - c0;
                 float sx = 0.f, sy = 0.f, sz = 0.f;
                 for (int el = lo; el < hi; ++el) {
-                    const float c = S.e_c[el];
-                    sx = fmaf(S.e_dx[el], c, sx);
-                    sy = fmaf(S.e_dy[el], c, sy);
-                    sz = fmaf(S.e_dz[el], c, sz);
+                    const float c = Gm.e_c[el];
+                    sx = fmaf(Gm.e_dx[el], c, sx);
+                    sy = fmaf(Gm.e_dy[el], c, sy);
+                    sz = fmaf(Gm.e_dz[el], c, sz);
                 }
-                S.xsum[tid][0] += sx;
-                S.xsum[tid][1] += sy;
-                S.xsum[tid][2] += sz;
+                Gm.xsum[tid][0] += sx;
+                Gm.xsum[tid][1] += sy;
+                Gm.xsum[tid][2] += sz;
             }
-            __syncthreads();
+            group_sync(g);
         }
         if (a.x_out != nullptr && tid < nn) {
             const int i = n0 + tid;
-            const int cnt = S.rp[tid + 1] - S.rp[tid];
+            const int cnt = Gm.rp[tid + 1] - Gm.rp[tid];
             const float inv = 1.0f / (float)(cnt > 0 ? cnt : 1);
             float ax = 0.f, ay = 0.f, az = 0.f;
             if (f_coords) {
-                ax = S.xsum[tid][0] * inv;
-                ay = S.xsum[tid][1] * inv;
-                az = S.xsum[tid][2] * inv;
+                ax = Gm.xsum[tid][0] * inv;
+                ay = Gm.xsum[tid][1] * inv;
+                az = Gm.xsum[tid][2] * inv;
             }
             a.x_out[3 * i] = a.x_in[3 * i] + ax;
             a.x_out[3 * i + 1] = a.x_in[3 * i + 1] + ay;
@@ -512,13 +534,14 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base);
+    if (threadIdx.x < 32) tmem_dealloc(tmem_base);
 }
 
 int launch_edge_tc(const EdgeArgs &a, int n_tiles_cap, int mode, cudaStream_t st) {
     const size_t smem = sizeof(TcSmem);
-    int grid = num_sms() * 3;
-    if (n_tiles_cap < grid) grid = n_tiles_cap;
+    int grid = num_sms();   // one persistent CTA (5 groups) per SM
+    const int need = (n_tiles_cap + TC_GROUPS - 1) / TC_GROUPS;
+    if (need < grid) grid = need;
     if (grid < 1) grid = 1;
     int rc;
     if (mode == PVS_MATH_BF16X3) {

@@ -271,6 +271,11 @@ radius_graph_kernel(const double *__restrict__ coords,
     __syncthreads();
 
     // ---- one warp per destination node ----
+    const double inter_lo = r_inter * r_inter * (1.0 - 1e-15);
+    const double inter_hi = r_inter * r_inter * (1.0 + 1e-15);
+    const double intra_lo = r_intra * r_intra * (1.0 - 1e-15);
+    const double intra_hi = r_intra * r_intra * (1.0 + 1e-15);
+    const double pos_hi = 1e-14 * (1.0 + 1e-15);
     unsigned *m_inter = masks + (size_t)warp * 2 * words;
     unsigned *m_intra = m_inter + words;
     const int nw = (n + 31) / 32;
@@ -310,14 +315,29 @@ radius_graph_kernel(const double *__restrict__ coords,
                     double ddx = __dsub_rn(xi, xj);
                     double ddy = __dsub_rn(yi, yj);
                     double ddz = __dsub_rn(zi, zj);
-                    double d = __dsqrt_rn(__dadd_rn(
+                    const double d2 = __dadd_rn(
                         __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)),
-                        __dmul_rn(ddz, ddz)));
-                    bool pos = d > 1e-7;
+                        __dmul_rn(ddz, ddz));
+                    // The reference compares the ROUNDED sqrt with the radius.
+                    // Outside a +-1e-15 relative band around r^2 the outcome is
+                    // decided by d2 alone (sqrt is monotone and correctly
+                    // rounded); only inside the band is the sqrt evaluated.
+                    bool pos, in_inter, in_intra;
+                    if (d2 > pos_hi && (d2 < inter_lo || d2 > inter_hi) &&
+                        (d2 < intra_lo || d2 > intra_hi)) {
+                        pos = true;
+                        in_inter = d2 < inter_lo;
+                        in_intra = d2 < intra_lo;
+                    } else {
+                        const double d = __dsqrt_rn(d2);
+                        pos = d > 1e-7;
+                        in_inter = d < r_inter;
+                        in_intra = d < r_intra;
+                    }
                     unsigned bit = 1u << (j & 31);
-                    if (pos && d < r_inter && bj != bi)
+                    if (pos && in_inter && bj != bi)
                         atomicOr(&m_inter[j >> 5], bit);   // :110-117
-                    if (pos && d < r_intra)
+                    if (pos && in_intra)
                         atomicOr(&m_intra[j >> 5], bit);   // :119-121
                 }
             }
