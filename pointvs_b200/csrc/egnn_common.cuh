@@ -39,5 +39,12 @@ int launch_linear(const float *in, int ld_in, int rows, int ki, const float *w,
                   int ld_out, cudaStream_t st, int w_in_major = 0,
                   int accumulate = 0);
 int persistent_grid(int work_items, int blocks_per_sm);
+// tensor-core node stages (egnn_node_tc.cu); mode = PVS_MATH_BF16X3 / BF16
+int launch_node_pre_tc(const float *h, const float *edge_w1, const float *edge_b1, float *P,
+                       float *Q, int n_nodes, int k, int in_e, int perm, int mode,
+                       cudaStream_t st);
+int launch_node_tc(const float *h_in, const float *M, float *h_out, float *natt_out,
+                   const pvs_layer_params *p, int n_nodes, int k, uint32_t flags, int att_act,
+                   int mode, cudaStream_t st);
 
 }  // namespace pvs

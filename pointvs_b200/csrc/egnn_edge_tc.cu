@@ -25,9 +25,8 @@
 // phase, so one group's gather latency hides behind another's MUFU-heavy
 // epilogue (the first version, 3 CTAs x 4 warps per SM, issued on only 38 % of
 // cycles with the gather as the top stall: profiles/r01_c_*).
-#include <cuda_bf16.h>
-
 #include "egnn_common.cuh"
+#include "tc_common.cuh"
 
 namespace pvs {
 
@@ -64,137 +63,6 @@ struct __align__(1024) TcSmem {
 // barrier among the 128 threads of one group (id 0 is __syncthreads)
 __device__ __forceinline__ void group_sync(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(TC_GROUP_THREADS) : "memory");
-}
-
-// ---- PTX wrappers -----------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-// bounded wait: a descriptor bug must fail the launch, not hang the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (done) return;
-    }
-    __trap();
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32(dst_smem)), "n"(TC_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
-                 ::"r"(taddr), "n"(TC_TMEM_COLS) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                 ::"r"(smem_u32(bar)) : "memory");
-}
-// 16 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]),
-          "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
-          "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// Shared-memory matrix descriptor, K-major, SWIZZLE_128B, 128-byte rows:
-// start address [0,14) (>>4), LBO [16,30) = 1 (unused for swizzled K-major),
-// SBO [32,46) = 1024 B between 8-row groups, version [46,48) = 1,
-// layout type [61,64) = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
-    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-    return ((uint64_t)hi << 32) | lo;
-}
-// Instruction descriptor (kind::f16): D fp32 [4,6)=1, A bf16 [7,10)=1,
-// B bf16 [10,13)=1, both K-major, N>>3 at [17,23), M>>4 at [24,29).
-constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) |
-                              ((64u >> 3) << 17) | ((128u >> 4) << 24);
-
-// byte offset of 16-byte chunk `c` (8 bf16 = channels 8c..8c+7) of row `r`
-__device__ __forceinline__ uint32_t swz(int r, int c) {
-    return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
-}
-
-// split 8 fp32 into bf16 hi (round-to-nearest) and bf16 lo = bf16(x - hi)
-template <bool WITH_LO>
-__device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        h[i] = *reinterpret_cast<uint32_t *>(&hb);
-        if (WITH_LO) {
-            float r0 = v[2 * i] - __uint_as_float(h[i] << 16);
-            float r1 = v[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
-            __nv_bfloat162 lb = __floats2bfloat162_rn(r0, r1);
-            l[i] = *reinterpret_cast<uint32_t *>(&lb);
-        } else {
-            l[i] = 0u;
-        }
-    }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-// W [k][k] fp32 (nn.Linear [out][in]) -> swizzled bf16 hi / lo B tiles
-template <bool WITH_LO>
-__device__ void load_weight_tiles(uint8_t *hi_tile, uint8_t *lo_tile,
-                                  const float *__restrict__ W, int k) {
-    for (int idx = threadIdx.x; idx < TC_K * 8; idx += TC_THREADS) {
-        const int n = idx >> 3, c = idx & 7;
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int kk = 8 * c + i;
-            v[i] = (n < k && kk < k) ? W[(size_t)n * k + kk] : 0.0f;
-        }
-        uint4 hi, lo;
-        split8<WITH_LO>(v, hi, lo);
-        *reinterpret_cast<uint4 *>(hi_tile + swz(n, c)) = hi;
-        if (WITH_LO) *reinterpret_cast<uint4 *>(lo_tile + swz(n, c)) = lo;
-    }
-}
-
-template <bool X3>
-__device__ __forceinline__ float silu_mode(float v) {
-    return X3 ? siluf_(v) : siluf_fast_(v);
 }
 
 // one 128 x 64 x 64 GEMM into TMEM columns [d_col, d_col + 64)
@@ -240,8 +108,8 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
     const bool f_eres = (a.flags & PVS_F_EDGE_RESIDUAL) && a.m_prev != nullptr;
 
     // ---- one-time setup (whole CTA) ----
-    load_weight_tiles<X3>(S.W2_hi, S.W2_lo, a.edge_w2, k);
-    load_weight_tiles<X3>(S.Wc1_hi, S.Wc1_lo, a.coord_w1, k);
+    load_weight_tiles<X3>(S.W2_hi, S.W2_lo, a.edge_w2, k, k, k);
+    load_weight_tiles<X3>(S.Wc1_hi, S.Wc1_lo, a.coord_w1, k, k, k);
     const int col_r = (a.flags & PVS_F_PERM_INVARIANT) ? k : 2 * k;
     for (int n = threadIdx.x; n < 64; n += TC_THREADS) {
         const bool ok = n < k;
@@ -255,7 +123,7 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                             ? a.edge_w1[(size_t)n * a.in_e + col_r + 1 + c] : 0.0f;
     }
     if (tid == 0) mbar_init(&Gm.mbar, 1);
-    if (threadIdx.x < 32) tmem_alloc(&S.tmem_base);
+    if (threadIdx.x < 32) tmem_alloc<TC_TMEM_COLS>(&S.tmem_base);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -534,7 +402,7 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc(tmem_base);
+    if (threadIdx.x < 32) tmem_dealloc<TC_TMEM_COLS>(tmem_base);
 }
 
 int launch_edge_tc(const EdgeArgs &a, int n_tiles_cap, int mode, cudaStream_t st) {

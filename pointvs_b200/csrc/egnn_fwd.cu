@@ -778,7 +778,12 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
     const int stages = (cfg->stages & PVS_STAGE_ALL) ? (cfg->stages & PVS_STAGE_ALL)
                                                      : PVS_STAGE_ALL;
     // node_pre: P = h W1a^T + b1 ; Q = h W1b^T (perm-invariant: Q = h W1a^T)
-    if (stages & PVS_STAGE_NODE_PRE) {
+    const bool tc_node = tc && !(f & PVS_F_GRAPHNORM);
+    if ((stages & PVS_STAGE_NODE_PRE) && tc_node) {
+        rc = launch_node_pre_tc(h_in, p->edge_w1, p->edge_b1, w.P, w.Q, n, k, in_e, perm ? 1 : 0,
+                                cfg->math, st);
+        if (rc) return rc;
+    } else if (stages & PVS_STAGE_NODE_PRE) {
     if (k < kp) {
         rc = cuda_call(cudaMemsetAsync(w.P, 0, (size_t)((char *)w.M - (char *)w.P), st));
         if (rc) return rc;
@@ -824,6 +829,8 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
     }
 
     if (!(stages & PVS_STAGE_NODE)) return PVS_OK;
+    if (tc_node)
+        return launch_node_tc(h_in, w.M, h_out, natt_out, p, n, k, f, cfg->att_act, cfg->math, st);
     NodeArgs na{};
     na.h_in = h_in; na.M = w.M; na.h_out = h_out; na.V = w.V;
     na.natt_out = natt_out;

@@ -1,0 +1,463 @@
+// Node-level stages of K2 on the tensor cores (PVS_MATH_BF16X3 / BF16):
+//
+//   node_pre_tc : [P | Q] = h . [W1a ; W1b]^T (+ b1 on P)      (N = 128, K = 64)
+//   node_tc     : o = Wn2 silu(Wn1 [h ; M] + bn1) + bn2, node attention,
+//                 residual -> h'                                (two K blocks of
+//                 64 into one accumulator, then a 64x64 GEMM)
+//
+// Reference: egnn_satorras.py:82-86, 103-106, 134-166 (node_model) and the
+// first Linear of edge_mlp :76-77 (factorised per node, see egnn_fwd.cu).
+// Same machinery as egnn_edge_tc.cu: tiles of 128 nodes, rows converted to
+// bf16 hi(/lo) K-major SWIZZLE_128B tiles by the threads, tcgen05.mma into
+// TMEM, one thread per row in the epilogue, several independent 4-warp groups
+// per persistent CTA sharing the weight tiles.  Outputs are staged through
+// shared memory so global stores are full 256-byte rows.
+#include "egnn_common.cuh"
+#include "tc_common.cuh"
+
+namespace pvs {
+
+constexpr int NT_GROUP_THREADS = 128;
+constexpr int NT_ROWS = 128;
+
+__device__ __forceinline__ void nt_group_sync(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(NT_GROUP_THREADS) : "memory");
+}
+
+// rows [row0, row0 + 128) x 64 columns of `src` (pitch ld, `cols` valid columns,
+// `n_rows` valid rows overall) -> bf16 hi/lo swizzled A tiles.  8 lanes per row.
+template <bool X3>
+__device__ __forceinline__ void load_block(uint8_t *A_hi, uint8_t *A_lo,
+                                           const float *__restrict__ src, int ld, int cols,
+                                           int row0, int n_rows, int tid) {
+    const int c = tid & 7, slot = tid >> 3;
+    const bool vec = (cols == 64) && ((ld & 3) == 0);
+#pragma unroll 4
+    for (int p = 0; p < NT_ROWS / 16; ++p) {
+        const int r = p * 16 + slot;
+        float v[8];
+        if (row0 + r < n_rows) {
+            const float *s = src + (size_t)(row0 + r) * ld + 8 * c;
+            if (vec) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(s));
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(s) + 1);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = (8 * c + i < cols) ? __ldg(s + i) : 0.0f;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+        }
+        uint4 hi, lo;
+        split8<X3>(v, hi, lo);
+        *reinterpret_cast<uint4 *>(A_hi + swz(r, c)) = hi;
+        if (X3) *reinterpret_cast<uint4 *>(A_lo + swz(r, c)) = lo;
+    }
+}
+
+// fp32 staging tile [128][64] with the 16-byte chunk index XOR-swizzled by the
+// row, so both the row-per-thread writes and the row-per-half-warp reads are
+// conflict free.
+__device__ __forceinline__ float4 *stage_ptr(float *stage, int r, int c4) {
+    return reinterpret_cast<float4 *>(stage + r * 64 + ((c4 ^ (r & 15)) << 2));
+}
+
+// cooperative copy of the staging tile to dst rows [row0, ...) (pitch ld, `cols`
+// valid columns): each half warp writes one full row.
+__device__ __forceinline__ void store_stage(const float *stage, float *__restrict__ dst,
+                                            int ld, int cols, int row0, int n_rows, int tid) {
+    const int c4 = tid & 15, slot = tid >> 4;
+    const bool vec = (ld & 3) == 0;
+#pragma unroll 4
+    for (int p = 0; p < NT_ROWS / 8; ++p) {
+        const int r = p * 8 + slot;
+        if (row0 + r >= n_rows) continue;
+        const float4 v = *stage_ptr(const_cast<float *>(stage), r, c4);
+        float *d = dst + (size_t)(row0 + r) * ld + 4 * c4;
+        if (vec && 4 * c4 + 3 < cols) {
+            *reinterpret_cast<float4 *>(d) = v;
+        } else {
+            if (4 * c4 < cols) d[0] = v.x;
+            if (4 * c4 + 1 < cols) d[1] = v.y;
+            if (4 * c4 + 2 < cols) d[2] = v.z;
+            if (4 * c4 + 3 < cols) d[3] = v.w;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// node_pre: P, Q
+// ---------------------------------------------------------------------------
+constexpr int NP_GROUPS = 4;
+constexpr int NP_THREADS = NP_GROUPS * NT_GROUP_THREADS;
+
+struct __align__(1024) NpSmem {
+    uint8_t A_hi[NP_GROUPS][NT_ROWS * 128];
+    uint8_t A_lo[NP_GROUPS][NT_ROWS * 128];
+    uint8_t W_hi[128 * 128];    // rows 0..63: W1a (P), rows 64..127: W1b (Q)
+    uint8_t W_lo[128 * 128];
+    float b1[64];
+    uint64_t mbar[NP_GROUPS];
+    uint32_t tmem_base;
+};
+
+struct NodePreArgs {
+    const float *h;       // [N][k]
+    const float *edge_w1; // [k][in_e]
+    const float *edge_b1; // [k]
+    float *P, *Q;         // [N][64]
+    int n_nodes, k, in_e, perm_invariant;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(NP_THREADS, 1)
+node_pre_tc_kernel(const NodePreArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    NpSmem &S = *reinterpret_cast<NpSmem *>(smem_dyn);
+    if ((smem_u32(smem_dyn) & 1023u) != 0u) __trap();
+    const int g = threadIdx.x / NT_GROUP_THREADS, tid = threadIdx.x % NT_GROUP_THREADS;
+    const int warp = tid >> 5;
+    uint8_t *A_hi = S.A_hi[g], *A_lo = S.A_lo[g];
+    const int k = a.k;
+    load_weight_tiles<X3>(S.W_hi, S.W_lo, a.edge_w1, a.in_e, k, k, 64);
+    load_weight_tiles<X3>(S.W_hi + 64 * 128, S.W_lo + 64 * 128,
+                          a.edge_w1 + (a.perm_invariant ? 0 : k), a.in_e, k, k, 64);
+    for (int n = threadIdx.x; n < 64; n += NP_THREADS) S.b1[n] = n < k ? a.edge_b1[n] : 0.0f;
+    if (tid == 0) mbar_init(&S.mbar[g], 1);
+    if (threadIdx.x < 32) tmem_alloc<512>(&S.tmem_base);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = S.tmem_base;
+    const uint32_t tmem_grp = tmem_base + (uint32_t)g * 128u;
+    const uint32_t tmem_lane = tmem_grp + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0;
+    const int n_tiles = (a.n_nodes + NT_ROWS - 1) / NT_ROWS;
+    for (int t = blockIdx.x * NP_GROUPS + g; t < n_tiles; t += gridDim.x * NP_GROUPS) {
+        const int row0 = t * NT_ROWS;
+        nt_group_sync(g);   // staging of the previous tile fully stored
+        load_block<X3>(A_hi, A_lo, a.h, k, k, row0, a.n_nodes, tid);
+        fence_proxy_async();
+        tc_fence_before();
+        nt_group_sync(g);
+        if (tid == 0) {
+            tc_fence_after();
+            issue_kblock<X3>(tmem_grp, tc_idesc(128), A_hi, A_lo, S.W_hi, S.W_lo, 0);
+            umma_commit(&S.mbar[g]);
+        }
+        mbar_wait(&S.mbar[g], phase);
+        phase ^= 1;
+        tc_fence_after();
+        // The A tiles are free once the MMA has completed: each 16 KB tile stages
+        // 64 rows of fp32 output (rows 0..63 in A_hi, 64..127 in A_lo), P first,
+        // then Q.
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {   // half 0: P (cols 0..63), 1: Q
+            const int r = tid;
+            float *st = reinterpret_cast<float *>(r < 64 ? A_hi : A_lo);
+            const int rr = r & 63;
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                float acc[16];
+                tmem_ld16(tmem_lane + 64 * half + 16 * q, acc);
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    float4 o = make_float4(acc[4 * v4], acc[4 * v4 + 1], acc[4 * v4 + 2],
+                                           acc[4 * v4 + 3]);
+                    if (half == 0) {
+                        const float4 b = *reinterpret_cast<const float4 *>(&S.b1[16 * q + 4 * v4]);
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    *stage_ptr(st, rr, 4 * q + v4) = o;
+                }
+            }
+            nt_group_sync(g);
+            // coalesced store: 128 rows in two 64-row staging tiles
+            {
+                float *dst = half == 0 ? a.P : a.Q;
+                const int c4 = tid & 15, slot = tid >> 4;
+#pragma unroll 4
+                for (int p = 0; p < NT_ROWS / 8; ++p) {
+                    const int row = p * 8 + slot;
+                    if (row0 + row >= a.n_nodes) continue;
+                    const float *sp = reinterpret_cast<const float *>(row < 64 ? A_hi : A_lo);
+                    const float4 v = *stage_ptr(const_cast<float *>(sp), row & 63, c4);
+                    *reinterpret_cast<float4 *>(dst + (size_t)(row0 + row) * 64 + 4 * c4) = v;
+                }
+            }
+            nt_group_sync(g);
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------
+// node model
+// ---------------------------------------------------------------------------
+constexpr int NM_GROUPS = 5;
+constexpr int NM_THREADS = NM_GROUPS * NT_GROUP_THREADS;
+
+struct __align__(1024) NmSmem {
+    uint8_t A_hi[NM_GROUPS][NT_ROWS * 128];
+    uint8_t A_lo[NM_GROUPS][NT_ROWS * 128];
+    uint8_t W1h_hi[64 * 128], W1h_lo[64 * 128];   // node_w1[:, 0:k]   (h part)
+    uint8_t W1m_hi[64 * 128], W1m_lo[64 * 128];   // node_w1[:, k:2k]  (M part)
+    uint8_t W2_hi[64 * 128], W2_lo[64 * 128];
+    float b1[64], b2[64], wn[64];
+    uint64_t mbar[NM_GROUPS];
+    uint32_t tmem_base;
+};
+
+struct NodeTcArgs {
+    const float *h_in;   // [N][k]
+    const float *M;      // [N][64]
+    float *h_out;        // [N][k]
+    float *natt_out;     // [N] or null
+    const float *node_w1, *node_b1, *node_w2, *node_b2, *natt_w, *natt_b, *node_gate;
+    int n_nodes, k;
+    uint32_t flags;
+    int att_act;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(NM_THREADS, 1)
+node_tc_kernel(const NodeTcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    NmSmem &S = *reinterpret_cast<NmSmem *>(smem_dyn);
+    if ((smem_u32(smem_dyn) & 1023u) != 0u) __trap();
+    const int g = threadIdx.x / NT_GROUP_THREADS, tid = threadIdx.x % NT_GROUP_THREADS;
+    const int warp = tid >> 5;
+    uint8_t *A_hi = S.A_hi[g], *A_lo = S.A_lo[g];
+    const int k = a.k;
+    load_weight_tiles<X3>(S.W1h_hi, S.W1h_lo, a.node_w1, 2 * k, k, k);
+    load_weight_tiles<X3>(S.W1m_hi, S.W1m_lo, a.node_w1 + k, 2 * k, k, k);
+    load_weight_tiles<X3>(S.W2_hi, S.W2_lo, a.node_w2, k, k, k);
+    for (int n = threadIdx.x; n < 64; n += NM_THREADS) {
+        S.b1[n] = n < k ? a.node_b1[n] : 0.0f;
+        S.b2[n] = n < k ? a.node_b2[n] : 0.0f;
+        S.wn[n] = (n < k && a.natt_w) ? a.natt_w[n] : 0.0f;
+    }
+    if (tid == 0) mbar_init(&S.mbar[g], 1);
+    if (threadIdx.x < 32) tmem_alloc<512>(&S.tmem_base);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = S.tmem_base;
+    const uint32_t tmem_grp = tmem_base + (uint32_t)g * 64u;
+    const uint32_t tmem_lane = tmem_grp + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0;
+    const bool f_natt = (a.flags & PVS_F_NODE_ATTENTION) && a.natt_w != nullptr;
+    const bool f_res = a.flags & PVS_F_RESIDUAL;
+    const float natt_b = (f_natt && a.natt_b) ? a.natt_b[0] : 0.0f;
+    const float gate = a.node_gate ? a.node_gate[0] : 1.0f;
+    const int n_tiles = (a.n_nodes + NT_ROWS - 1) / NT_ROWS;
+    for (int t = blockIdx.x * NM_GROUPS + g; t < n_tiles; t += gridDim.x * NM_GROUPS) {
+        const int row0 = t * NT_ROWS;
+        nt_group_sync(g);
+        // ---- v = Wn1 [h ; M]: two K blocks through the same A tiles ----
+        load_block<X3>(A_hi, A_lo, a.h_in, k, k, row0, a.n_nodes, tid);
+        fence_proxy_async();
+        tc_fence_before();
+        nt_group_sync(g);
+        if (tid == 0) {
+            tc_fence_after();
+            issue_kblock<X3>(tmem_grp, tc_idesc(64), A_hi, A_lo, S.W1h_hi, S.W1h_lo, 0);
+            umma_commit(&S.mbar[g]);
+        }
+        mbar_wait(&S.mbar[g], phase);
+        phase ^= 1;
+        load_block<X3>(A_hi, A_lo, a.M, 64, 64, row0, a.n_nodes, tid);
+        fence_proxy_async();
+        tc_fence_before();
+        nt_group_sync(g);
+        if (tid == 0) {
+            tc_fence_after();
+            issue_kblock<X3>(tmem_grp, tc_idesc(64), A_hi, A_lo, S.W1m_hi, S.W1m_lo, 1);
+            umma_commit(&S.mbar[g]);
+        }
+        mbar_wait(&S.mbar[g], phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- u = silu(v + b1) -> A tiles ----
+        {
+            const int r = tid;
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                float acc[16];
+                tmem_ld16(tmem_lane + 16 * q, acc);
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    const int nb = 16 * q + 8 * hlf;
+                    const float4 ba = *reinterpret_cast<const float4 *>(&S.b1[nb]);
+                    const float4 bb = *reinterpret_cast<const float4 *>(&S.b1[nb + 4]);
+                    const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                    float u[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) u[i] = silu_mode<X3>(acc[8 * hlf + i] + bias[i]);
+                    uint4 hi, lo;
+                    split8<X3>(u, hi, lo);
+                    *reinterpret_cast<uint4 *>(A_hi + swz(r, 2 * q + hlf)) = hi;
+                    if (X3) *reinterpret_cast<uint4 *>(A_lo + swz(r, 2 * q + hlf)) = lo;
+                }
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        nt_group_sync(g);
+        if (tid == 0) {
+            tc_fence_after();
+            issue_kblock<X3>(tmem_grp, tc_idesc(64), A_hi, A_lo, S.W2_hi, S.W2_lo, 0);
+            umma_commit(&S.mbar[g]);
+        }
+        mbar_wait(&S.mbar[g], phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- o = D + b2, node attention, residual -> staging -> h_out ----
+        {
+            const int r = tid;
+            const bool ok = row0 + r < a.n_nodes;
+            float s = 1.0f;
+            if (f_natt) {
+                float dot = 0.0f;
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {
+                    float acc[16];
+                    tmem_ld16(tmem_lane + 16 * q, acc);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        dot = fmaf(S.wn[16 * q + i], acc[i] + S.b2[16 * q + i], dot);
+                }
+                const float zn = dot + natt_b;
+                s = (a.flags & PVS_F_SOFTMAX_ATTENTION) ? zn : apply_act(zn, a.att_act);
+                if (a.natt_out && ok) a.natt_out[row0 + r] = s;
+            }
+            // A tiles are free (GEMM 2 has completed): 64 rows of fp32 staging in
+            // each 16 KB tile
+            float *st = reinterpret_cast<float *>(r < 64 ? A_hi : A_lo);
+            const int rr = r & 63;
+            const float *hrow = a.h_in + (size_t)(row0 + r) * k;
+            const bool hvec = (k & 3) == 0;
+            const float G = fmaxf(gate, 0.0f);
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                float acc[16];
+                tmem_ld16(tmem_lane + 16 * q, acc);
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    const int n = 16 * q + 4 * v4;
+                    float o[4], hv[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (f_res && ok) {
+                        if (hvec && n + 3 < k) {
+                            const float4 h4 = __ldg(reinterpret_cast<const float4 *>(hrow + n));
+                            hv[0] = h4.x; hv[1] = h4.y; hv[2] = h4.z; hv[3] = h4.w;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) hv[i] = (n + i < k) ? __ldg(hrow + n + i) : 0.0f;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float out = (acc[4 * v4 + i] + S.b2[n + i]) * s;
+                        if (f_res) {
+                            if (a.flags & PVS_F_REZERO) out = hv[i] + gate * out;
+                            else if (a.flags & PVS_F_GATED_RESIDUAL) out = G * out + (1.0f - G) * hv[i];
+                            else out = hv[i] + out;
+                        }
+                        o[i] = out;
+                    }
+                    *stage_ptr(st, rr, 4 * q + v4) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+        tc_fence_before();
+        nt_group_sync(g);
+        {
+            const int c4 = tid & 15, slot = tid >> 4;
+            const bool vec = (k & 3) == 0;
+#pragma unroll 4
+            for (int p = 0; p < NT_ROWS / 8; ++p) {
+                const int row = p * 8 + slot;
+                if (row0 + row >= a.n_nodes) continue;
+                const float *sp = reinterpret_cast<const float *>(row < 64 ? A_hi : A_lo);
+                const float4 v = *stage_ptr(const_cast<float *>(sp), row & 63, c4);
+                float *d = a.h_out + (size_t)(row0 + row) * k + 4 * c4;
+                if (vec && 4 * c4 + 3 < k) {
+                    *reinterpret_cast<float4 *>(d) = v;
+                } else {
+                    if (4 * c4 < k) d[0] = v.x;
+                    if (4 * c4 + 1 < k) d[1] = v.y;
+                    if (4 * c4 + 2 < k) d[2] = v.z;
+                    if (4 * c4 + 3 < k) d[3] = v.w;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc<512>(tmem_base);
+}
+
+int launch_node_pre_tc(const float *h, const float *edge_w1, const float *edge_b1, float *P,
+                       float *Q, int n_nodes, int k, int in_e, int perm, int mode,
+                       cudaStream_t st) {
+    NodePreArgs a{h, edge_w1, edge_b1, P, Q, n_nodes, k, in_e, perm};
+    const size_t smem = sizeof(NpSmem);
+    const int tiles = (n_nodes + NT_ROWS - 1) / NT_ROWS;
+    int grid = num_sms();
+    const int need = (tiles + NP_GROUPS - 1) / NP_GROUPS;
+    if (need < grid) grid = need;
+    if (grid < 1) grid = 1;
+    int rc;
+    if (mode == PVS_MATH_BF16X3) {
+        rc = cuda_call(cudaFuncSetAttribute(node_pre_tc_kernel<true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (rc) return rc;
+        node_pre_tc_kernel<true><<<grid, NP_THREADS, smem, st>>>(a);
+    } else {
+        rc = cuda_call(cudaFuncSetAttribute(node_pre_tc_kernel<false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (rc) return rc;
+        node_pre_tc_kernel<false><<<grid, NP_THREADS, smem, st>>>(a);
+    }
+    return check_launch();
+}
+
+int launch_node_tc(const float *h_in, const float *M, float *h_out, float *natt_out,
+                   const pvs_layer_params *p, int n_nodes, int k, uint32_t flags, int att_act,
+                   int mode, cudaStream_t st) {
+    NodeTcArgs a{};
+    a.h_in = h_in; a.M = M; a.h_out = h_out; a.natt_out = natt_out;
+    a.node_w1 = p->node_w1; a.node_b1 = p->node_b1; a.node_w2 = p->node_w2;
+    a.node_b2 = p->node_b2; a.natt_w = p->natt_w; a.natt_b = p->natt_b;
+    a.node_gate = p->node_gate;
+    a.n_nodes = n_nodes; a.k = k; a.flags = flags; a.att_act = att_act;
+    const size_t smem = sizeof(NmSmem);
+    const int tiles = (n_nodes + NT_ROWS - 1) / NT_ROWS;
+    int grid = num_sms();
+    const int need = (tiles + NM_GROUPS - 1) / NM_GROUPS;
+    if (need < grid) grid = need;
+    if (grid < 1) grid = 1;
+    int rc;
+    if (mode == PVS_MATH_BF16X3) {
+        rc = cuda_call(cudaFuncSetAttribute(node_tc_kernel<true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (rc) return rc;
+        node_tc_kernel<true><<<grid, NM_THREADS, smem, st>>>(a);
+    } else {
+        rc = cuda_call(cudaFuncSetAttribute(node_tc_kernel<false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (rc) return rc;
+        node_tc_kernel<false><<<grid, NM_THREADS, smem, st>>>(a);
+    }
+    return check_launch();
+}
+
+}  // namespace pvs
