@@ -166,23 +166,32 @@ int64_t pvs_launch_count(void);
  * Two passes so the caller can size col/attr:
  *   count: deg[N] = edges per node, n_inter[N] = of which inter edges,
  *          row_ptr[N+1] = exclusive scan of deg (row_ptr[N] = total edges).
+ *          If mask_scratch != NULL (pvs_radius_graph_mask_bytes) the per-node
+ *          neighbour bit masks are kept there and `fill` only expands them
+ *          (no second neighbour search).
  *   fill:  col / attr, and optionally ref_pos[E] = index of each CSR edge in
- *          the reference's (PyG-collated) edge order.
+ *          the reference's (PyG-collated) edge order.  edge_capacity = size of
+ *          col/attr in edges: a caller that wants NO host sync between the
+ *          passes allocates an upper bound instead of reading row_ptr[N];
+ *          edges beyond the capacity are dropped and *overflow (device int,
+ *          may be NULL) is set non-zero.
  * coords: fp64 [N][3]; bp: int32 [N] (0 ligand, 1 receptor; :106);
  * complex_ptr: int32 [B+1] node offsets.  scratch: pvs_scan_scratch_bytes(N). */
+int64_t pvs_radius_graph_mask_bytes(int32_t n_nodes, int32_t max_complex_nodes);
 int pvs_radius_graph_count(const double *coords, const int32_t *bp,
                            const int32_t *complex_ptr, int32_t n_complexes,
                            int32_t n_nodes, int32_t max_complex_nodes,
                            double inter_radius, double intra_radius,
                            int32_t *deg, int32_t *n_inter, int32_t *row_ptr,
-                           void *scratch, void *stream);
+                           uint32_t *mask_scratch, void *scratch, void *stream);
 int pvs_radius_graph_fill(const double *coords, const int32_t *bp,
                           const int32_t *complex_ptr, int32_t n_complexes,
                           int32_t n_nodes, int32_t max_complex_nodes,
                           double inter_radius, double intra_radius,
                           const int32_t *n_inter, const int32_t *row_ptr,
+                          const uint32_t *mask_scratch, int32_t edge_capacity,
                           int32_t *col, uint8_t *attr, int32_t *ref_pos,
-                          void *stream);
+                          int32_t *overflow, void *stream);
 /* Connected-component mask for `prune` (preprocessing.py:144-153): keep[i]=1
  * iff node i is reachable from the row of its complex's first inter edge
  * (or every node of a complex that has no inter edge). */

@@ -159,7 +159,9 @@ radius_graph_kernel(const double *__restrict__ coords,
                     const int32_t *__restrict__ n_inter_in,
                     const int32_t *__restrict__ row_ptr,
                     int32_t *__restrict__ col, uint8_t *__restrict__ attr,
-                    int32_t *__restrict__ ref_pos, int max_n, int stage) {
+                    int32_t *__restrict__ ref_pos, int max_n, int stage,
+                    uint32_t *__restrict__ mask_out, int edge_capacity,
+                    int32_t *__restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RgSmem &S = *reinterpret_cast<RgSmem *>(smem_raw);
     const int n0 = complex_ptr[blockIdx.x];
@@ -355,6 +357,13 @@ radius_graph_kernel(const double *__restrict__ coords,
                 deg[n0 + i] = ci + ca;
                 n_inter_out[n0 + i] = ci;
             }
+            if (mask_out != nullptr) {   // keep the masks: fill only expands them
+                uint32_t *mo = mask_out + (size_t)(n0 + i) * 2 * words;
+                for (int w = lane; w < nw; w += 32) {
+                    mo[w] = m_inter[w];
+                    mo[words + w] = m_intra[w];
+                }
+            }
         } else {
             const int e_row = row_ptr[n0 + i];
             int run = e_row;
@@ -375,6 +384,11 @@ radius_graph_kernel(const double *__restrict__ coords,
                         bits &= bits - 1;
                         int j = w * 32 + b;
                         int bj = cbp[j];
+                        if (off >= edge_capacity) {
+                            if (overflow) *overflow = 1;
+                            ++off;
+                            continue;
+                        }
                         col[off] = n0 + j;
                         uint8_t a;
                         if (pass == 0)   // :129-133
@@ -396,6 +410,56 @@ radius_graph_kernel(const double *__restrict__ coords,
             }
         }
         __syncwarp();
+    }
+}
+
+// fill from the masks stored by the count pass: one warp per node, flat grid
+__global__ void __launch_bounds__(256)
+radius_graph_emit_kernel(const uint32_t *__restrict__ masks, int words,
+                         const int32_t *__restrict__ bp,
+                         const int32_t *__restrict__ complex_ptr, int n_complexes,
+                         int n_nodes, const int32_t *__restrict__ row_ptr,
+                         int32_t *__restrict__ col, uint8_t *__restrict__ attr,
+                         int edge_capacity, int32_t *__restrict__ overflow) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n_nodes) return;
+    int lo = 0, hi = n_complexes;     // complex of node i
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (complex_ptr[mid] <= i) lo = mid; else hi = mid;
+    }
+    const int n0 = complex_ptr[lo];
+    const int nw = (complex_ptr[lo + 1] - n0 + 31) / 32;
+    const int bi = bp[i];
+    int run = row_ptr[i];
+    const uint32_t *mk0 = masks + (size_t)i * 2 * words;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const uint32_t *mk = mk0 + pass * words;
+        for (int w0 = 0; w0 < nw; w0 += 32) {
+            const int w = w0 + lane;
+            unsigned bits = w < nw ? mk[w] : 0u;
+            const int cnt = __popc(bits);
+            const int incl = warp_scan_incl(cnt, lane);
+            int off = run + incl - cnt;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int j = n0 + w * 32 + b;
+                if (off < edge_capacity) {
+                    const int bj = bp[j];
+                    col[off] = j;
+                    attr[off] = pass == 0
+                        ? (((bi == 0 && bj == 1) || (bi == 1 && bj == 0)) ? 1 : 0)
+                        : ((bi == 1 && bj == 1) ? 2 : 0);
+                } else if (overflow) {
+                    *overflow = 1;
+                }
+                ++off;
+            }
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
     }
 }
 
@@ -443,7 +507,7 @@ prune_mask_kernel(const int32_t *__restrict__ row_ptr,
 // ---------------------------------------------------------------------------
 // work tiles
 // ---------------------------------------------------------------------------
-constexpr int TILE_CHUNK = 1024;
+constexpr int TILE_CHUNK = 256;   // nodes walked serially by one thread
 
 __global__ void __launch_bounds__(256)
 tiles_walk_kernel(const int32_t *__restrict__ row_ptr, int n_nodes,
@@ -576,6 +640,11 @@ using namespace pvs;
 // ===========================================================================
 extern "C" {
 
+int64_t pvs_radius_graph_mask_bytes(int32_t n_nodes, int32_t max_complex_nodes) {
+    const int64_t words = ((int64_t)max_complex_nodes + 31) / 32;
+    return align_up((int64_t)n_nodes * 2 * words * 4, 256);
+}
+
 int64_t pvs_scan_scratch_bytes(int32_t n) {
     int64_t nb = ((int64_t)n + SCAN_TILE - 1) / SCAN_TILE + 1;
     return align_up(nb * (int64_t)sizeof(int32_t), 256);
@@ -603,7 +672,7 @@ int pvs_radius_graph_count(const double *coords, const int32_t *bp,
                            int32_t n_nodes, int32_t max_complex_nodes,
                            double inter_radius, double intra_radius,
                            int32_t *deg, int32_t *n_inter, int32_t *row_ptr,
-                           void *scratch, void *stream) {
+                           uint32_t *mask_scratch, void *scratch, void *stream) {
     int rc = rg_check(coords, bp, complex_ptr, n_complexes, n_nodes,
                       max_complex_nodes, inter_radius, intra_radius);
     if (rc) return rc;
@@ -624,7 +693,8 @@ int pvs_radius_graph_count(const double *coords, const int32_t *bp,
         if (rc) return rc;
         radius_graph_kernel<false><<<n_complexes, RG_THREADS, smem, st>>>(
             coords, bp, complex_ptr, inter_radius, intra_radius, deg, n_inter,
-            nullptr, nullptr, nullptr, nullptr, nullptr, max_complex_nodes, stage);
+            nullptr, nullptr, nullptr, nullptr, nullptr, max_complex_nodes, stage,
+            mask_scratch, 0, nullptr);
         rc = check_launch();
         if (rc) return rc;
     }
@@ -636,13 +706,21 @@ int pvs_radius_graph_fill(const double *coords, const int32_t *bp,
                           int32_t n_nodes, int32_t max_complex_nodes,
                           double inter_radius, double intra_radius,
                           const int32_t *n_inter, const int32_t *row_ptr,
+                          const uint32_t *mask_scratch, int32_t edge_capacity,
                           int32_t *col, uint8_t *attr, int32_t *ref_pos,
-                          void *stream) {
+                          int32_t *overflow, void *stream) {
     int rc = rg_check(coords, bp, complex_ptr, n_complexes, n_nodes,
                       max_complex_nodes, inter_radius, intra_radius);
     if (rc) return rc;
     if (n_nodes == 0 || n_complexes == 0) return PVS_OK;
-    if (!n_inter || !row_ptr || !col || !attr) return PVS_ERR_INVALID_ARG;
+    if (!n_inter || !row_ptr || !col || !attr || edge_capacity < 0) return PVS_ERR_INVALID_ARG;
+    if (mask_scratch != nullptr && ref_pos == nullptr) {
+        const int words = (max_complex_nodes + 31) / 32;
+        radius_graph_emit_kernel<<<(n_nodes + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+            mask_scratch, words, bp, complex_ptr, n_complexes, n_nodes, row_ptr, col, attr,
+            edge_capacity, overflow);
+        return check_launch();
+    }
     int stage = 1;
     size_t smem = rg_smem_bytes(max_complex_nodes, ref_pos != nullptr, true);
     if (smem > (size_t)max_optin_smem()) {
@@ -657,7 +735,8 @@ int pvs_radius_graph_fill(const double *coords, const int32_t *bp,
     radius_graph_kernel<true><<<n_complexes, RG_THREADS, smem,
                                 (cudaStream_t)stream>>>(
         coords, bp, complex_ptr, inter_radius, intra_radius, nullptr, nullptr,
-        n_inter, row_ptr, col, attr, ref_pos, max_complex_nodes, stage);
+        n_inter, row_ptr, col, attr, ref_pos, max_complex_nodes, stage, nullptr,
+        edge_capacity, overflow);
     return check_launch();
 }
 

@@ -40,7 +40,32 @@ class CSRGraph:
         self.device = row_ptr.device
         self._inv_perm = None
         self._csc = None
+        self.exact_edge_count = True
+        self.n_edges_dev = None
+        self._overflow = None
         self._build_tiles()
+
+    def check_overflow(self):
+        """Host sync: raise if a capacity-bounded build dropped edges."""
+        if self._overflow is not None and int(self._overflow.item()):
+            raise _cabi.PvsError(
+                f'edge capacity {self.n_edges} too small for '
+                f'{int(self.n_edges_dev.item())} edges')
+
+    def true_edge_count(self):
+        """Exact number of edges (a host sync for capacity-bounded graphs)."""
+        if self.exact_edge_count:
+            return self.n_edges
+        return int(self.n_edges_dev.item())
+
+    def _exact(self):
+        """Trim a capacity-bounded graph to its exact size (host sync)."""
+        if not self.exact_edge_count:
+            self.check_overflow()
+            e = int(self.n_edges_dev.item())
+            self.n_edges = e
+            self.col, self.attr = self.col[:e], self.attr[:e]
+            self.exact_edge_count = True
 
     def _build_tiles(self):
         h = lib()
@@ -64,6 +89,7 @@ class CSRGraph:
     # -- orderings -------------------------------------------------------
     def rows(self):
         """Destination node of every CSR edge, int64 [E]."""
+        self._exact()
         deg = (self.row_ptr[1:] - self.row_ptr[:-1]).long()
         return torch.repeat_interleave(
             torch.arange(self.n_nodes, device=self.device), deg,
@@ -93,6 +119,7 @@ class CSRGraph:
     def csc(self):
         """(csc_ptr [N+1], csc_eid [E]): CSR edge ids grouped by neighbour."""
         if self._csc is None:
+            self._exact()
             h = lib()
             dev = self.device
             csc_ptr = torch.empty(self.n_nodes + 1, dtype=torch.int32, device=dev)
@@ -120,6 +147,7 @@ class CSRGraph:
         return ei
 
     def edge_attr_onehot(self, order='csr'):
+        self._exact()
         a = torch.nn.functional.one_hot(self.attr.long(), self.n_classes)
         if order == 'reference':
             out = torch.empty_like(a)
@@ -133,17 +161,26 @@ def _as_i32(x, device):
 
 
 def radius_graph_batch(coords, bp, complex_ptr, inter_radius=4.0,
-                       intra_radius=2.0, with_ref_pos=False, device=None):
+                       intra_radius=2.0, with_ref_pos=False, device=None,
+                       edge_capacity=None):
     """K1 over a packed batch.
 
     coords: float64 [N,3] (tensor or array), bp: int [N], complex_ptr: int
     [B+1] host array of node offsets.  Returns a CSRGraph whose within-row
     order is the stable sort by destination of the reference's edge list.
+
+    edge_capacity=None reads the edge count back once (the only host sync) to
+    size col/attr exactly.  With an int (an upper bound on E; 'auto' = 24
+    edges per atom) nothing is read back: `n_edges` of the result is the
+    capacity, `n_edges_dev` the true count on the device, and
+    `check_overflow()` (a sync, call it whenever convenient) raises if the
+    bound was too small.
     """
     device = torch.device(device or 'cuda')
     h = lib()
     coords = torch.as_tensor(coords, dtype=torch.float64).to(device).contiguous()
-    bp = torch.as_tensor(bp).to(device=device, dtype=torch.int32).contiguous()
+    bp = torch.as_tensor(np.array(bp) if isinstance(bp, np.ndarray) else bp
+                         ).to(device=device, dtype=torch.int32).contiguous()
     cptr_host = np.asarray(complex_ptr, dtype=np.int32)
     n = int(coords.shape[0])
     n_complexes = len(cptr_host) - 1
@@ -156,27 +193,43 @@ def radius_graph_batch(coords, bp, complex_ptr, inter_radius=4.0,
     row_ptr = torch.empty(n + 1, dtype=torch.int32, device=device)
     scratch = torch.empty(int(h.pvs_scan_scratch_bytes(n)) + 256,
                           dtype=torch.uint8, device=device)
+    # neighbour masks kept between the passes (skipped when they would be huge
+    # or when the reference-order positions need the per-complex pass anyway)
+    mask_bytes = int(h.pvs_radius_graph_mask_bytes(n, max_n))
+    masks = None
+    if not with_ref_pos and 0 < mask_bytes <= (1 << 30):
+        masks = torch.empty(mask_bytes, dtype=torch.uint8, device=device)
     with torch.cuda.device(device):
         check(h.pvs_radius_graph_count(
             ptr(coords), ptr(bp), ptr(cptr), n_complexes, n, max_n,
             C.c_double(inter_radius), C.c_double(intra_radius), ptr(deg),
-            ptr(n_inter), ptr(row_ptr), ptr(scratch), stream()),
+            ptr(n_inter), ptr(row_ptr), ptr(masks), ptr(scratch), stream()),
             'pvs_radius_graph_count')
-        n_edges = int(row_ptr[-1].item())   # the one host sync: sizes col/attr
-        col = torch.empty(max(1, n_edges), dtype=torch.int32, device=device)
-        attr = torch.empty(max(1, n_edges), dtype=torch.uint8, device=device)
-        ref_pos = torch.empty(max(1, n_edges), dtype=torch.int32,
+        if edge_capacity is None:
+            n_edges = int(row_ptr[-1].item())   # the one host sync
+            capacity = n_edges
+        else:
+            capacity = 24 * n if edge_capacity == 'auto' else int(edge_capacity)
+            n_edges = capacity
+        col = torch.empty(max(1, capacity), dtype=torch.int32, device=device)
+        attr = torch.empty(max(1, capacity), dtype=torch.uint8, device=device)
+        ref_pos = torch.empty(max(1, capacity), dtype=torch.int32,
                               device=device) if with_ref_pos else None
+        overflow = torch.zeros(1, dtype=torch.int32, device=device)
         check(h.pvs_radius_graph_fill(
             ptr(coords), ptr(bp), ptr(cptr), n_complexes, n, max_n,
             C.c_double(inter_radius), C.c_double(intra_radius), ptr(n_inter),
-            ptr(row_ptr), ptr(col), ptr(attr), ptr(ref_pos), stream()),
+            ptr(row_ptr), ptr(masks), capacity, ptr(col), ptr(attr),
+            ptr(ref_pos), ptr(overflow), stream()),
             'pvs_radius_graph_fill')
         g = CSRGraph(n, n_edges, row_ptr, col[:n_edges], attr[:n_edges],
                      perm=None, n_inter=n_inter[:n],
                      ref_pos=None if ref_pos is None else ref_pos[:n_edges])
     g.complex_ptr = cptr
     g.complex_ptr_host = cptr_host
+    g.n_edges_dev = row_ptr[-1:]
+    g.exact_edge_count = edge_capacity is None
+    g._overflow = overflow
     return g
 
 
@@ -292,13 +345,14 @@ class PackedBatch:
     @staticmethod
     def from_arrays(coords, bp, feats, complex_ptr, inter_radius=4.0,
                     intra_radius=4.0, y=None, device=None, lig_fname=None,
-                    rec_fname=None):
+                    rec_fname=None, edge_capacity=None):
         """coords f64 [N,3], bp [N], feats f32 [N,F], complex_ptr [B+1]
         (host arrays, or device tensors for coords/bp/feats)."""
         device = torch.device(device or 'cuda')
         coords_d = torch.as_tensor(coords, dtype=torch.float64).to(device)
         csr = radius_graph_batch(coords_d, bp, complex_ptr, inter_radius,
-                                 intra_radius, device=device)
+                                 intra_radius, device=device,
+                                 edge_capacity=edge_capacity)
         cptr = np.asarray(complex_ptr, dtype=np.int64)
         sizes = torch.from_numpy(np.diff(cptr)).to(device)
         batch = torch.repeat_interleave(

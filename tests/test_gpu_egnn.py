@@ -295,3 +295,21 @@ def test_high_degree_node_multi_chunk():
     assert helpers.scaled_err(h2.cpu().numpy(), ho.numpy()) < ELEM_TOL
     assert helpers.scaled_err(x2.cpu().numpy(), xo.numpy()) < 1e-5
     assert helpers.scaled_err(m2.cpu().numpy(), mo.numpy()) < ELEM_TOL
+
+
+def test_capacity_bounded_batch_scores_identically():
+    from pointvs_b200.graph import PackedBatch
+    from pointvs_b200.synthetic import synthetic_batch
+    kw = dict(dim_input=13, dim_output=1, k=64, num_layers=3,
+              edge_attention=True, node_attention=True, residual=True,
+              normalize=True, tanh=True, graphnorm=False)
+    model = gh.build_model(kw, seed=1, coord_gain=1.0)
+    coords, bp, feats, cptr = synthetic_batch(70, 3, 500, 20, ragged=True)
+    outs = []
+    for cap in (None, 'auto'):
+        batch = PackedBatch.from_arrays(coords, bp, feats, cptr, 4.0, 4.0,
+                                        edge_capacity=cap)
+        with torch.no_grad():
+            outs.append(model(batch))
+        batch.pvs_csr.check_overflow()
+    assert torch.equal(outs[0], outs[1])

@@ -207,8 +207,8 @@ def test_tile_partition(radii):
     edges = rp[tp[1:]] - rp[tp[:-1]]
     nodes = np.diff(tp)
     assert np.all((edges <= 128) | (nodes == 1)) and np.all(nodes <= 128)
-    # greedy: neighbouring tiles cannot be merged (inside one 1024-node chunk)
-    same_chunk = (tp[1:-1] % 1024) != 0
+    # greedy: neighbouring tiles cannot be merged (inside one 256-node chunk)
+    same_chunk = (tp[1:-1] % 256) != 0
     merged_e = edges[:-1] + edges[1:]
     merged_n = nodes[:-1] + nodes[1:]
     assert np.all(~same_chunk | (merged_e > 128) | (merged_n > 128))
@@ -233,3 +233,37 @@ def test_batch_to_ptr():
     assert ptr == [0, 3, 3, 5, 5, 5, 6, 6]
     assert batch_to_ptr(torch.zeros(0, dtype=torch.long, device='cuda'),
                         2).cpu().tolist() == [0, 0, 0]
+
+
+def test_capacity_bounded_build_matches_exact_build():
+    """No-host-sync path: col/attr sized by an upper bound."""
+    from pointvs_b200._cabi import PvsError
+    from pointvs_b200.graph import radius_graph_batch
+    from pointvs_b200.synthetic import synthetic_batch
+    coords, bp, _, cptr = synthetic_batch(40, 4, 600, 20, ragged=True)
+    exact = radius_graph_batch(coords, bp, cptr, 4.0, 4.0)
+    loose = radius_graph_batch(coords, bp, cptr, 4.0, 4.0, edge_capacity='auto')
+    assert loose.n_edges == 24 * exact.n_nodes and not loose.exact_edge_count
+    loose.check_overflow()
+    assert loose.true_edge_count() == exact.n_edges
+    e = exact.n_edges
+    assert torch.equal(loose.row_ptr, exact.row_ptr)
+    assert torch.equal(loose.col[:e], exact.col)
+    assert torch.equal(loose.attr[:e], exact.attr)
+    assert torch.equal(loose.edge_index('csr'), exact.edge_index('csr'))
+    assert loose.n_edges == e           # trimmed by the call above
+    tight = radius_graph_batch(coords, bp, cptr, 4.0, 4.0, edge_capacity=e - 5)
+    with pytest.raises(PvsError):
+        tight.check_overflow()
+
+
+def test_mask_reuse_and_recompute_fill_agree():
+    """fill from stored masks (packed path) == per-complex fill (ref_pos path)."""
+    from pointvs_b200.graph import radius_graph_batch
+    from pointvs_b200.synthetic import synthetic_batch
+    coords, bp, _, cptr = synthetic_batch(60, 5, 400, 20, ragged=True)
+    a = radius_graph_batch(coords, bp, cptr, 4.0, 2.0)
+    b = radius_graph_batch(coords, bp, cptr, 4.0, 2.0, with_ref_pos=True)
+    assert a.n_edges == b.n_edges
+    assert torch.equal(a.row_ptr, b.row_ptr)
+    assert torch.equal(a.col, b.col) and torch.equal(a.attr, b.attr)
