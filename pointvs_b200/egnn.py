@@ -373,11 +373,24 @@ class PNNGeometricBase(PointNeuralNetworkBase):
             out = out.reshape(-1)
         return out
 
+    def _unpack_for_forward(self, graph):
+        """unpack_graph, except that a batch carrying a prebuilt CSR
+        (PackedBatch) never materialises edge_index / one-hot edge_attr."""
+        csr = getattr(graph, 'pvs_csr', None)
+        if csr is None:
+            return (*self.unpack_graph(graph), None)
+        dev = self.device_for_inputs()
+        batch = None if getattr(graph, 'graph_ptr', None) is not None \
+            else graph.batch.to(dev)
+        return (graph.x.float().to(dev), None, graph.pos.float().to(dev), None,
+                batch, csr)
+
     def forward(self, x):
-        feats, edges, coords, edge_attributes, batch = self.unpack_graph(x)
+        feats, edges, coords, edge_attributes, batch, csr = \
+            self._unpack_for_forward(x)
         feats, _ = self.get_embeddings(
             feats, edges, coords, edge_attributes, batch,
-            _csr=getattr(x, 'pvs_csr', None), _want_messages=False)
+            _csr=csr, _want_messages=False)
         if self.feats_linear_layers is not None:
             feats = self._pool_and_head(feats, batch, x,
                                         self.feats_linear_layers)
@@ -566,10 +579,11 @@ class MultitaskSatorrasEGNN(SartorrasEGNN):
         return nn.Sequential(*embedding_layers)
 
     def forward(self, graph):
-        feats, edges, coords, edge_attributes, batch = self.unpack_graph(graph)
+        feats, edges, coords, edge_attributes, batch, csr = \
+            self._unpack_for_forward(graph)
         feats, _ = self.get_embeddings(
             feats, edges, coords, edge_attributes, batch,
-            _csr=getattr(graph, 'pvs_csr', None), _want_messages=False)
+            _csr=csr, _want_messages=False)
         head = self.feats_linear_layers_pose \
             if 'classification' in self.model_task \
             else self.feats_linear_layers_affinity

@@ -316,16 +316,18 @@ class PackedBatch:
     """Variable-size complexes packed for the EGNN kernels; duck-types the PyG
     `Batch` consumed by `forward(graph)` (x, pos, edge_index, edge_attr,
     batch, y, lig_fname, rec_fname) and carries the prebuilt CSR as
-    `pvs_csr`, so the model skips the edge sort."""
+    `pvs_csr` and the node offsets as `graph_ptr`, so the model neither sorts
+    edges nor derives the batch size on the host.  edge_index / edge_attr /
+    batch are materialised only if somebody asks for them."""
 
-    def __init__(self, x, pos, csr, batch, y=None, lig_fname=None,
+    def __init__(self, x, pos, csr, graph_ptr, y=None, lig_fname=None,
                  rec_fname=None):
-        self.x, self.pos, self.pvs_csr, self.batch = x, pos, csr, batch
+        self.x, self.pos, self.pvs_csr, self.graph_ptr = x, pos, csr, graph_ptr
         self.y = y
+        self.num_graphs = int(graph_ptr.numel()) - 1
         self.lig_fname = lig_fname if lig_fname is not None else []
         self.rec_fname = rec_fname if rec_fname is not None else []
-        self._edge_index = None
-        self._edge_attr = None
+        self._edge_index = self._edge_attr = self._batch = None
 
     @property
     def edge_index(self):
@@ -338,6 +340,15 @@ class PackedBatch:
         if self._edge_attr is None:
             self._edge_attr = self.pvs_csr.edge_attr_onehot('csr')
         return self._edge_attr
+
+    @property
+    def batch(self):
+        if self._batch is None:
+            sizes = (self.graph_ptr[1:] - self.graph_ptr[:-1]).long()
+            self._batch = torch.repeat_interleave(
+                torch.arange(self.num_graphs, device=sizes.device), sizes,
+                output_size=int(self.x.shape[0]))
+        return self._batch
 
     def to(self, device):
         return self
@@ -353,13 +364,6 @@ class PackedBatch:
         csr = radius_graph_batch(coords_d, bp, complex_ptr, inter_radius,
                                  intra_radius, device=device,
                                  edge_capacity=edge_capacity)
-        cptr = np.asarray(complex_ptr, dtype=np.int64)
-        sizes = torch.from_numpy(np.diff(cptr)).to(device)
-        batch = torch.repeat_interleave(
-            torch.arange(len(cptr) - 1, device=device), sizes,
-            output_size=int(cptr[-1]))
         x = torch.as_tensor(feats, dtype=torch.float32).to(device)
-        pb = PackedBatch(x, coords_d.float(), csr, batch, y=y,
-                         lig_fname=lig_fname, rec_fname=rec_fname)
-        pb.graph_ptr = torch.from_numpy(cptr.astype(np.int32)).to(device)
-        return pb
+        return PackedBatch(x, coords_d.float(), csr, csr.complex_ptr, y=y,
+                           lig_fname=lig_fname, rec_fname=rec_fname)
