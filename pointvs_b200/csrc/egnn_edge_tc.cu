@@ -179,13 +179,14 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                 // every LDG.128 warp instruction reads 4 full 256-byte rows.
                 {
                     const int c = tid & 7, slot = tid >> 3;
-                    float wr8[8];
+                    float2 wr2[4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) wr8[i] = S.wr[8 * c + i];
+                    for (int i = 0; i < 4; ++i)
+                        wr2[i] = *reinterpret_cast<const float2 *>(&S.wr[8 * c + 2 * i]);
 #pragma unroll 4
                     for (int p = 0; p < TE / 16; ++p) {
                         const int r = p * 16 + slot;
-                        float v[8];
+                        float2 v[4];
                         if (r < ne) {
                             const float4 *pp = reinterpret_cast<const float4 *>(
                                 a.P + (size_t)(n0 + Gm.e_rowl[r]) * TC_K + 8 * c);
@@ -194,23 +195,26 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                             const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
                             const float4 q0 = __ldg(qq), q1 = __ldg(qq + 1);
                             const float rad = Gm.e_rad[r];
+                            const float2 rad2 = make_float2(rad, rad);
                             const float4 *t4 = reinterpret_cast<const float4 *>(
                                 &S.T[Gm.e_attr[r]][8 * c]);
                             const float4 ta = t4[0], tb = t4[1];
-                            const float tt[8] = {ta.x, ta.y, ta.z, ta.w,
-                                                 tb.x, tb.y, tb.z, tb.w};
-                            const float pq[8] = {p0.x + q0.x, p0.y + q0.y, p0.z + q0.z,
-                                                 p0.w + q0.w, p1.x + q1.x, p1.y + q1.y,
-                                                 p1.z + q1.z, p1.w + q1.w};
+                            const float2 pv[4] = {make_float2(p0.x, p0.y), make_float2(p0.z, p0.w),
+                                                  make_float2(p1.x, p1.y), make_float2(p1.z, p1.w)};
+                            const float2 qv[4] = {make_float2(q0.x, q0.y), make_float2(q0.z, q0.w),
+                                                  make_float2(q1.x, q1.y), make_float2(q1.z, q1.w)};
+                            const float2 tv[4] = {make_float2(ta.x, ta.y), make_float2(ta.z, ta.w),
+                                                  make_float2(tb.x, tb.y), make_float2(tb.z, tb.w)};
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                v[i] = silu_mode<X3>(fmaf(wr8[i], rad, pq[i]) + tt[i]);
+                            for (int i = 0; i < 4; ++i)
+                                v[i] = silu2_mode<X3>(ffma2(
+                                    wr2[i], rad2, fadd2(fadd2(pv[i], qv[i]), tv[i])));
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+                            for (int i = 0; i < 4; ++i) v[i] = make_float2(0.0f, 0.0f);
                         }
                         uint4 hi, lo;
-                        split8<X3>(v, hi, lo);
+                        split8p<X3>(v, hi, lo);
                         *reinterpret_cast<uint4 *>(A_hi + swz(r, c)) = hi;
                         if (X3) *reinterpret_cast<uint4 *>(A_lo + swz(r, c)) = lo;
                     }
@@ -230,7 +234,7 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                 // attention logit, and m back into the A tile for GEMM 2 ----
                 {
                     const int r = tid;
-                    float dot = 0.0f;
+                    float2 dot2 = make_float2(0.0f, 0.0f);
 #pragma unroll 1
                     for (int q = 0; q < 4; ++q) {
                         float acc[16];
@@ -241,39 +245,44 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                             const float4 *b4 = reinterpret_cast<const float4 *>(&S.b2[nb]);
                             const float4 *w4 = reinterpret_cast<const float4 *>(&S.wa[nb]);
                             const float4 ba = b4[0], bb = b4[1], wa0 = w4[0], wa1 = w4[1];
-                            const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-                            const float wat[8] = {wa0.x, wa0.y, wa0.z, wa0.w,
-                                                  wa1.x, wa1.y, wa1.z, wa1.w};
+                            const float2 bias[4] = {make_float2(ba.x, ba.y), make_float2(ba.z, ba.w),
+                                                    make_float2(bb.x, bb.y), make_float2(bb.z, bb.w)};
+                            const float2 wat[4] = {make_float2(wa0.x, wa0.y), make_float2(wa0.z, wa0.w),
+                                                   make_float2(wa1.x, wa1.y), make_float2(wa1.z, wa1.w)};
                             // Padded channels (n >= k) need no masking: their
                             // weight rows and biases are zero, so m = silu(0) = 0.
                             // Rows >= ne hold values nobody reads.
-                            float mv[8];
+                            float2 mv[4];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                mv[i] = silu_mode<X3>(acc[8 * hlf + i] + bias[i]);
+                            for (int i = 0; i < 4; ++i)
+                                mv[i] = silu2_mode<X3>(fadd2(
+                                    make_float2(acc[8 * hlf + 2 * i], acc[8 * hlf + 2 * i + 1]),
+                                    bias[i]));
                             if (f_eres && r < ne) {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     const int n = nb + i;
                                     if (n < k) {
+                                        float &mref = (i & 1) ? mv[i >> 1].y : mv[i >> 1].x;
                                         float mp = a.m_prev[(size_t)(c0 + r) * k + n];
-                                        if (a.flags & PVS_F_REZERO) mv[i] = mp + gate * mv[i];
+                                        if (a.flags & PVS_F_REZERO) mref = mp + gate * mref;
                                         else if (a.flags & PVS_F_GATED_RESIDUAL) {
                                             float gg = fmaxf(gate, 0.0f);
-                                            mv[i] = gg * mv[i] + (1.0f - gg) * mp;
-                                        } else mv[i] = mv[i] + mp;
+                                            mref = gg * mref + (1.0f - gg) * mp;
+                                        } else mref = mref + mp;
                                     }
                                 }
                             }
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) dot = fmaf(wat[i], mv[i], dot);
+                            for (int i = 0; i < 4; ++i) dot2 = ffma2(wat[i], mv[i], dot2);
                             uint4 hi, lo;
-                            split8<X3>(mv, hi, lo);
+                            split8p<X3>(mv, hi, lo);
                             const int c = 2 * q + hlf;
                             *reinterpret_cast<uint4 *>(A_hi + swz(r, c)) = hi;
                             if (X3) *reinterpret_cast<uint4 *>(A_lo + swz(r, c)) = lo;
                         }
                     }
+                    const float dot = dot2.x + dot2.y;
                     // attention value per edge (alpha, or the raw logit when
                     // a softmax pass follows)
                     float al = 1.0f;
@@ -348,7 +357,7 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                 mbar_wait(&Gm.mbar, phase);
                 phase ^= 1;
                 tc_fence_after();
-                float dot = 0.0f;
+                float2 d2 = make_float2(0.0f, 0.0f);
 #pragma unroll 1
                 for (int q = 0; q < 4; ++q) {
                     float acc[16];
@@ -357,12 +366,15 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                     for (int v4 = 0; v4 < 4; ++v4) {
                         const float4 bb = *reinterpret_cast<const float4 *>(&S.bc1[16 * q + 4 * v4]);
                         const float4 ww = *reinterpret_cast<const float4 *>(&S.wc2[16 * q + 4 * v4]);
-                        dot = fmaf(ww.x, silu_mode<X3>(acc[4 * v4] + bb.x), dot);
-                        dot = fmaf(ww.y, silu_mode<X3>(acc[4 * v4 + 1] + bb.y), dot);
-                        dot = fmaf(ww.z, silu_mode<X3>(acc[4 * v4 + 2] + bb.z), dot);
-                        dot = fmaf(ww.w, silu_mode<X3>(acc[4 * v4 + 3] + bb.w), dot);
+                        d2 = ffma2(make_float2(ww.x, ww.y),
+                                   silu2_mode<X3>(fadd2(make_float2(acc[4 * v4], acc[4 * v4 + 1]),
+                                                        make_float2(bb.x, bb.y))), d2);
+                        d2 = ffma2(make_float2(ww.z, ww.w),
+                                   silu2_mode<X3>(fadd2(make_float2(acc[4 * v4 + 2], acc[4 * v4 + 3]),
+                                                        make_float2(bb.z, bb.w))), d2);
                     }
                 }
+                const float dot = d2.x + d2.y;
                 Gm.e_c[tid] = (a.flags & PVS_F_TANH) ? tanhf(dot) : dot;
                 tc_fence_before();
             }

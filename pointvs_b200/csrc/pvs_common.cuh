@@ -52,6 +52,39 @@ __device__ __forceinline__ float tanh_approx(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// Packed fp32x2 arithmetic (Blackwell FFMA2/FADD2/FMUL2): one issue slot for
+// two lanes.  The edge kernels are issue-bound, not FMA-pipe-bound.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long *>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+// two SiLUs: 3 packed FMA-pipe ops + 4 MUFU (fp32-class) or 2 packed + 2 MUFU
+__device__ __forceinline__ float2 silu2_(float2 v) {
+    const float2 t = fmul2(v, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+    float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+    e = fadd2(e, make_float2(1.0f, 1.0f));
+    return fmul2(v, make_float2(rcp_approx(e.x), rcp_approx(e.y)));
+}
+__device__ __forceinline__ float2 silu2_fast_(float2 v) {
+    const float2 h = fmul2(v, make_float2(0.5f, 0.5f));
+    return ffma2(h, make_float2(tanh_approx(h.x), tanh_approx(h.y)), h);
+}
+
 __device__ __forceinline__ float sigmoidf_(float v) {
     return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v));
 }

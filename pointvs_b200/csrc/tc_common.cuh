@@ -144,6 +144,33 @@ template <bool X3>
 __device__ __forceinline__ float silu_mode(float v) {
     return X3 ? siluf_(v) : siluf_fast_(v);
 }
+template <bool X3>
+__device__ __forceinline__ float2 silu2_mode(float2 v) {
+    return X3 ? silu2_(v) : silu2_fast_(v);
+}
+
+// split 4 fp32 pairs into bf16 hi (round-to-nearest) and bf16 lo = bf16(x - hi),
+// packed arithmetic: per pair 1 cvt + 2 ALU + 1 FFMA2 + 1 cvt
+template <bool WITH_LO>
+__device__ __forceinline__ void split8p(const float2 (&v)[4], uint4 &hi, uint4 &lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 hb = __floats2bfloat162_rn(v[i].x, v[i].y);
+        h[i] = *reinterpret_cast<uint32_t *>(&hb);
+        if (WITH_LO) {
+            const float2 hf = make_float2(__uint_as_float(h[i] << 16),
+                                          __uint_as_float(h[i] & 0xffff0000u));
+            const float2 r = ffma2(hf, make_float2(-1.0f, -1.0f), v[i]);
+            __nv_bfloat162 lb = __floats2bfloat162_rn(r.x, r.y);
+            l[i] = *reinterpret_cast<uint32_t *>(&lb);
+        } else {
+            l[i] = 0u;
+        }
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
 
 // MMAs of one 64-wide K block: D[128 x N] (+)= A[128 x 64] . B[N x 64]^T with the
 // bf16 hi/lo operand tiles (X3: Ahi.Bhi + Alo.Bhi + Ahi.Blo).  `acc` = 0 makes the
