@@ -104,6 +104,10 @@ typedef struct pvs_layer_config {
     int32_t stages;         /* PVS_STAGE_* mask; 0 = all.  Lets a profiler put
                                events between the three launches of a layer;
                                the workspace carries state between calls.     */
+    void *ev_edge_begin;    /* optional cudaEvent_t pair recorded on `stream`  */
+    void *ev_edge_end;      /* around the edge stage (NULL = none): lets a     */
+                            /* caller time the dominant kernel with no extra   */
+                            /* host work inside a step                          */
 } pvs_layer_config;
 
 #define PVS_STAGE_NODE_PRE 1 /* P = h W1a^T + b1, Q = h W1b^T                 */

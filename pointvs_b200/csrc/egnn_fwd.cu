@@ -816,6 +816,7 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
     ea.k = k; ea.in_e = in_e; ea.n_classes = cfg->n_edge_classes;
     ea.flags = f; ea.att_act = cfg->att_act;
     if (stages & PVS_STAGE_EDGE) {
+    if (cfg->ev_edge_begin) cudaEventRecord((cudaEvent_t)cfg->ev_edge_begin, st);
     if (tc) rc = launch_edge_tc(ea, g->n_tiles_cap, cfg->math, st);
     else rc = kp == 32 ? launch_edge<32>(ea, g->n_tiles_cap, st)
                        : launch_edge<64>(ea, g->n_tiles_cap, st);
@@ -827,6 +828,8 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
         rc = check_launch();
         if (rc) return rc;
     }
+    if ((stages & PVS_STAGE_EDGE) && cfg->ev_edge_end)
+        cudaEventRecord((cudaEvent_t)cfg->ev_edge_end, st);
 
     if (!(stages & PVS_STAGE_NODE)) return PVS_OK;
     if (tc_node)

@@ -42,7 +42,7 @@ def test_argument_validation_happens_before_any_launch():
     from pointvs_b200 import _cabi
     lib = _cabi.lib()
     # k out of range -> workspace query reports -1, layer call reports status 2
-    cfg = _cabi.LayerConfig(96, 3, 0, 0, 0, 0)
+    cfg = _cabi.LayerConfig(96, 3, 0, 0, 0, 0, None, None)
     assert lib.pvs_egnn_layer_workspace_bytes(10, 10, C.byref(cfg)) == -1
     g = _cabi.Graph(10, 10, None, None, None, None, None, 1)
     p = _cabi.LayerParams()
@@ -50,7 +50,7 @@ def test_argument_validation_happens_before_any_launch():
                                 None, None, None, None, None, None, None, None,
                                 C.c_int64(0), None)
     assert rc == 2
-    cfg = _cabi.LayerConfig(64, 3, 0, 0, 0, 0)
+    cfg = _cabi.LayerConfig(64, 3, 0, 0, 0, 0, None, None)
     rc = lib.pvs_egnn_layer_fwd(C.byref(g), C.byref(cfg), C.byref(p), None,
                                 None, None, None, None, None, None, None, None,
                                 C.c_int64(0), None)
@@ -64,7 +64,7 @@ def test_argument_validation_happens_before_any_launch():
 
 def test_structs_match_header_layout():
     from pointvs_b200 import _cabi
-    assert C.sizeof(_cabi.LayerConfig) == 6 * 4
+    assert C.sizeof(_cabi.LayerConfig) == 6 * 4 + 2 * 8
     assert C.sizeof(_cabi.LayerParams) == 20 * 8
     assert C.sizeof(_cabi.LayerGrads) == 17 * 8
     assert C.sizeof(_cabi.Graph) == 8 + 5 * 8 + 8
