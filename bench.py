@@ -372,12 +372,14 @@ def run_ours(args):
     # 1-element adds per step) and read once after the timed region
     edges_dev = torch.zeros(1, dtype=torch.int64, device=dev)
     overflow_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         _, csr = step_device(args.warmup + i)
         edges_dev += csr.n_edges_dev
         overflow_dev += csr._overflow
         del csr
     ev1.record()
+    host_submit_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
     barrier()
     if int(overflow_dev.item()):
         raise SystemExit('edge capacity overflow: raise the bound')
@@ -488,6 +490,7 @@ def run_ours(args):
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(launches),
+            'host_submit_ms_per_step': host_submit_ms,
             'roofline': roofline,
             'cpu_baseline': cpu_baseline,
         }

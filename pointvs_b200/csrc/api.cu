@@ -1,4 +1,7 @@
 // Library-level entry points of the C ABI.
+#include <mutex>
+#include <vector>
+
 #include "pvs_common.cuh"
 
 namespace pvs {
@@ -14,6 +17,22 @@ int num_sms() {
         cached_dev = dev;
     }
     return cached > 0 ? cached : 148;
+}
+
+int ensure_dynamic_smem(const void *func, size_t bytes) {
+    struct Entry { const void *f; int dev; size_t bytes; };
+    static std::mutex mu;
+    static std::vector<Entry> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Entry &e : done)
+        if (e.f == func && e.dev == dev && e.bytes >= bytes) return PVS_OK;
+    int rc = cuda_call(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)bytes));
+    if (rc) return rc;
+    done.push_back({func, dev, bytes});
+    return PVS_OK;
 }
 
 int max_optin_smem() {

@@ -1017,8 +1017,7 @@ int pvs_linear_bwd(const float *in, int32_t ld_in, int32_t rows, int32_t ki,
     float *partial = (float *)p;
     const int kip = (ki + 3) & ~3;
     size_t smem = ((size_t)kip * 64 + 64 * 128 + (size_t)64 * (kip + 4) + 64 * LDT + 64) * sizeof(float);
-    int rc = cuda_call(cudaFuncSetAttribute(linear_bwd_data_kernel,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int rc = ensure_smem(linear_bwd_data_kernel, smem);
     if (rc) return rc;
     const int grid = persistent_grid((rows + 63) / 64, 1);
     linear_bwd_data_kernel<<<grid, BT, smem, st>>>(in, ld_in, rows, ki, w, ld_w, b, ko, act,
@@ -1115,8 +1114,7 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
     {
         size_t smem = ((size_t)128 * 64 + 64 * 64 * 2 + 64 * 128 + 64 * (2 * KB + 4) +
                        2 * 64 * LDT + 3 * 64) * sizeof(float);
-        rc = cuda_call(cudaFuncSetAttribute(egnn_node_bwd_kernel,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rc = ensure_smem(egnn_node_bwd_kernel, smem);
         if (rc) return rc;
         egnn_node_bwd_kernel<<<persistent_grid((n + 63) / 64, 1), BT, smem, st>>>(na);
         rc = check_launch();
@@ -1156,8 +1154,7 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
     eb.att_act = cfg->att_act;
     {
         size_t smem = sizeof(EdgeBwdSmem);
-        rc = cuda_call(cudaFuncSetAttribute(egnn_edge_bwd_kernel,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rc = ensure_smem(egnn_edge_bwd_kernel, smem);
         if (rc) return rc;
         egnn_edge_bwd_kernel<<<w.edge_grid, BT, smem, st>>>(eb);
         edge_bwd_reduce_kernel<<<(EP_STRIDE + 255) / 256, 256, 0, st>>>(

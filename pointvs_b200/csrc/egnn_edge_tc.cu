@@ -425,15 +425,11 @@ int launch_edge_tc(const EdgeArgs &a, int n_tiles_cap, int mode, cudaStream_t st
     if (grid < 1) grid = 1;
     int rc;
     if (mode == PVS_MATH_BF16X3) {
-        rc = cuda_call(cudaFuncSetAttribute(egnn_edge_tc_kernel<true>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
+        rc = ensure_smem(egnn_edge_tc_kernel<true>, smem);
         if (rc) return rc;
         egnn_edge_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(a);
     } else {
-        rc = cuda_call(cudaFuncSetAttribute(egnn_edge_tc_kernel<false>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
+        rc = ensure_smem(egnn_edge_tc_kernel<false>, smem);
         if (rc) return rc;
         egnn_edge_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(a);
     }

@@ -614,17 +614,13 @@ int launch_linear(const float *in, int ld_in, int rows, int ki,
     const int grid = persistent_grid(tiles, 2);
     int rc;
     if (nj4 == 1) {
-        rc = cuda_call(cudaFuncSetAttribute(linear_fwd_kernel<1>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
+        rc = ensure_smem(linear_fwd_kernel<1>, smem);
         if (rc) return rc;
         linear_fwd_kernel<1><<<grid, FWD_THREADS, smem, st>>>(
             in, ld_in, rows, ki, w, ld_w, b, ko, act, out, ld_out, w_in_major,
             accumulate);
     } else {
-        rc = cuda_call(cudaFuncSetAttribute(linear_fwd_kernel<2>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
+        rc = ensure_smem(linear_fwd_kernel<2>, smem);
         if (rc) return rc;
         linear_fwd_kernel<2><<<grid, FWD_THREADS, smem, st>>>(
             in, ld_in, rows, ki, w, ld_w, b, ko, act, out, ld_out, w_in_major,
@@ -636,9 +632,7 @@ int launch_linear(const float *in, int ld_in, int rows, int ki,
 template <int KP>
 static int launch_edge(const EdgeArgs &a, int n_tiles_cap, cudaStream_t st) {
     size_t smem = sizeof(EdgeSmem<KP>);
-    int rc = cuda_call(cudaFuncSetAttribute(egnn_edge_fwd_kernel<KP>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
+    int rc = ensure_smem(egnn_edge_fwd_kernel<KP>, smem);
     if (rc) return rc;
     const int grid = persistent_grid(n_tiles_cap, 2);
     egnn_edge_fwd_kernel<KP><<<grid, FWD_THREADS, smem, st>>>(a);
@@ -653,9 +647,7 @@ template <int KP>
 static int launch_node(const NodeArgs &a, cudaStream_t st) {
     size_t smem = ((size_t)3 * KP * 64 + (size_t)NODE_ROWS * (2 * KP + 4) +
                    (size_t)NODE_ROWS * (KP + 4) + 5 * 64) * sizeof(float);
-    int rc = cuda_call(cudaFuncSetAttribute(egnn_node_fwd_kernel<KP>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
+    int rc = ensure_smem(egnn_node_fwd_kernel<KP>, smem);
     if (rc) return rc;
     const int tiles = (a.n_nodes + NODE_ROWS - 1) / NODE_ROWS;
     const int grid = persistent_grid(tiles, 2);

@@ -417,13 +417,11 @@ int launch_node_pre_tc(const float *h, const float *edge_w1, const float *edge_b
     if (grid < 1) grid = 1;
     int rc;
     if (mode == PVS_MATH_BF16X3) {
-        rc = cuda_call(cudaFuncSetAttribute(node_pre_tc_kernel<true>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rc = ensure_smem(node_pre_tc_kernel<true>, smem);
         if (rc) return rc;
         node_pre_tc_kernel<true><<<grid, NP_THREADS, smem, st>>>(a);
     } else {
-        rc = cuda_call(cudaFuncSetAttribute(node_pre_tc_kernel<false>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rc = ensure_smem(node_pre_tc_kernel<false>, smem);
         if (rc) return rc;
         node_pre_tc_kernel<false><<<grid, NP_THREADS, smem, st>>>(a);
     }
@@ -447,13 +445,11 @@ int launch_node_tc(const float *h_in, const float *M, float *h_out, float *natt_
     if (grid < 1) grid = 1;
     int rc;
     if (mode == PVS_MATH_BF16X3) {
-        rc = cuda_call(cudaFuncSetAttribute(node_tc_kernel<true>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rc = ensure_smem(node_tc_kernel<true>, smem);
         if (rc) return rc;
         node_tc_kernel<true><<<grid, NM_THREADS, smem, st>>>(a);
     } else {
-        rc = cuda_call(cudaFuncSetAttribute(node_tc_kernel<false>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rc = ensure_smem(node_tc_kernel<false>, smem);
         if (rc) return rc;
         node_tc_kernel<false><<<grid, NM_THREADS, smem, st>>>(a);
     }

@@ -120,6 +120,8 @@ __device__ int smem_scan_excl(int *data, int n, int *warp_buf) {
 // ---------------------------------------------------------------------------
 constexpr int RG_THREADS = 512;
 constexpr int RG_WARPS = RG_THREADS / 32;
+constexpr int RG_SPLIT = 4;        // CTAs per complex (each bins all atoms,
+                                   // handles a quarter of the destinations)
 constexpr int RG_MAX_DIM = 16;
 constexpr int RG_MAX_CELLS = RG_MAX_DIM * RG_MAX_DIM * RG_MAX_DIM;
 
@@ -144,8 +146,11 @@ static size_t rg_smem_bytes(int max_n, bool with_prefix, bool stage) {
     return b;
 }
 
-__device__ __forceinline__ int cell_coord(double v, double lo, double cs, int dim) {
-    int c = (int)floor(__ddiv_rn(__dsub_rn(v, lo), cs));
+// cell index along one axis; `inv` = 1 / cell edge.  Monotone in v, and the same
+// expression bins the atoms and locates the query, so neighbours within r_max
+// (< cell edge / (1 + 1e-6)) are never more than one cell apart.
+__device__ __forceinline__ int cell_coord(double v, double lo, double inv, int dim) {
+    int c = (int)floor(__dmul_rn(__dsub_rn(v, lo), inv));
     return max(0, min(dim - 1, c));
 }
 
@@ -164,8 +169,9 @@ radius_graph_kernel(const double *__restrict__ coords,
                     int32_t *__restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RgSmem &S = *reinterpret_cast<RgSmem *>(smem_raw);
-    const int n0 = complex_ptr[blockIdx.x];
-    const int n = complex_ptr[blockIdx.x + 1] - n0;
+    const int cplx = blockIdx.x / RG_SPLIT, part = blockIdx.x % RG_SPLIT;
+    const int n0 = complex_ptr[cplx];
+    const int n = complex_ptr[cplx + 1] - n0;
     if (n <= 0 || n > max_n) return;   // host sizes smem from max_n
     const int words = (max_n + 31) / 32;
     int *sorted_idx = reinterpret_cast<int *>(smem_raw + sizeof(RgSmem));
@@ -226,10 +232,10 @@ radius_graph_kernel(const double *__restrict__ coords,
         double q = ext / cs0;
         if (q + 1.0 > (double)RG_MAX_DIM) {
             dim[a] = RG_MAX_DIM;
-            cs[a] = ext / RG_MAX_DIM * (1.0 + 1e-6);
+            cs[a] = 1.0 / (ext / RG_MAX_DIM * (1.0 + 1e-6));
         } else {
             dim[a] = (int)q + 1;
-            cs[a] = cs0;
+            cs[a] = 1.0 / cs0;
         }
     }
     const int ncell = dim[0] * dim[1] * dim[2];
@@ -281,7 +287,7 @@ radius_graph_kernel(const double *__restrict__ coords,
     unsigned *m_inter = masks + (size_t)warp * 2 * words;
     unsigned *m_intra = m_inter + words;
     const int nw = (n + 31) / 32;
-    for (int i = warp; i < n; i += RG_WARPS) {
+    for (int i = warp + RG_WARPS * part; i < n; i += RG_WARPS * RG_SPLIT) {
         for (int w = lane; w < nw; w += 32) {
             m_inter[w] = 0u;
             m_intra[w] = 0u;
@@ -687,11 +693,9 @@ int pvs_radius_graph_count(const double *coords, const int32_t *bp,
             smem = rg_smem_bytes(max_complex_nodes, false, false);
         }
         if (smem > (size_t)max_optin_smem()) return PVS_ERR_TOO_LARGE;
-        rc = cuda_call(cudaFuncSetAttribute(
-            radius_graph_kernel<false>,
-            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rc = ensure_smem(radius_graph_kernel<false>, smem);
         if (rc) return rc;
-        radius_graph_kernel<false><<<n_complexes, RG_THREADS, smem, st>>>(
+        radius_graph_kernel<false><<<n_complexes * RG_SPLIT, RG_THREADS, smem, st>>>(
             coords, bp, complex_ptr, inter_radius, intra_radius, deg, n_inter,
             nullptr, nullptr, nullptr, nullptr, nullptr, max_complex_nodes, stage,
             mask_scratch, 0, nullptr);
@@ -728,11 +732,9 @@ int pvs_radius_graph_fill(const double *coords, const int32_t *bp,
         smem = rg_smem_bytes(max_complex_nodes, ref_pos != nullptr, false);
     }
     if (smem > (size_t)max_optin_smem()) return PVS_ERR_TOO_LARGE;
-    rc = cuda_call(cudaFuncSetAttribute(
-        radius_graph_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        (int)smem));
+    rc = ensure_smem(radius_graph_kernel<true>, smem);
     if (rc) return rc;
-    radius_graph_kernel<true><<<n_complexes, RG_THREADS, smem,
+    radius_graph_kernel<true><<<n_complexes * RG_SPLIT, RG_THREADS, smem,
                                 (cudaStream_t)stream>>>(
         coords, bp, complex_ptr, inter_radius, intra_radius, nullptr, nullptr,
         n_inter, row_ptr, col, attr, ref_pos, max_complex_nodes, stage, nullptr,

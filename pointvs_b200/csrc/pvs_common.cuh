@@ -30,6 +30,13 @@ inline int cuda_call(cudaError_t e) {
 }
 
 int num_sms();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device,
+// size): it is a driver call and was being issued before every launch.
+int ensure_dynamic_smem(const void *func, size_t bytes);
+template <typename K>
+inline int ensure_smem(K kernel, size_t bytes) {
+    return ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), bytes);
+}
 int max_optin_smem();
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }

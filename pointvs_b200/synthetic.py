@@ -54,3 +54,38 @@ def synthetic_batch(first_seed, n_complexes, n_atoms=1000, n_lig=30,
         ptr.append(ptr[-1] + n)
     return (np.concatenate(coords), np.concatenate(bps),
             np.concatenate(feats), np.asarray(ptr, dtype=np.int32))
+
+
+def synthetic_pocket_poses(first_pose, n_poses, n_pocket=800, n_lig=30,
+                           density=DENSITY):
+    """BASELINE configs[4] shape: ONE fixed pocket (seed 0, inner cavity
+    removed) and `n_poses` ligand poses (seed = pose index) placed in the
+    cavity.  Returns the same packed arrays as synthetic_batch."""
+    rng = np.random.default_rng(0)
+    n_all = n_pocket + n_lig
+    ball_r = (3.0 * n_all / (4.0 * np.pi * density)) ** (1.0 / 3.0)
+    cavity_r = (3.0 * n_lig / (4.0 * np.pi * density)) ** (1.0 / 3.0)
+    direction = rng.normal(size=(n_pocket, 3))
+    direction /= np.linalg.norm(direction, axis=1, keepdims=True)
+    u = rng.random(n_pocket)
+    radius = (cavity_r ** 3 + u * (ball_r ** 3 - cavity_r ** 3)) ** (1.0 / 3.0)
+    pocket = (direction * radius[:, None]).astype(np.float32).astype(np.float64)
+    pocket_types = rng.integers(0, N_TYPES, n_pocket)
+    coords, bps, feats, ptr = [], [], [], [0]
+    for pose in range(first_pose, first_pose + n_poses):
+        prng = np.random.default_rng(1_000_003 + pose)
+        d = prng.normal(size=(n_lig, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        lig = d * (cavity_r * prng.random(n_lig) ** (1.0 / 3.0))[:, None]
+        lig = lig.astype(np.float32).astype(np.float64)
+        c = np.concatenate([lig, pocket])
+        types = np.concatenate([prng.integers(0, N_TYPES, n_lig), pocket_types])
+        bp = np.ones(n_all, dtype=np.int32)
+        bp[:n_lig] = 0
+        f = np.zeros((n_all, DIM_INPUT), dtype=np.float32)
+        f[np.arange(n_all), types] = 1.0
+        f[:, DIM_INPUT - 1] = bp
+        coords.append(c), bps.append(bp), feats.append(f)
+        ptr.append(ptr[-1] + n_all)
+    return (np.concatenate(coords), np.concatenate(bps), np.concatenate(feats),
+            np.asarray(ptr, dtype=np.int32))

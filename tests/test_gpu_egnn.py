@@ -313,3 +313,29 @@ def test_capacity_bounded_batch_scores_identically():
             outs.append(model(batch))
         batch.pvs_csr.check_overflow()
     assert torch.equal(outs[0], outs[1])
+
+
+def test_config5_pocket_poses_vs_oracle():
+    """BASELINE configs[4] shape: one 800-atom pocket, many 30-atom ligand
+    poses (830 atoms per complex), scored in one packed batch."""
+    from pointvs_b200.graph import PackedBatch
+    from pointvs_b200.synthetic import synthetic_pocket_poses
+    kw = dict(dim_input=13, dim_output=1, k=64, num_layers=8,
+              edge_attention=True, node_attention=True, residual=True,
+              normalize=True, tanh=True, graphnorm=False)
+    model = gh.build_model(kw, seed=0, coord_gain=1.0)
+    coords, bp, feats, cptr = synthetic_pocket_poses(0, 6)
+    assert cptr[1] == 830
+    batch = PackedBatch.from_arrays(coords, bp, feats, cptr, 4.0, 4.0)
+    pos0 = batch.pos.clone()
+    with torch.no_grad():
+        out = model(batch)
+    assert 10.0 < batch.pvs_csr.n_edges / (6 * 830) < 20.0
+    graph_cpu = SimpleNamespace(x=batch.x, pos=pos0,
+                                edge_index=batch.edge_index,
+                                edge_attr=batch.edge_attr, batch=batch.batch)
+    want, _ = gh.oracle_forward(model, kw, graph_cpu)
+    assert helpers.rel_err(out.cpu().numpy().reshape(-1),
+                           want.numpy().reshape(-1)) < SCORE_RTOL
+    # poses differ, so scores must differ
+    assert float(out.std()) > 0
