@@ -38,6 +38,7 @@ EDGE_RADIUS = 4.0
 FLOP_PER_EDGE_LAYER = 2 * (4 * 64 * 64 + 6 * 64)      # 33 536
 FLOP_PER_NODE_LAYER = 2 * (3 * 64 * 64 + 64)          # 24 704
 BYTES_PER_COMPLEX_FWD = 4.94e6
+NCU_EDGE_TRAFFIC_BYTES = 77.57e6 + 15.06e6   # profiles/r01_d_edge_tc_ncu_full.csv
 
 
 def parse_args():
@@ -49,8 +50,15 @@ def parse_args():
     ap.add_argument('--batch', type=int, default=128,
                     help='complexes per GPU per step')
     ap.add_argument('--atoms', type=int, default=1000)
-    ap.add_argument('--math', default=os.environ.get('PVS_MATH', 'fp32'),
-                    choices=['fp32', 'bf16x3', 'bf16'])
+    ap.add_argument('--math', default=os.environ.get('PVS_MATH', 'bf16x3'),
+                    choices=['fp32', 'bf16x3', 'bf16'],
+                    help='arithmetic of the edge/node contractions: fp32 = FFMA; '
+                         'bf16x3 = tcgen05 with error-compensated bf16 split '
+                         '(fp32-class: score error ~4e-6 vs the 1e-4 bound, the '
+                         'default); bf16 = single-pass tcgen05 (fast mode, ~3e-3)')
+    ap.add_argument('--other-modes', action='store_true',
+                    help='also time the other two math modes (short run) and '
+                         'report them under "modes"')
     ap.add_argument('--input-sets', type=int, default=3,
                     help='distinct input batches rotated through the steps')
     ap.add_argument('--cpu-sample', type=int, default=16,
@@ -436,7 +444,12 @@ def run_ours(args):
     roofline = {
         'kernel': 'egnn_edge_fwd (per-layer edge MLP + attention + segment reduce)',
         'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf,
-        'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf, 'traffic': None,
+        'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel,
+        # ncu --set full, profiles/r01_d_edge_tc_ncu_full.csv (tcgen05 modes, the
+        # default batch); null for other configurations
+        'traffic': NCU_EDGE_TRAFFIC_BYTES if (args.math != 'fp32' and args.batch == 128
+                                              and args.atoms == 1000) else None,
         'peak_source': peak_src,
         'algorithmic_flop_per_launch': flop_per_launch,
         'avg_launch_ms': avg_launch_s * 1e3,
@@ -449,6 +462,25 @@ def run_ours(args):
         'hbm_algorithmic_gbs': value / n_gpus * BYTES_PER_COMPLEX_FWD / 1e9,
         'hbm_peak_gbs': peaks.get('hbm_gbs'),
     }
+
+    modes = None
+    if args.other_modes:
+        modes = {}
+        for m in ('fp32', 'bf16x3', 'bf16'):
+            if m == args.math:
+                continue
+            model.set_math(m)
+            for i in range(2):
+                step_device(i)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(5):
+                step_device(i)
+            e1.record()
+            barrier()
+            modes[m] = args.batch * 5 * n_gpus / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+        model.set_math(args.math)
 
     cpu_baseline = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -480,8 +512,10 @@ def run_ours(args):
             'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None,
-            'dtype': {'fp32': 'f32', 'bf16x3': 'bf16x3 (fp32-class)',
-                      'bf16': 'bf16'}[args.math],
+            'dtype': {'fp32': 'f32',
+                      'bf16x3': 'f32 (tcgen05 bf16x3 error-compensated, '
+                                'fp32 accumulate; score error ~4e-6 rel)',
+                      'bf16': 'bf16 (single pass, score error ~3e-3 rel)'}[args.math],
             'data': 'synthetic',
             'config': workload_config(args),
             'edges_per_s': total_edges / (ms_total * 1e-3),
@@ -493,6 +527,7 @@ def run_ours(args):
             'host_submit_ms_per_step': host_submit_ms,
             'roofline': roofline,
             'cpu_baseline': cpu_baseline,
+            'modes': modes,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
