@@ -281,6 +281,42 @@ int pvs_egnn_layer_fwd(const pvs_graph *graph, const pvs_layer_config *cfg,
                        float *natt_out, void *workspace,
                        int64_t workspace_bytes, void *stream);
 
+/* ---- whole-model scoring pass ----------------------------------------------
+ * SartorrasEGNN.forward / MultitaskSatorrasEGNN.forward
+ * (pnn_geometric_base.py:24-41, egnn_multitask.py:150-166) in ONE call:
+ * embedding Linear -> n_layers x pvs_egnn_layer_fwd -> mean pool -> head
+ * (up to 3 Linear layers with fused activations).  Same kernels and the same
+ * results as issuing the per-layer calls; it exists so that a scoring step
+ * costs one host call instead of ~40 (the Python launch path was the
+ * bottleneck at ~4 ms of GPU work per step).  No side channels, no autograd.
+ *   feats [N][dim_input] (pitch ld_feats), x_in [N][3], graph_ptr [B+1].
+ *   scores [B][head[n_head-1].ko]; x_out [N][3] (final coordinates, may be
+ *   NULL or == x_in for the reference's in-place update); h_out [N][k] or NULL. */
+typedef struct pvs_head_layer {
+    const float *w;   /* [ko][ki] */
+    const float *b;   /* [ko] or NULL */
+    int32_t ki, ko;
+    int32_t act;      /* pvs_act applied after this Linear */
+} pvs_head_layer;
+
+typedef struct pvs_model_desc {
+    int32_t n_layers, k, dim_input, n_head;
+    const float *embed_w;                  /* layers.0.m.weight [k][dim_input] */
+    const float *embed_b;                  /* layers.0.m.bias   [k]            */
+    const pvs_layer_config *layer_cfg;     /* [n_layers] */
+    const pvs_layer_params *layer_params;  /* [n_layers] */
+    const pvs_head_layer *head;            /* [n_head], n_head <= 3 */
+} pvs_model_desc;
+
+int64_t pvs_egnn_model_workspace_bytes(int32_t n_nodes, int32_t n_edges,
+                                       int32_t n_graphs,
+                                       const pvs_model_desc *model);
+int pvs_egnn_model_fwd(const pvs_graph *graph, const pvs_model_desc *model,
+                       const float *feats, int32_t ld_feats, const float *x_in,
+                       const int32_t *graph_ptr, int32_t n_graphs,
+                       float *scores, float *x_out, float *h_out,
+                       void *workspace, int64_t workspace_bytes, void *stream);
+
 /* ---- K3: one EGNN layer, backward ---------------------------------------
  * Autograd of pvs_egnn_layer_fwd (PyTorch autograd of
  * egnn_satorras.py:123-206 in the reference).  Recomputes the layer from

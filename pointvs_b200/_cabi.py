@@ -68,6 +68,20 @@ class LayerGrads(C.Structure):
     _fields_ = [(n, _fp) for n in GRAD_FIELDS]
 
 
+class HeadLayer(C.Structure):
+    _fields_ = [('w', _fp), ('b', _fp), ('ki', C.c_int32), ('ko', C.c_int32),
+                ('act', C.c_int32)]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [('n_layers', C.c_int32), ('k', C.c_int32),
+                ('dim_input', C.c_int32), ('n_head', C.c_int32),
+                ('embed_w', _fp), ('embed_b', _fp),
+                ('layer_cfg', C.POINTER(LayerConfig)),
+                ('layer_params', C.POINTER(LayerParams)),
+                ('head', C.POINTER(HeadLayer))]
+
+
 class PvsError(RuntimeError):
     pass
 
@@ -90,6 +104,9 @@ def lib():
         handle.pvs_launch_count.restype = C.c_int64
         for name in ('pvs_scan_scratch_bytes', 'pvs_tiles_scratch_bytes',
                      'pvs_egnn_layer_workspace_bytes',
+                     'pvs_egnn_model_workspace_bytes',
+                     'pvs_radius_graph_mask_bytes',
+                     'pvs_linear_bwd_workspace_bytes',
                      'pvs_egnn_layer_bwd_workspace_bytes'):
             if hasattr(handle, name):
                 getattr(handle, name).restype = C.c_int64

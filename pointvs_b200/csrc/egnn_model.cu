@@ -1,0 +1,139 @@
+// Whole-model scoring pass: one C call per step (pvs_egnn_model_fwd).
+// Composition only -- every kernel is launched through the same code paths as
+// the per-layer entry points.
+#include "egnn_common.cuh"
+
+using namespace pvs;
+
+namespace {
+
+struct ModelWs {
+    float *h[2], *x[2], *m[2], *pooled, *head_tmp[2];
+    void *layer_ws;
+    int64_t layer_ws_bytes;
+    int64_t bytes;
+};
+
+bool any_edge_residual(const pvs_model_desc *md) {
+    for (int l = 0; l < md->n_layers; ++l)
+        if (md->layer_cfg[l].flags & PVS_F_EDGE_RESIDUAL) return true;
+    return false;
+}
+
+ModelWs carve_model(void *base, int n, int e, int b, const pvs_model_desc *md) {
+    ModelWs w{};
+    char *p = (char *)base;
+    auto take = [&](int64_t bytes) {
+        void *r = p;
+        p += align_up(bytes, 256);
+        return r;
+    };
+    const int k = md->k;
+    for (int i = 0; i < 2; ++i) w.h[i] = (float *)take((int64_t)n * k * 4);
+    for (int i = 0; i < 2; ++i) w.x[i] = (float *)take((int64_t)n * 3 * 4);
+    if (any_edge_residual(md))
+        for (int i = 0; i < 2; ++i) w.m[i] = (float *)take((int64_t)e * k * 4);
+    w.pooled = (float *)take((int64_t)b * k * 4);
+    for (int i = 0; i < 2; ++i) w.head_tmp[i] = (float *)take((int64_t)b * 128 * 4);
+    int64_t lw = 0;
+    for (int l = 0; l < md->n_layers; ++l) {
+        int64_t v = pvs_egnn_layer_workspace_bytes(n, e, &md->layer_cfg[l]);
+        if (v > lw) lw = v;
+    }
+    w.layer_ws_bytes = lw;
+    w.layer_ws = take(lw);
+    w.bytes = p - (char *)base;
+    return w;
+}
+
+int check_desc(const pvs_model_desc *md) {
+    if (!md || md->n_layers < 0 || md->n_head < 1 || md->n_head > 3) return PVS_ERR_INVALID_ARG;
+    if (md->k < 1 || md->k > PVS_MAX_K) return PVS_ERR_UNSUPPORTED_K;
+    if (md->dim_input < 1 || md->dim_input > 128) return PVS_ERR_INVALID_ARG;
+    if (!md->embed_w || !md->head || (md->n_layers > 0 && (!md->layer_cfg || !md->layer_params)))
+        return PVS_ERR_INVALID_ARG;
+    for (int l = 0; l < md->n_layers; ++l)
+        if (md->layer_cfg[l].k != md->k) return PVS_ERR_INVALID_ARG;
+    for (int i = 0; i < md->n_head; ++i) {
+        const pvs_head_layer &hl = md->head[i];
+        if (!hl.w || hl.ki < 1 || hl.ki > 128 || hl.ko < 1 || hl.ko > 128) return PVS_ERR_INVALID_ARG;
+    }
+    if (md->head[0].ki != md->k) return PVS_ERR_INVALID_ARG;
+    return PVS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t pvs_egnn_model_workspace_bytes(int32_t n_nodes, int32_t n_edges, int32_t n_graphs,
+                                       const pvs_model_desc *md) {
+    if (check_desc(md) != PVS_OK || n_nodes < 0 || n_edges < 0 || n_graphs < 0) return -1;
+    return carve_model(nullptr, n_nodes, n_edges, n_graphs, md).bytes + 256;
+}
+
+int pvs_egnn_model_fwd(const pvs_graph *g, const pvs_model_desc *md, const float *feats,
+                       int32_t ld_feats, const float *x_in, const int32_t *graph_ptr,
+                       int32_t n_graphs, float *scores, float *x_out, float *h_out,
+                       void *workspace, int64_t workspace_bytes, void *stream) {
+    int rc = check_desc(md);
+    if (rc) return rc;
+    if (!g || g->n_nodes < 0 || g->n_edges < 0 || n_graphs < 0) return PVS_ERR_INVALID_ARG;
+    if (g->n_nodes == 0 || n_graphs == 0) return PVS_OK;
+    if (!feats || !x_in || !graph_ptr || !scores || !workspace || ld_feats < md->dim_input)
+        return PVS_ERR_INVALID_ARG;
+    if (workspace_bytes < pvs_egnn_model_workspace_bytes(g->n_nodes, g->n_edges, n_graphs, md))
+        return PVS_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = g->n_nodes, k = md->k;
+    ModelWs w = carve_model((void *)align_up((int64_t)(uintptr_t)workspace, 256), n, g->n_edges,
+                            n_graphs, md);
+    // embedding (PygLinearPass)
+    rc = launch_linear(feats, ld_feats, n, md->dim_input, md->embed_w, md->dim_input,
+                       md->embed_b, k, PVS_ACT_NONE, w.h[0], k, st);
+    if (rc) return rc;
+    const float *h_cur = w.h[0];
+    const float *x_cur = x_in;
+    const float *m_cur = nullptr;
+    int hb = 0, xb = 0, mb = 0;
+    for (int l = 0; l < md->n_layers; ++l) {
+        const pvs_layer_config &cfg = md->layer_cfg[l];
+        const bool coords = cfg.flags & PVS_F_UPDATE_COORDS;
+        const bool next_eres = l + 1 < md->n_layers &&
+                               (md->layer_cfg[l + 1].flags & PVS_F_EDGE_RESIDUAL);
+        float *h_next = w.h[hb ^ 1];
+        float *x_next = coords ? w.x[xb] : nullptr;
+        float *m_next = next_eres ? w.m[mb] : nullptr;
+        rc = pvs_egnn_layer_fwd(g, &cfg, &md->layer_params[l], h_cur, x_cur,
+                                (cfg.flags & PVS_F_EDGE_RESIDUAL) ? m_cur : nullptr, h_next,
+                                x_next, m_next, nullptr, nullptr, w.layer_ws, w.layer_ws_bytes,
+                                stream);
+        if (rc) return rc;
+        h_cur = h_next; hb ^= 1;
+        if (coords) { x_cur = x_next; xb ^= 1; }
+        m_cur = m_next;
+        if (next_eres) mb ^= 1;
+    }
+    if (h_out) {
+        rc = cuda_call(cudaMemcpyAsync(h_out, h_cur, (size_t)n * k * 4, cudaMemcpyDeviceToDevice, st));
+        if (rc) return rc;
+    }
+    if (x_out && x_out != x_cur) {
+        rc = cuda_call(cudaMemcpyAsync(x_out, x_cur, (size_t)n * 3 * 4, cudaMemcpyDeviceToDevice, st));
+        if (rc) return rc;
+    }
+    rc = pvs_mean_pool_fwd(h_cur, graph_ptr, n_graphs, k, w.pooled, stream);
+    if (rc) return rc;
+    const float *in = w.pooled;
+    for (int i = 0; i < md->n_head; ++i) {
+        const pvs_head_layer &hl = md->head[i];
+        float *out = (i == md->n_head - 1) ? scores : w.head_tmp[i & 1];
+        rc = launch_linear(in, hl.ki, n_graphs, hl.ki, hl.w, hl.ki, hl.b, hl.ko, hl.act, out,
+                           hl.ko, st);
+        if (rc) return rc;
+        in = out;
+    }
+    return PVS_OK;
+}
+
+}  // extern "C"

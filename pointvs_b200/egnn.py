@@ -390,7 +390,124 @@ class PNNGeometricBase(PointNeuralNetworkBase):
         return (graph.x.float().to(dev), None, graph.pos.float().to(dev), None,
                 batch, csr)
 
+    # -- one-call scoring path ---------------------------------------------------
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop('_c_cache', None)      # parameter storage may move
+        return super()._apply(fn, *args, **kwargs)
+
+    def _fast_path_ok(self):
+        if torch.is_grad_enabled() and any(
+                p.requires_grad for p in self.parameters()):
+            return False
+        if STAGE_TIMER is not None and getattr(STAGE_TIMER, 'split_stages', True):
+            return False
+        egnn = [l for l in self.layers if isinstance(l, EGNNLayer)]
+        if any(l.record_side_channels for l in egnn):
+            return False
+        if getattr(self, 'record_embed_coords', True):
+            return False
+        return not self.layers[0].feats_appended_to_coords
+
+    def _c_model(self, head):
+        """ctypes descriptor of the whole model (cached; it holds raw pointers
+        into the live parameter storage, so in-place optimiser updates and
+        load_state_dict are seen without rebuilding)."""
+        cache = self.__dict__.setdefault('_c_cache', {})
+        egnn = [l for l in self.layers if isinstance(l, EGNNLayer)]
+        key = (id(head), tuple(l.math for l in egnn))
+        if key in cache:
+            return cache[key]
+        keep = []
+
+        def dptr(t):
+            if t is None:
+                return None
+            t = t.detach()
+            if not t.is_contiguous():
+                raise _cabi.PvsError('parameters must be contiguous')
+            keep.append(t)
+            return C.c_void_p(t.data_ptr())
+
+        cfgs = (_cabi.LayerConfig * max(1, len(egnn)))()
+        params = (_cabi.LayerParams * max(1, len(egnn)))()
+        for i, layer in enumerate(egnn):
+            cfgs[i] = layer.c_config()
+            params[i] = _cabi.LayerParams(*[dptr(p) for p in layer.param_list()])
+        mods = list(head)
+        heads = []
+        i = 0
+        while i < len(mods):
+            lin = mods[i]
+            if not isinstance(lin, nn.Linear):
+                raise NotImplementedError(f'head module {type(lin).__name__}')
+            act = 'none'
+            if i + 1 < len(mods) and not isinstance(mods[i + 1], nn.Linear):
+                act = {nn.SiLU: 'silu', nn.ReLU: 'relu',
+                       nn.Softplus: 'softplus'}[type(mods[i + 1])]
+                i += 1
+            heads.append(_cabi.HeadLayer(dptr(lin.weight), dptr(lin.bias),
+                                         lin.in_features, lin.out_features,
+                                         _cabi.ACT[act]))
+            i += 1
+        head_arr = (_cabi.HeadLayer * len(heads))(*heads)
+        embed = self.layers[0].m
+        desc = _cabi.ModelDesc(len(egnn), egnn[0].hidden_nf if egnn else
+                               embed.out_features, embed.in_features,
+                               len(heads), dptr(embed.weight), dptr(embed.bias),
+                               cfgs, params, head_arr)
+        cache[key] = (desc, cfgs, (params, head_arr, keep), heads[-1].ko)
+        return cache[key]
+
+    def _forward_fast(self, graph, head):
+        """Whole scoring pass in one C call (pvs_egnn_model_fwd)."""
+        dev = self.device_for_inputs()
+        csr = getattr(graph, 'pvs_csr', None)
+        feats = graph.x.float().to(dev).contiguous()
+        pos = graph.pos.float().to(dev).contiguous()
+        if csr is None:
+            csr = _csr_for(graph.edge_index.to(dev), graph.edge_attr.to(dev),
+                           feats.shape[0])
+        graph_ptr = getattr(graph, 'graph_ptr', None)
+        if graph_ptr is None:
+            from .dense import batch_to_ptr
+            batch = graph.batch.to(dev)
+            n_graphs = int(batch.max().item()) + 1   # as the reference (:27)
+            graph_ptr = batch_to_ptr(batch, n_graphs)
+        n_graphs = int(graph_ptr.numel()) - 1
+        desc, cfgs, _keep, dim_out = self._c_model(head)
+        timer = STAGE_TIMER
+        if timer is not None:
+            for i in range(desc.n_layers):
+                cfgs[i].ev_edge_begin, cfgs[i].ev_edge_end = \
+                    timer.next_edge_events()
+        elif cfgs[0].ev_edge_begin:
+            for i in range(desc.n_layers):
+                cfgs[i].ev_edge_begin = cfgs[i].ev_edge_end = None
+        h = lib()
+        nbytes = int(h.pvs_egnn_model_workspace_bytes(
+            csr.n_nodes, csr.n_edges, n_graphs, C.byref(desc)))
+        if nbytes < 0:
+            raise _cabi.PvsError(
+                f'unsupported model for the fused scoring pass (k={desc.k}; '
+                f'hidden width must be 1..{_cabi.MAX_K})')
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        scores = torch.empty((n_graphs, dim_out), dtype=torch.float32,
+                             device=dev)
+        g = csr.c_struct()
+        with torch.cuda.device(dev):
+            check(h.pvs_egnn_model_fwd(
+                C.byref(g), C.byref(desc), ptr(feats), feats.shape[1],
+                ptr(pos), ptr(graph_ptr), n_graphs, ptr(scores), ptr(pos),
+                None, ptr(ws), C.c_int64(nbytes), stream()),
+                'pvs_egnn_model_fwd')
+        if pos.data_ptr() != graph.pos.data_ptr() and \
+                graph.pos.dtype == torch.float32 and graph.pos.is_cuda:
+            graph.pos.copy_(pos)      # keep the in-place coordinate update
+        return scores.reshape(-1) if n_graphs == 1 else scores
+
     def forward(self, x):
+        if self.feats_linear_layers is not None and self._fast_path_ok():
+            return self._forward_fast(x, self.feats_linear_layers)
         feats, edges, coords, edge_attributes, batch, csr = \
             self._unpack_for_forward(x)
         feats, _ = self.get_embeddings(
@@ -478,6 +595,7 @@ class SartorrasEGNN(PNNGeometricBase):
         for layer in self.layers:
             if isinstance(layer, EGNNLayer):
                 layer.math = math
+        self.__dict__.pop('_c_cache', None)
         return self
 
     def set_record_side_channels(self, on):
@@ -584,6 +702,11 @@ class MultitaskSatorrasEGNN(SartorrasEGNN):
         return nn.Sequential(*embedding_layers)
 
     def forward(self, graph):
+        head = self.feats_linear_layers_pose \
+            if 'classification' in self.model_task \
+            else self.feats_linear_layers_affinity
+        if self._fast_path_ok():
+            return self._forward_fast(graph, head)
         feats, edges, coords, edge_attributes, batch, csr = \
             self._unpack_for_forward(graph)
         feats, _ = self.get_embeddings(

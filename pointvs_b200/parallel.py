@@ -97,9 +97,10 @@ class GradAllReducer:
         off = 0
         for p in self.params:
             n = p.numel()
-            if p.grad is None:
-                p.grad = flat[off:off + n].view_as(p).clone()
-            else:
+            # a parameter unused on this rank is unused on every rank (same
+            # model, same task): leave its grad None so the optimiser skips
+            # it exactly as a single process would
+            if p.grad is not None:
                 p.grad.copy_(flat[off:off + n].view_as(p))
             off += n
 

@@ -71,16 +71,18 @@ def main():
     model.zero_grad()
     out = model(batch_of(all_c, labels)).reshape(-1)
     torch.nn.functional.binary_cross_entropy_with_logits(out, labels).backward()
+    used = [p.grad is not None for p in model.parameters()]
     ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()
                      if p.grad is not None]).clone()
     # data-parallel: each rank its shard, then the flat all-reduce
     reducer = parallel.make_data_parallel(model)
-    model.zero_grad()
+    model.zero_grad(set_to_none=True)
     lo, hi = rank * per_rank, (rank + 1) * per_rank
     out = model(batch_of(all_c[lo:hi], labels[lo:hi])).reshape(-1)
     torch.nn.functional.binary_cross_entropy_with_logits(
         out, labels[lo:hi]).backward()
     reducer.sync()
+    assert used == [p.grad is not None for p in model.parameters()]
     got = torch.cat([p.grad.reshape(-1) for p in model.parameters()
                      if p.grad is not None])
     gerr = float((got - ref).abs().max() / ref.abs().max())

@@ -339,3 +339,50 @@ def test_config5_pocket_poses_vs_oracle():
                            want.numpy().reshape(-1)) < SCORE_RTOL
     # poses differ, so scores must differ
     assert float(out.std()) > 0
+
+
+@pytest.mark.parametrize('name', ['cfg3_k32', 'gated_tanhatt_multifc',
+                                  'multitask_firstfinal', 'alloff_multitask',
+                                  'testkwargs_fixture82',
+                                  'rezero_perminv_static'])
+def test_one_call_scoring_path_equals_layerwise_path(name):
+    """pvs_egnn_model_fwd (side channels off) vs the per-layer calls: same
+    kernels, so bitwise equal scores and the same in-place coordinate update;
+    and still within 1e-4 of the reference golden."""
+    _, _, tasks = helpers.MODEL_GOLDENS[name]
+    for task in tasks:
+        model, g = gh.cuda_model(name, task)
+        slow_graph = gh.cuda_graph(g)
+        with torch.no_grad():
+            slow = model(slow_graph)
+        assert not model._fast_path_ok()
+        model.set_record_side_channels(False)
+        model.record_embed_coords = False
+        assert model._fast_path_ok()
+        fast_graph = gh.cuda_graph(g)
+        with torch.no_grad():
+            fast = model(fast_graph)
+        assert torch.equal(fast, slow)
+        assert torch.equal(fast_graph.pos, slow_graph.pos)
+        assert helpers.rel_err(fast.cpu().numpy().reshape(-1),
+                               g[f'out.{task}'].reshape(-1)) < SCORE_RTOL
+        # with grad enabled the autograd path must be taken
+        model.train()
+        assert not model._fast_path_ok()
+
+
+def test_one_call_path_sees_in_place_parameter_updates():
+    kw = dict(dim_input=13, dim_output=1, k=32, num_layers=2, graphnorm=False,
+              edge_attention=True)
+    model = gh.build_model(kw, seed=4)
+    model.set_record_side_channels(False)
+    model.record_embed_coords = False
+    with torch.no_grad():
+        a = model(gh.synthetic_graph(3, 2, 150, 10))
+        for p in model.parameters():
+            p.mul_(1.1)                     # what an optimiser step does
+        b = model(gh.synthetic_graph(3, 2, 150, 10))
+        model.set_record_side_channels(True)
+        c = model(gh.synthetic_graph(3, 2, 150, 10))
+    assert not torch.equal(a, b)
+    assert torch.equal(b, c)
