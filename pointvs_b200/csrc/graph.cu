@@ -604,12 +604,15 @@ __global__ void segment_sort_kernel(const int32_t *__restrict__ ptr, int n_nodes
 __global__ void csr_gather_kernel(const int64_t *__restrict__ edge_col,
                                   const int64_t *__restrict__ onehot,
                                   int n_classes, const int32_t *__restrict__ perm,
+                                  const int32_t *__restrict__ n_valid,
                                   int64_t n_edges, int n_nodes,
                                   int32_t *__restrict__ col,
                                   uint8_t *__restrict__ attr,
                                   int32_t *__restrict__ bad) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_edges) return;
+    // edges with an out-of-range row were never placed: slots past the valid
+    // count hold no permutation entry
+    if (p >= n_edges || p >= *n_valid) return;
     const int e = perm[p];
     int64_t c = edge_col[e];
     if (c < 0 || c >= n_nodes) {
@@ -832,7 +835,7 @@ int pvs_edge_index_to_csr(const int64_t *edge_index, int64_t n_edges,
                                                                perm);
         csr_gather_kernel<<<nb, T, 0, st>>>(edge_index + n_edges,
                                             edge_attr_onehot, n_classes, perm,
-                                            n_edges, n_nodes, col, attr,
+                                            row_ptr + n_nodes, n_edges, n_nodes, col, attr,
                                             bad_index);
         g_launches += 3;
     }

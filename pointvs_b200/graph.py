@@ -156,8 +156,22 @@ class CSRGraph:
         return a
 
 
-def _as_i32(x, device):
-    return torch.as_tensor(np.asarray(x, dtype=np.int32)).to(device)
+_INT_CACHE = {}
+
+
+def _device_ints(arr, device):
+    """Small host int32 array -> device tensor, cached by content.  A copy
+    from pageable host memory blocks the host until the stream drains, i.e. a
+    hidden full sync in every step; batches of a repeated shape (the common
+    case in screening) hit the cache instead."""
+    key = (str(device), arr.tobytes())
+    t = _INT_CACHE.get(key)
+    if t is None:
+        if len(_INT_CACHE) > 256:
+            _INT_CACHE.clear()
+        t = torch.from_numpy(arr.copy()).to(device)
+        _INT_CACHE[key] = t
+    return t
 
 
 def radius_graph_batch(coords, bp, complex_ptr, inter_radius=4.0,
@@ -187,7 +201,7 @@ def radius_graph_batch(coords, bp, complex_ptr, inter_radius=4.0,
     if n_complexes < 0 or (n_complexes >= 0 and int(cptr_host[-1]) != n):
         raise ValueError('complex_ptr must end at the number of atoms')
     max_n = int(np.max(np.diff(cptr_host))) if n_complexes > 0 else 0
-    cptr = torch.from_numpy(cptr_host).to(device)
+    cptr = _device_ints(cptr_host, device)
     deg = torch.empty(max(1, n), dtype=torch.int32, device=device)
     n_inter = torch.empty(max(1, n), dtype=torch.int32, device=device)
     row_ptr = torch.empty(n + 1, dtype=torch.int32, device=device)

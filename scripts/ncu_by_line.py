@@ -44,6 +44,8 @@ def main():
     hdr = rows[hdr_i]
     insts = [dict(zip(hdr, r)) for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
     lm = line_map(cubin, kernel)
+    if len(insts) > len(lm) and len(insts) % len(lm) == 0:
+        insts = insts[:len(lm)]      # several launches captured: use the first
     if len(lm) != len(insts):
         print(f'warning: {len(insts)} profiled vs {len(lm)} disassembled')
     agg = collections.defaultdict(lambda: [0, 0, 0])
@@ -58,7 +60,7 @@ def main():
         tot_s += s
     print(f'total warp-instructions {tot_i}, samples {tot_s}')
     src = {}
-    for loc, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+    for loc, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
         text = ''
         if loc:
             try:

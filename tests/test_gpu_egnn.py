@@ -355,19 +355,18 @@ def test_one_call_scoring_path_equals_layerwise_path(name):
         slow_graph = gh.cuda_graph(g)
         with torch.no_grad():
             slow = model(slow_graph)
-        assert not model._fast_path_ok()
+            assert not model._fast_path_ok()     # side channels are on
         model.set_record_side_channels(False)
         model.record_embed_coords = False
-        assert model._fast_path_ok()
         fast_graph = gh.cuda_graph(g)
         with torch.no_grad():
+            assert model._fast_path_ok()
             fast = model(fast_graph)
         assert torch.equal(fast, slow)
         assert torch.equal(fast_graph.pos, slow_graph.pos)
         assert helpers.rel_err(fast.cpu().numpy().reshape(-1),
                                g[f'out.{task}'].reshape(-1)) < SCORE_RTOL
         # with grad enabled the autograd path must be taken
-        model.train()
         assert not model._fast_path_ok()
 
 
