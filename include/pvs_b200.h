@@ -141,12 +141,15 @@ typedef struct pvs_layer_params {
     const float *node_gate; /* node_gate_parameter [1] */
 } pvs_layer_params;
 
-/* Gradients of pvs_layer_params, same shapes; accumulated into (+=). */
+/* Gradients of pvs_layer_params: same members, same shapes, accumulated into
+ * (+=); NULL members are skipped. */
 typedef struct pvs_layer_grads {
     float *edge_w1, *edge_b1, *edge_w2, *edge_b2;
     float *coord_w1, *coord_b1, *coord_w2;
     float *att_w, *att_b;
-    float *node_w1, *node_b1, *node_w2, *node_b2;
+    float *node_w1, *node_b1;
+    float *gn_weight, *gn_bias, *gn_mean_scale;
+    float *node_w2, *node_b2;
     float *natt_w, *natt_b;
     float *edge_gate, *node_gate;
 } pvs_layer_grads;
@@ -328,8 +331,8 @@ int pvs_egnn_model_fwd(const pvs_graph *graph, const pvs_model_desc *model,
  *   d_h_in [N][k], d_x_in [N][3] are overwritten; d_m_prev [E][k] is
  *   overwritten when the layer has an edge residual and m_prev != NULL.
  *   Parameter gradients are ACCUMULATED into `grads` (NULL members skipped).
- * Returns PVS_ERR_UNSUPPORTED for PVS_F_GRAPHNORM / PVS_F_SOFTMAX_ATTENTION
- * (their backward is not implemented yet). */
+ * GraphNorm (batch-wide statistics) and softmax attention are differentiated
+ * too. */
 int pvs_csr_transpose(const pvs_graph *graph, int32_t *csc_ptr,
                       int32_t *csc_eid, void *scratch, void *stream);
 int64_t pvs_egnn_layer_bwd_workspace_bytes(int32_t n_nodes, int32_t n_edges,

@@ -54,10 +54,7 @@ PARAM_FIELDS = ('edge_w1', 'edge_b1', 'edge_w2', 'edge_b2', 'coord_w1',
                 'coord_b1', 'coord_w2', 'att_w', 'att_b', 'node_w1', 'node_b1',
                 'gn_weight', 'gn_bias', 'gn_mean_scale', 'node_w2', 'node_b2',
                 'natt_w', 'natt_b', 'edge_gate', 'node_gate')
-GRAD_FIELDS = ('edge_w1', 'edge_b1', 'edge_w2', 'edge_b2', 'coord_w1',
-               'coord_b1', 'coord_w2', 'att_w', 'att_b', 'node_w1', 'node_b1',
-               'node_w2', 'node_b2', 'natt_w', 'natt_b', 'edge_gate',
-               'node_gate')
+GRAD_FIELDS = PARAM_FIELDS
 
 
 class LayerParams(C.Structure):
@@ -139,3 +136,21 @@ def require_cuda(*tensors):
         if t is not None and not t.is_cuda:
             raise PvsError('pointvs_b200 kernels need CUDA tensors; there is '
                            'no CPU fallback')
+
+
+_SCRATCH = {}
+
+
+def scratch(name, nbytes, device):
+    """Grow-only device scratch buffer, reused across calls on the same
+    stream.  Reuse is safe because every kernel that touches it is ordered on
+    that stream; it keeps a run-ahead host from growing the allocator (a
+    cudaMalloc is a device-wide sync) and saves an allocator call per use.
+    Only for memory that never escapes to the caller."""
+    key = (name, str(device), torch.cuda.current_stream(device).cuda_stream)
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes * 1.25), 256), dtype=torch.uint8,
+                          device=device)
+        _SCRATCH[key] = buf
+    return buf

@@ -21,11 +21,6 @@ def _zeros_like_or_none(p):
 def egnn_layer_backward(ctx, d_h, d_x, d_m):
     layer, csr = ctx.layer, ctx.csr
     h, x, m_prev, *params = ctx.saved_tensors
-    if layer.graphnorm or (layer.edge_attention and layer.softmax_attention):
-        raise NotImplementedError(
-            'backward through GraphNorm / softmax attention is not implemented '
-            'in the CUDA path yet (train with graphnorm=False, '
-            'softmax_attention=False; scoring supports both)')
     cfg = layer.c_config()
     n, e, k = csr.n_nodes, csr.n_edges, layer.hidden_nf
     dev = h.device
@@ -59,7 +54,7 @@ def egnn_layer_backward(ctx, d_h, d_x, d_m):
     param_grads = []
     for name, p in zip(_cabi.PARAM_FIELDS, params):
         if p is None or name not in grads or grads[name] is None:
-            param_grads.append(None)   # GraphNorm params: unsupported above
+            param_grads.append(None)
         else:
             param_grads.append(grads[name].reshape(p.shape))
     return (None, None, None, None, d_h_in, d_x_in, d_m_prev, *param_grads)

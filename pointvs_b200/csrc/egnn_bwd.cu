@@ -234,6 +234,13 @@ struct NodeBwdArgs {
     int n_nodes, k;
     uint32_t flags;
     int att_act;
+    // GraphNorm (phase 1: stop at dy = dL/d(gn output); phase 2: resume from dv)
+    int phase;                     // 0 = no GraphNorm
+    const float *V;                // [N][64] pre-activation (phase 1, 2)
+    const float *gn_a, *gn_b;      // y = a v + b
+    const float *gn_shift, *gn_invstd;   // c_hat = (v - shift) * invstd
+    float *DY, *DYC;               // [N][64] dy and dy * c_hat (phase 1 out, 2 in)
+    const float *coef;             // [3][64]: dv = c0 dy + c1 c_hat + c2 (phase 2)
 };
 
 __global__ void __launch_bounds__(BT)
@@ -248,8 +255,10 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
     float *Us = IN + 64 * LDIN;        // [64][LDT]
     float *Gs = Us + 64 * LDT;         // [64][LDT]
     float *b1 = Gs + 64 * LDT, *b2 = b1 + 64, *wn = b2 + 64;
+    float *gnv = wn + 64;   // [7][64]: a, b, shift, invstd, coef0..2
     const int tid = threadIdx.x, rg = tid >> 4, cg = tid & 15;
     const int k = a.k;
+    const int phase = a.phase;
     for (int idx = tid; idx < 128 * 64; idx += BT) {
         int kk = idx >> 6, n = idx & 63;
         int src = kk < KB ? kk : k + (kk - KB);
@@ -271,6 +280,12 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
         b1[n] = n < k ? a.node_b1[n] : 0.0f;
         b2[n] = n < k ? a.node_b2[n] : 0.0f;
         wn[n] = (n < k && a.natt_w) ? a.natt_w[n] : 0.0f;
+        gnv[n] = phase ? a.gn_a[n] : 1.0f;
+        gnv[64 + n] = phase ? a.gn_b[n] : 0.0f;
+        gnv[128 + n] = phase ? a.gn_shift[n] : 0.0f;
+        gnv[192 + n] = phase ? a.gn_invstd[n] : 0.0f;
+        for (int c = 0; c < 3; ++c)
+            gnv[256 + 64 * c + n] = (phase == 2) ? a.coef[64 * c + n] : 0.0f;
     }
     const bool f_natt = (a.flags & PVS_F_NODE_ATTENTION) && a.natt_w != nullptr;
     const bool f_res = a.flags & PVS_F_RESIDUAL;
@@ -290,18 +305,51 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
             IN[r * LDIN + KB + c] = ok ? a.M[(size_t)(r0 + r) * KB + c] : 0.0f;
         }
         __syncthreads();
+        if (phase == 2) {
+            // resume: dv = c0 dy + c1 c_hat + c2 (GraphNorm backward, all rows)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = rg + 16 * i;
+                float4 dy = make_float4(0.f, 0.f, 0.f, 0.f), v4 = dy;
+                const bool ok = r0 + r < a.n_nodes;
+                if (ok) {
+                    dy = *reinterpret_cast<const float4 *>(&a.DY[(size_t)(r0 + r) * KB + 4 * cg]);
+                    v4 = *reinterpret_cast<const float4 *>(&a.V[(size_t)(r0 + r) * KB + 4 * cg]);
+                }
+                const float dyv[4] = {dy.x, dy.y, dy.z, dy.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+                float dv[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int n = 4 * cg + c;
+                    const float chat = (vv[c] - gnv[128 + n]) * gnv[192 + n];
+                    dv[c] = (ok && n < k) ? gnv[256 + n] * dyv[c] + gnv[320 + n] * chat + gnv[384 + n]
+                                          : 0.0f;
+                }
+                *reinterpret_cast<float4 *>(&Gs[r * LDT + 4 * cg]) =
+                    make_float4(dv[0], dv[1], dv[2], dv[3]);
+                if (ok)
+                    *reinterpret_cast<float4 *>(&a.DV[(size_t)(r0 + r) * KB + 4 * cg]) =
+                        make_float4(dv[0], dv[1], dv[2], dv[3]);
+            }
+        } else {
         // forward recompute: v -> u
         float sgv[4][4];
         {
             float acc[4][1][4] = {};
-            tile_gemm<4, 1>(IN, LDIN, W1t, 2 * KB, acc);
+            if (phase == 0) tile_gemm<4, 1>(IN, LDIN, W1t, 2 * KB, acc);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int r = rg + 16 * i;
                 float u[4];
+                float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (phase == 1 && r0 + r < a.n_nodes)
+                    v4 = *reinterpret_cast<const float4 *>(&a.V[(size_t)(r0 + r) * KB + 4 * cg]);
+                const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const float v = acc[i][0][c] + b1[4 * cg + c];
+                    const int n = 4 * cg + c;
+                    const float v = phase == 0 ? acc[i][0][c] + b1[n]
+                                               : fmaf(gnv[n], vv[c], gnv[64 + n]);
                     u[c] = siluf_(v);
                     sgv[i][c] = silu_gradf_(v);
                 }
@@ -314,7 +362,6 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
         }
         __syncthreads();
         // o, node attention, residual; then their backward down to `do`
-        float dres[4][4];
         {
             float acc[4][1][4] = {};
             tile_gemm<4, 1>(Us, LDT, W2t, KB, acc);
@@ -342,12 +389,12 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
                 for (int c = 0; c < 4; ++c) {
                     const float o2 = o[c] * s;
                     if (f_rez) {            // h' = h + g o2
-                        do2[c] = gate * gh[c]; dres[i][c] = gh[c]; gd = fmaf(gh[c], o2, gd);
+                        do2[c] = gate * gh[c]; gd = fmaf(gh[c], o2, gd);
                     } else if (f_gat) {     // h' = G o2 + (1 - G) h
-                        do2[c] = G * gh[c]; dres[i][c] = (1.0f - G) * gh[c];
+                        do2[c] = G * gh[c];
                         if (gate > 0.0f) gd = fmaf(gh[c], o2 - hv[c], gd);
                     } else {
-                        do2[c] = gh[c]; dres[i][c] = f_res ? gh[c] : 0.0f;
+                        do2[c] = gh[c];
                     }
                     dsd = fmaf(do2[c], o[c], dsd);
                 }
@@ -388,6 +435,26 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
                 float dv[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) dv[c] = acc[i][0][c] * sgv[i][c];
+                if (phase == 1) {
+                    // dv here is dy = dL/d(GraphNorm output): hand it, and
+                    // dy * c_hat, to the batch-wide reductions
+                    if (r0 + r < a.n_nodes) {
+                        const float4 v4 = *reinterpret_cast<const float4 *>(
+                            &a.V[(size_t)(r0 + r) * KB + 4 * cg]);
+                        const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+                        float dyc[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int n = 4 * cg + c;
+                            dyc[c] = dv[c] * (vv[c] - gnv[128 + n]) * gnv[192 + n];
+                        }
+                        *reinterpret_cast<float4 *>(&a.DY[(size_t)(r0 + r) * KB + 4 * cg]) =
+                            make_float4(dv[0], dv[1], dv[2], dv[3]);
+                        *reinterpret_cast<float4 *>(&a.DYC[(size_t)(r0 + r) * KB + 4 * cg]) =
+                            make_float4(dyc[0], dyc[1], dyc[2], dyc[3]);
+                    }
+                    continue;
+                }
                 *reinterpret_cast<float4 *>(&Gs[r * LDT + 4 * cg]) =
                     make_float4(dv[0], dv[1], dv[2], dv[3]);
                 if (r0 + r < a.n_nodes)
@@ -395,6 +462,8 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
                         make_float4(dv[0], dv[1], dv[2], dv[3]);
             }
         }
+        }   // phase != 2
+        if (phase == 1) continue;
         __syncthreads();
         // d[h ; M] = dv . W1
         {
@@ -407,7 +476,11 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int n = 4 * cg + c;
-                    if (n < k) a.d_h_in[(size_t)r * k + n] = dres[i][c] + acc[i][0][c];
+                    if (n >= k) continue;
+                    // residual branch of dL/dh: gh (plain, rezero), (1 - G) gh (gated)
+                    const float gh = a.d_h_out[(size_t)r * k + n];
+                    const float dres = !f_res ? 0.0f : (f_gat ? (1.0f - G) * gh : gh);
+                    a.d_h_in[(size_t)r * k + n] = dres + acc[i][0][c];
                 }
                 *reinterpret_cast<float4 *>(&a.dM[(size_t)r * KB + 4 * cg]) =
                     make_float4(acc[i][1][0], acc[i][1][1], acc[i][1][2], acc[i][1][3]);
@@ -436,6 +509,8 @@ struct EdgeBwdArgs {
     float *d_x_in;          // [N][3]
     float *d_m_prev;        // [E][k] or null
     float *partial;         // [grid][EP_STRIDE]
+    const float *alpha_in;  // [E] softmax attention values (softmax mode) or null
+    const float *seg_s;     // [N] sum over the dst segment of alpha * d(alpha)
     const float *edge_w1, *edge_w2, *edge_b2, *coord_w1, *coord_b1, *coord_w2;
     const float *att_w, *att_b, *edge_gate;
     int k, in_e, n_classes;
@@ -477,6 +552,7 @@ egnn_edge_bwd_kernel(const EdgeBwdArgs a) {
     const bool f_rez = f_eres && (a.flags & PVS_F_REZERO);
     const bool f_gat = f_eres && (a.flags & PVS_F_GATED_RESIDUAL);
     const bool f_norm = a.flags & PVS_F_NORMALIZE;
+    const bool f_softmax = f_att && (a.flags & PVS_F_SOFTMAX_ATTENTION) && a.alpha_in != nullptr;
 
     load_wt(S.W2t, 64, 64, a.edge_w2, k, k, k);
     load_wt(S.Wc1t, 64, 64, a.coord_w1, k, k, k);
@@ -704,10 +780,19 @@ egnn_edge_bwd_kernel(const EdgeBwdArgs a) {
                     float dot = d4.x * m4.x + d4.y * m4.y + d4.z * m4.z + d4.w * m4.w;
                     dot = rowgroup_sum(dot);
                     if (cg == 0) {
-                        const float z = S.e_z[r];
-                        const float al = apply_act(z, a.att_act);
-                        S.e_alpha[r] = al;
-                        S.e_dza[r] = r < ne ? dot * act_grad(z, al, a.att_act) : 0.0f;
+                        if (f_softmax) {
+                            // alpha = softmax over the dst segment:
+                            // dz = alpha (d alpha - sum_seg alpha d alpha)
+                            const float al = r < ne ? a.alpha_in[c0 + r] : 0.0f;
+                            S.e_alpha[r] = al;
+                            S.e_dza[r] = r < ne
+                                ? al * (dot - a.seg_s[n0 + S.e_rowl[r]]) : 0.0f;
+                        } else {
+                            const float z = S.e_z[r];
+                            const float al = apply_act(z, a.att_act);
+                            S.e_alpha[r] = al;
+                            S.e_dza[r] = r < ne ? dot * act_grad(z, al, a.att_act) : 0.0f;
+                        }
                     }
                 }
             }
@@ -960,14 +1045,59 @@ __global__ void add_inplace_kernel(float *__restrict__ dst, const float *__restr
     if (i < n) dst[i] += src[i];
 }
 
+// softmax attention: S_i = sum_{e in segment i} alpha_e (dM_i . m_e).  Warp per node.
+__global__ void __launch_bounds__(256)
+softmax_bwd_prep_kernel(const int32_t *__restrict__ row_ptr, int n_nodes,
+                        const float *__restrict__ alpha, const float *__restrict__ m /*[E][64]*/,
+                        const float *__restrict__ dM, float *__restrict__ seg_s) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n_nodes) return;
+    const float2 d2 = *reinterpret_cast<const float2 *>(dM + (size_t)i * KB + 2 * lane);
+    float s = 0.0f;
+    for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
+        const float2 m2 = *reinterpret_cast<const float2 *>(m + (size_t)e * KB + 2 * lane);
+        const float dot = warp_sum(d2.x * m2.x + d2.y * m2.y);
+        s = fmaf(alpha[e], dot, s);
+    }
+    if (lane == 0) seg_s[i] = s;
+}
+
+// GraphNorm backward coefficients from the batch reductions R1 = sum dy,
+// R2 = sum dy c_hat:  dv = c0 dy + c1 c_hat + c2; also the parameter gradients.
+__global__ void gn_bwd_coef_kernel(const float *__restrict__ R1, const float *__restrict__ R2,
+                                   int n, int k, const float *__restrict__ gn_w,
+                                   const float *__restrict__ gn_ms,
+                                   const float *__restrict__ mean,
+                                   const float *__restrict__ invstd, float *__restrict__ coef,
+                                   float *__restrict__ d_w, float *__restrict__ d_b,
+                                   float *__restrict__ d_ms) {
+    const int c = threadIdx.x;
+    if (c >= 64) return;
+    if (c >= k) { coef[c] = coef[64 + c] = coef[128 + c] = 0.0f; return; }
+    const float N = (float)(n > 0 ? n : 1);
+    const float w = gn_w[c], s = gn_ms[c], mu = mean[c], inv = invstd[c];
+    const float A1 = w * R1[c] / N, A2 = w * R2[c] / N;
+    const float mhat = mu * (1.0f - s) * inv;        // mean of c_hat
+    const float mdc = inv * (A1 - mhat * A2);        // mean of dL/dc
+    coef[c] = w * inv;
+    coef[64 + c] = -A2 * inv;
+    coef[128 + c] = -s * mdc;
+    if (d_b) d_b[c] += R1[c];
+    if (d_w) d_w[c] += R2[c];
+    if (d_ms) d_ms[c] += -mu * N * mdc;
+}
+
 struct BwdWorkspace {
-    float *P, *Q, *M, *dM, *dP, *dQ, *DO, *U, *DV, *O, *dzn, *gdot, *DT1, *DD;
+    float *dM, *dP, *dQ, *DO, *U, *DV, *O, *dzn, *gdot, *DT1, *DD;
+    float *DY, *DYC, *gn_r, *gn_coef, *seg_s;
     float *edge_partial, *wg_partial;
+    void *fwd;
     int edge_grid;
     int64_t bytes;
 };
 
-static BwdWorkspace carve_bwd(void *base, int n, int e) {
+static BwdWorkspace carve_bwd(void *base, int n, int e, uint32_t flags) {
     BwdWorkspace w{};
     char *p = (char *)base;
     auto take = [&](int64_t count) {
@@ -976,15 +1106,22 @@ static BwdWorkspace carve_bwd(void *base, int n, int e) {
         return r;
     };
     const int64_t nk = (int64_t)n * KB;
-    w.P = take(nk); w.Q = take(nk); w.M = take(nk); w.dM = take(nk);
+    w.dM = take(nk);
     w.dP = take(nk); w.dQ = take(nk); w.DO = take(nk); w.U = take(nk);
     w.DV = take(nk); w.O = take(nk);
     w.dzn = take(n); w.gdot = take(n);
+    if (flags & PVS_F_GRAPHNORM) {
+        w.DY = take(nk); w.DYC = take(nk);
+        w.gn_r = take(128); w.gn_coef = take(192);
+    }
+    if ((flags & PVS_F_EDGE_ATTENTION) && (flags & PVS_F_SOFTMAX_ATTENTION)) w.seg_s = take(n);
     w.DT1 = take((int64_t)e * KB);
     w.DD = take((int64_t)e * 3);
     w.edge_grid = num_sms();
     w.edge_partial = take((int64_t)w.edge_grid * EP_STRIDE);
     w.wg_partial = take((int64_t)num_sms() * 2 * WG_PART);
+    w.fwd = (void *)p;
+    p += align_up(fwd_recompute_bytes(n, e, flags), 256);
     w.bytes = p - (char *)base;
     return w;
 }
@@ -1039,7 +1176,7 @@ int pvs_mean_pool_bwd(const float *d_pooled, const int32_t *graph_ptr, int32_t n
 int64_t pvs_egnn_layer_bwd_workspace_bytes(int32_t n_nodes, int32_t n_edges,
                                            const pvs_layer_config *cfg) {
     if (!cfg || cfg->k < 1 || cfg->k > PVS_MAX_K) return -1;
-    return carve_bwd(nullptr, n_nodes, n_edges).bytes + 256;
+    return carve_bwd(nullptr, n_nodes, n_edges, cfg->flags).bytes + 256;
 }
 
 int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t *csc_eid,
@@ -1053,8 +1190,9 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
     if (cfg->k < 1 || cfg->k > PVS_MAX_K) return PVS_ERR_UNSUPPORTED_K;
     if (cfg->math < PVS_MATH_FP32 || cfg->math > PVS_MATH_BF16) return PVS_ERR_INVALID_ARG;
     const uint32_t f = cfg->flags;
-    if (f & PVS_F_GRAPHNORM) return PVS_ERR_UNSUPPORTED;
-    if ((f & PVS_F_EDGE_ATTENTION) && (f & PVS_F_SOFTMAX_ATTENTION)) return PVS_ERR_UNSUPPORTED;
+    const bool graphnorm = f & PVS_F_GRAPHNORM;
+    const bool softmax = (f & PVS_F_EDGE_ATTENTION) && (f & PVS_F_SOFTMAX_ATTENTION);
+    if (graphnorm && (!p->gn_weight || !p->gn_bias || !p->gn_mean_scale)) return PVS_ERR_INVALID_ARG;
     if (g->n_nodes < 0 || g->n_edges < 0) return PVS_ERR_INVALID_ARG;
     if (g->n_nodes == 0) return PVS_OK;
     if (!g->row_ptr || !g->tile_ptr || !g->n_tiles || (g->n_edges > 0 && (!g->col || !csc_eid)) ||
@@ -1074,58 +1212,64 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
     const bool perm = f & PVS_F_PERM_INVARIANT;
     const int in_e = (perm ? k : 2 * k) + 1 + cfg->n_edge_classes;
     const int col_r = perm ? k : 2 * k;
-    BwdWorkspace w = carve_bwd((void *)align_up((int64_t)(uintptr_t)workspace, 256), n, E);
+    BwdWorkspace w = carve_bwd((void *)align_up((int64_t)(uintptr_t)workspace, 256), n, E, f);
     int rc;
 
-    // ---- recompute P, Q, M ----
-    if (k < KB) {
-        rc = cuda_call(cudaMemsetAsync(w.P, 0, (size_t)((char *)w.M - (char *)w.P), st));
-        if (rc) return rc;
-    }
-    rc = launch_linear(h_in, k, n, k, p->edge_w1, in_e, p->edge_b1, k, PVS_ACT_NONE, w.P, KB, st);
-    if (rc) return rc;
-    rc = launch_linear(h_in, k, n, k, p->edge_w1 + (perm ? 0 : k), in_e, nullptr, k,
-                       PVS_ACT_NONE, w.Q, KB, st);
-    if (rc) return rc;
-    EdgeArgs ea{};
-    ea.row_ptr = g->row_ptr; ea.col = g->col; ea.tile_ptr = g->tile_ptr;
-    ea.n_tiles = g->n_tiles; ea.attr = cfg->n_edge_classes > 0 ? g->attr : nullptr;
-    ea.P = w.P; ea.Q = w.Q; ea.x_in = x_in; ea.m_prev = m_prev; ea.M = w.M;
-    ea.x_out = nullptr; ea.m_out = nullptr; ea.ld_m = k; ea.att_out = nullptr;
-    ea.edge_w1 = p->edge_w1; ea.edge_w2 = p->edge_w2; ea.edge_b2 = p->edge_b2;
-    ea.coord_w1 = p->coord_w1 ? p->coord_w1 : p->edge_w2;
-    ea.coord_b1 = p->coord_b1 ? p->coord_b1 : p->edge_b2;
-    ea.coord_w2 = p->coord_w2 ? p->coord_w2 : p->edge_b2;
-    ea.att_w = p->att_w; ea.att_b = p->att_b; ea.edge_gate = p->edge_gate;
-    ea.k = k; ea.in_e = in_e; ea.n_classes = cfg->n_edge_classes;
-    ea.flags = f; ea.att_act = cfg->att_act;
-    rc = cfg->math == PVS_MATH_FP32 ? launch_edge_fp32_k64(ea, g->n_tiles_cap, st)
-                                    : launch_edge_tc(ea, g->n_tiles_cap, cfg->math, st);
+    // ---- recompute P, Q, M (+ softmax alpha / messages, GraphNorm V + statistics) ----
+    FwdWorkspace fw{};
+    rc = fwd_recompute(g, cfg, p, h_in, x_in, m_prev, w.fwd, &fw, st);
     if (rc) return rc;
 
     // ---- node backward ----
     NodeBwdArgs na{};
-    na.h_in = h_in; na.M = w.M; na.d_h_out = d_h_out; na.d_h_in = d_h_in; na.dM = w.dM;
+    na.h_in = h_in; na.M = fw.M; na.d_h_out = d_h_out; na.d_h_in = d_h_in; na.dM = w.dM;
     na.DO = w.DO; na.U = w.U; na.DV = w.DV; na.O = w.O; na.dzn = w.dzn; na.gdot = w.gdot;
     na.node_w1 = p->node_w1; na.node_b1 = p->node_b1; na.node_w2 = p->node_w2;
     na.node_b2 = p->node_b2; na.natt_w = p->natt_w; na.natt_b = p->natt_b;
     na.node_gate = p->node_gate;
     na.n_nodes = n; na.k = k; na.flags = f; na.att_act = cfg->att_act;
+    na.V = fw.V; na.gn_a = fw.gn_a; na.gn_b = fw.gn_b; na.gn_shift = fw.gn_shift;
+    na.gn_invstd = fw.gn_invstd; na.DY = w.DY; na.DYC = w.DYC; na.coef = w.gn_coef;
     {
         size_t smem = ((size_t)128 * 64 + 64 * 64 * 2 + 64 * 128 + 64 * (2 * KB + 4) +
-                       2 * 64 * LDT + 3 * 64) * sizeof(float);
+                       2 * 64 * LDT + 10 * 64) * sizeof(float);
         rc = ensure_smem(egnn_node_bwd_kernel, smem);
         if (rc) return rc;
-        egnn_node_bwd_kernel<<<persistent_grid((n + 63) / 64, 1), BT, smem, st>>>(na);
-        rc = check_launch();
-        if (rc) return rc;
+        const int grid = persistent_grid((n + 63) / 64, 1);
+        if (!graphnorm) {
+            na.phase = 0;
+            egnn_node_bwd_kernel<<<grid, BT, smem, st>>>(na);
+            rc = check_launch();
+            if (rc) return rc;
+        } else {
+            na.phase = 1;
+            egnn_node_bwd_kernel<<<grid, BT, smem, st>>>(na);
+            rc = check_launch();
+            if (rc) return rc;
+            // batch reductions R1 = sum dy, R2 = sum dy c_hat, then the coefficients
+            rc = cuda_call(cudaMemsetAsync(w.gn_r, 0, 128 * sizeof(float), st));
+            if (rc) return rc;
+            rc = launch_wgrad(w.DY, KB, 64, nullptr, 0, 0, n, nullptr, 0, w.gn_r, w.wg_partial, st);
+            if (rc) return rc;
+            rc = launch_wgrad(w.DYC, KB, 64, nullptr, 0, 0, n, nullptr, 0, w.gn_r + 64,
+                              w.wg_partial, st);
+            if (rc) return rc;
+            gn_bwd_coef_kernel<<<1, 64, 0, st>>>(w.gn_r, w.gn_r + 64, n, k, p->gn_weight,
+                                                 p->gn_mean_scale, fw.gn_mean, fw.gn_invstd,
+                                                 w.gn_coef, grads->gn_weight, grads->gn_bias,
+                                                 grads->gn_mean_scale);
+            na.phase = 2;
+            egnn_node_bwd_kernel<<<grid, BT, smem, st>>>(na);
+            rc = check_launch(2);
+            if (rc) return rc;
+        }
     }
     // node weight gradients
     rc = launch_wgrad(w.DO, KB, k, w.U, KB, k, n, grads->node_w2, k, grads->node_b2, w.wg_partial, st);
     if (rc) return rc;
     rc = launch_wgrad(w.DV, KB, k, h_in, k, k, n, grads->node_w1, 2 * k, grads->node_b1, w.wg_partial, st);
     if (rc) return rc;
-    rc = launch_wgrad(w.DV, KB, k, w.M, KB, k, n, grads->node_w1 ? grads->node_w1 + k : nullptr,
+    rc = launch_wgrad(w.DV, KB, k, fw.M, KB, k, n, grads->node_w1 ? grads->node_w1 + k : nullptr,
                       2 * k, nullptr, w.wg_partial, st);
     if (rc) return rc;
     if ((f & PVS_F_NODE_ATTENTION) && p->natt_w) {
@@ -1142,13 +1286,22 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
     // ---- edge backward ----
     EdgeBwdArgs eb{};
     eb.row_ptr = g->row_ptr; eb.col = g->col; eb.tile_ptr = g->tile_ptr; eb.n_tiles = g->n_tiles;
-    eb.attr = ea.attr;
-    eb.P = w.P; eb.Q = w.Q; eb.x_in = x_in; eb.m_prev = m_prev; eb.dM = w.dM;
+    eb.attr = cfg->n_edge_classes > 0 ? g->attr : nullptr;
+    eb.P = fw.P; eb.Q = fw.Q; eb.x_in = x_in; eb.m_prev = m_prev; eb.dM = w.dM;
+    if (softmax) {
+        softmax_bwd_prep_kernel<<<(n + 7) / 8, 256, 0, st>>>(g->row_ptr, n, fw.z_ws, fw.m_ws,
+                                                            w.dM, w.seg_s);
+        rc = check_launch();
+        if (rc) return rc;
+        eb.alpha_in = fw.z_ws; eb.seg_s = w.seg_s;
+    }
     eb.d_x_out = d_x_out; eb.d_m_out = d_m_out;
     eb.dP = w.dP; eb.DT1 = w.DT1; eb.DD = w.DD; eb.d_x_in = d_x_in; eb.d_m_prev = d_m_prev;
     eb.partial = w.edge_partial;
     eb.edge_w1 = p->edge_w1; eb.edge_w2 = p->edge_w2; eb.edge_b2 = p->edge_b2;
-    eb.coord_w1 = ea.coord_w1; eb.coord_b1 = ea.coord_b1; eb.coord_w2 = ea.coord_w2;
+    eb.coord_w1 = p->coord_w1 ? p->coord_w1 : p->edge_w2;
+    eb.coord_b1 = p->coord_b1 ? p->coord_b1 : p->edge_b2;
+    eb.coord_w2 = p->coord_w2 ? p->coord_w2 : p->edge_b2;
     eb.att_w = p->att_w; eb.att_b = p->att_b; eb.edge_gate = p->edge_gate;
     eb.k = k; eb.in_e = in_e; eb.n_classes = cfg->n_edge_classes; eb.flags = f;
     eb.att_act = cfg->att_act;

@@ -39,6 +39,17 @@ int launch_linear(const float *in, int ld_in, int rows, int ki, const float *w,
                   int ld_out, cudaStream_t st, int w_in_major = 0,
                   int accumulate = 0);
 int persistent_grid(int work_items, int blocks_per_sm);
+
+// per-layer forward workspace (egnn_fwd.cu)
+struct FwdWorkspace {
+    float *P, *Q, *M, *V, *m_ws, *z_ws, *gn_partial, *gn_shift, *gn_a, *gn_b;
+    float *gn_mean, *gn_invstd;
+    int64_t bytes;
+};
+int64_t fwd_recompute_bytes(int n, int e, uint32_t flags);
+int fwd_recompute(const pvs_graph *g, const pvs_layer_config *cfg, const pvs_layer_params *p,
+                  const float *h_in, const float *x_in, const float *m_prev, void *ws_base,
+                  FwdWorkspace *out, cudaStream_t st);
 // tensor-core node stages (egnn_node_tc.cu); mode = PVS_MATH_BF16X3 / BF16
 int launch_node_pre_tc(const float *h, const float *edge_w1, const float *edge_b1, float *P,
                        float *Q, int n_nodes, int k, int in_e, int perm, int mode,

@@ -580,7 +580,9 @@ __global__ void gn_finalize_kernel(const float *__restrict__ partial, int nblock
                                    const float *__restrict__ gn_b,
                                    const float *__restrict__ gn_ms,
                                    float *__restrict__ shift,
-                                   float *__restrict__ ga, float *__restrict__ gb) {
+                                   float *__restrict__ ga, float *__restrict__ gb,
+                                   float *__restrict__ mean_out,
+                                   float *__restrict__ invstd_out) {
     const int c = threadIdx.x;
     if (c >= 64) return;
     float s = 0.0f;
@@ -588,10 +590,13 @@ __global__ void gn_finalize_kernel(const float *__restrict__ partial, int nblock
     const float mean = s / (float)(n > 0 ? n : 1);
     if (stage == 0) {
         shift[c] = c < k ? mean * gn_ms[c] : 0.0f;
+        mean_out[c] = c < k ? mean : 0.0f;
     } else {
-        const float av = c < k ? gn_w[c] / sqrtf(mean + 1e-5f) : 0.0f;
+        const float inv = 1.0f / sqrtf(mean + 1e-5f);
+        const float av = c < k ? gn_w[c] * inv : 0.0f;
         ga[c] = av;
         gb[c] = c < k ? gn_b[c] - av * shift[c] : 0.0f;
+        invstd_out[c] = c < k ? inv : 0.0f;
     }
 }
 
@@ -655,11 +660,6 @@ static int launch_node(const NodeArgs &a, cudaStream_t st) {
     return check_launch();
 }
 
-struct FwdWorkspace {
-    float *P, *Q, *M, *V, *m_ws, *z_ws, *gn_partial, *gn_shift, *gn_a, *gn_b;
-    int64_t bytes;
-};
-
 constexpr int GN_BLOCKS = 128;
 
 static FwdWorkspace carve_workspace(void *base, int n, int e, int kp, uint32_t flags) {
@@ -679,6 +679,8 @@ static FwdWorkspace carve_workspace(void *base, int n, int e, int kp, uint32_t f
         w.gn_shift = take(64);
         w.gn_a = take(64);
         w.gn_b = take(64);
+        w.gn_mean = take(64);
+        w.gn_invstd = take(64);
     }
     if ((flags & PVS_F_EDGE_ATTENTION) && (flags & PVS_F_SOFTMAX_ATTENTION)) {
         w.m_ws = take((int64_t)e * kp);
@@ -686,6 +688,87 @@ static FwdWorkspace carve_workspace(void *base, int n, int e, int kp, uint32_t f
     }
     w.bytes = p - (char *)base;
     return w;
+}
+
+int64_t fwd_recompute_bytes(int n, int e, uint32_t flags) {
+    return carve_workspace(nullptr, n, e, 64, flags).bytes + 256;
+}
+
+// Forward recompute for the backward pass (64-wide pitch): P, Q, M (and the
+// softmax attention values + messages, and the GraphNorm pre-activation V with
+// its batch statistics).  No h_out / x_out is produced.
+int fwd_recompute(const pvs_graph *g, const pvs_layer_config *cfg, const pvs_layer_params *p,
+                  const float *h_in, const float *x_in, const float *m_prev, void *ws_base,
+                  FwdWorkspace *out, cudaStream_t st) {
+    const uint32_t f = cfg->flags;
+    const int k = cfg->k, n = g->n_nodes, E = g->n_edges;
+    const bool tc = cfg->math != PVS_MATH_FP32;
+    const bool perm = f & PVS_F_PERM_INVARIANT;
+    const int in_e = (perm ? k : 2 * k) + 1 + cfg->n_edge_classes;
+    const bool softmax = (f & PVS_F_EDGE_ATTENTION) && (f & PVS_F_SOFTMAX_ATTENTION);
+    FwdWorkspace w = carve_workspace((void *)align_up((int64_t)(uintptr_t)ws_base, 256), n, E, 64, f);
+    int rc;
+    if (tc) {
+        rc = launch_node_pre_tc(h_in, p->edge_w1, p->edge_b1, w.P, w.Q, n, k, in_e, perm ? 1 : 0,
+                                cfg->math, st);
+        if (rc) return rc;
+    } else {
+        if (k < 64) {
+            rc = cuda_call(cudaMemsetAsync(w.P, 0, (size_t)((char *)w.M - (char *)w.P), st));
+            if (rc) return rc;
+        }
+        rc = launch_linear(h_in, k, n, k, p->edge_w1, in_e, p->edge_b1, k, PVS_ACT_NONE, w.P, 64, st);
+        if (rc) return rc;
+        rc = launch_linear(h_in, k, n, k, p->edge_w1 + (perm ? 0 : k), in_e, nullptr, k,
+                           PVS_ACT_NONE, w.Q, 64, st);
+        if (rc) return rc;
+    }
+    EdgeArgs ea{};
+    ea.row_ptr = g->row_ptr; ea.col = g->col; ea.tile_ptr = g->tile_ptr;
+    ea.n_tiles = g->n_tiles; ea.attr = cfg->n_edge_classes > 0 ? g->attr : nullptr;
+    ea.P = w.P; ea.Q = w.Q; ea.x_in = x_in; ea.m_prev = m_prev; ea.M = w.M;
+    ea.x_out = nullptr;
+    ea.m_out = softmax ? w.m_ws : nullptr; ea.ld_m = 64;
+    ea.att_out = softmax ? w.z_ws : nullptr;
+    ea.edge_w1 = p->edge_w1; ea.edge_w2 = p->edge_w2; ea.edge_b2 = p->edge_b2;
+    ea.coord_w1 = p->coord_w1 ? p->coord_w1 : p->edge_w2;
+    ea.coord_b1 = p->coord_b1 ? p->coord_b1 : p->edge_b2;
+    ea.coord_w2 = p->coord_w2 ? p->coord_w2 : p->edge_b2;
+    ea.att_w = p->att_w; ea.att_b = p->att_b; ea.edge_gate = p->edge_gate;
+    ea.k = k; ea.in_e = in_e; ea.n_classes = cfg->n_edge_classes;
+    ea.flags = f; ea.att_act = cfg->att_act;
+    rc = tc ? launch_edge_tc(ea, g->n_tiles_cap, cfg->math, st)
+            : launch_edge<64>(ea, g->n_tiles_cap, st);
+    if (rc) return rc;
+    if (softmax) {
+        segment_softmax_agg_kernel<<<(n + 7) / 8, 256, 0, st>>>(g->row_ptr, n, w.m_ws, 64, 64,
+                                                               w.z_ws, w.M);
+        rc = check_launch();
+        if (rc) return rc;
+    }
+    if (f & PVS_F_GRAPHNORM) {
+        NodeArgs na{};
+        na.h_in = h_in; na.M = w.M; na.h_out = nullptr; na.V = w.V;
+        na.node_w1 = p->node_w1; na.node_b1 = p->node_b1; na.node_w2 = p->node_w2;
+        na.node_b2 = p->node_b2; na.natt_w = p->natt_w; na.natt_b = p->natt_b;
+        na.node_gate = p->node_gate;
+        na.n_nodes = n; na.k = k; na.flags = f; na.att_act = cfg->att_act;
+        na.phase = 1;
+        rc = launch_node<64>(na, st);
+        if (rc) return rc;
+        gn_colsum_kernel<<<GN_BLOCKS, 256, 0, st>>>(w.V, n, 64, nullptr, 0, w.gn_partial);
+        gn_finalize_kernel<<<1, 64, 0, st>>>(w.gn_partial, GN_BLOCKS, n, k, 0, p->gn_weight,
+                                             p->gn_bias, p->gn_mean_scale, w.gn_shift, w.gn_a,
+                                             w.gn_b, w.gn_mean, w.gn_invstd);
+        gn_colsum_kernel<<<GN_BLOCKS, 256, 0, st>>>(w.V, n, 64, w.gn_shift, 1, w.gn_partial);
+        gn_finalize_kernel<<<1, 64, 0, st>>>(w.gn_partial, GN_BLOCKS, n, k, 1, p->gn_weight,
+                                             p->gn_bias, p->gn_mean_scale, w.gn_shift, w.gn_a,
+                                             w.gn_b, w.gn_mean, w.gn_invstd);
+        rc = check_launch(4);
+        if (rc) return rc;
+    }
+    *out = w;
+    return PVS_OK;
 }
 
 }  // namespace pvs
@@ -840,11 +923,13 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
         gn_colsum_kernel<<<GN_BLOCKS, 256, 0, st>>>(w.V, n, kp, nullptr, 0, w.gn_partial);
         gn_finalize_kernel<<<1, 64, 0, st>>>(w.gn_partial, GN_BLOCKS, n, k, 0,
                                              p->gn_weight, p->gn_bias,
-                                             p->gn_mean_scale, w.gn_shift, w.gn_a, w.gn_b);
+                                             p->gn_mean_scale, w.gn_shift, w.gn_a, w.gn_b,
+                                             w.gn_mean, w.gn_invstd);
         gn_colsum_kernel<<<GN_BLOCKS, 256, 0, st>>>(w.V, n, kp, w.gn_shift, 1, w.gn_partial);
         gn_finalize_kernel<<<1, 64, 0, st>>>(w.gn_partial, GN_BLOCKS, n, k, 1,
                                              p->gn_weight, p->gn_bias,
-                                             p->gn_mean_scale, w.gn_shift, w.gn_a, w.gn_b);
+                                             p->gn_mean_scale, w.gn_shift, w.gn_a, w.gn_b,
+                                             w.gn_mean, w.gn_invstd);
         rc = check_launch(4);
         if (rc) return rc;
         na.phase = 2;

@@ -490,7 +490,7 @@ class PNNGeometricBase(PointNeuralNetworkBase):
             raise _cabi.PvsError(
                 f'unsupported model for the fused scoring pass (k={desc.k}; '
                 f'hidden width must be 1..{_cabi.MAX_K})')
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = _cabi.scratch('model_fwd', nbytes, dev)
         scores = torch.empty((n_graphs, dim_out), dtype=torch.float32,
                              device=dev)
         g = csr.c_struct()
@@ -498,7 +498,7 @@ class PNNGeometricBase(PointNeuralNetworkBase):
             check(h.pvs_egnn_model_fwd(
                 C.byref(g), C.byref(desc), ptr(feats), feats.shape[1],
                 ptr(pos), ptr(graph_ptr), n_graphs, ptr(scores), ptr(pos),
-                None, ptr(ws), C.c_int64(nbytes), stream()),
+                None, ptr(ws), C.c_int64(ws.numel()), stream()),
                 'pvs_egnn_model_fwd')
         if pos.data_ptr() != graph.pos.data_ptr() and \
                 graph.pos.dtype == torch.float32 and graph.pos.is_cuda:

@@ -74,9 +74,8 @@ class CSRGraph:
         self.n_tiles_cap = int(cap)
         self.tile_ptr = torch.empty(cap + 1, dtype=torch.int32, device=dev)
         self.n_tiles = torch.zeros(1, dtype=torch.int32, device=dev)
-        scratch = torch.empty(
-            max(1, int(h.pvs_tiles_scratch_bytes(self.n_nodes))),
-            dtype=torch.uint8, device=dev)
+        scratch = _cabi.scratch(
+            'tiles', max(1, int(h.pvs_tiles_scratch_bytes(self.n_nodes))), dev)
         check(h.pvs_build_tiles(ptr(self.row_ptr), self.n_nodes,
                                 ptr(self.tile_ptr), ptr(self.n_tiles),
                                 ptr(scratch), stream()), 'pvs_build_tiles')
@@ -205,14 +204,14 @@ def radius_graph_batch(coords, bp, complex_ptr, inter_radius=4.0,
     deg = torch.empty(max(1, n), dtype=torch.int32, device=device)
     n_inter = torch.empty(max(1, n), dtype=torch.int32, device=device)
     row_ptr = torch.empty(n + 1, dtype=torch.int32, device=device)
-    scratch = torch.empty(int(h.pvs_scan_scratch_bytes(n)) + 256,
-                          dtype=torch.uint8, device=device)
+    scratch = _cabi.scratch('k1_scan', int(h.pvs_scan_scratch_bytes(n)) + 256,
+                            device)
     # neighbour masks kept between the passes (skipped when they would be huge
     # or when the reference-order positions need the per-complex pass anyway)
     mask_bytes = int(h.pvs_radius_graph_mask_bytes(n, max_n))
     masks = None
     if not with_ref_pos and 0 < mask_bytes <= (1 << 30):
-        masks = torch.empty(mask_bytes, dtype=torch.uint8, device=device)
+        masks = _cabi.scratch('k1_masks', mask_bytes, device)
     with torch.cuda.device(device):
         check(h.pvs_radius_graph_count(
             ptr(coords), ptr(bp), ptr(cptr), n_complexes, n, max_n,

@@ -25,7 +25,8 @@ def _close(got, want, name, rtol=2e-4, atol=2e-6):
     assert err <= bound, f'{name}: err {err:.3e} > {bound:.3e}'
 
 
-@pytest.mark.parametrize('name', ['cfg3_k32', 'alloff_multitask'])
+@pytest.mark.parametrize('name', ['cfg3_k32', 'alloff_multitask',
+                                  'testkwargs_fixture82'])
 def test_param_grads_vs_reference_golden(name):
     model, g = gh.cuda_model(name, 'classification')
     model.train()
@@ -65,6 +66,17 @@ VARIANTS = {
                   residual=True, edge_residual=True, gated_residual=True,
                   normalize=True, tanh=False,
                   attention_activation_fn='silu'),
+    'graphnorm_softmax': dict(k=32, num_layers=3, edge_attention=True,
+                              node_attention=True, residual=True,
+                              normalize=True, tanh=True, graphnorm=True,
+                              softmax_attention=True),
+    'graphnorm_only': dict(k=64, num_layers=2, edge_attention=True,
+                           node_attention=False, residual=True,
+                           normalize=True, tanh=True, graphnorm=True),
+    'softmax_only_eres': dict(k=32, num_layers=3, edge_attention=True,
+                              node_attention=True, residual=True,
+                              edge_residual=True, normalize=False, tanh=True,
+                              softmax_attention=True),
     'perminv_static': dict(k=32, num_layers=2, edge_attention=True,
                            node_attention=False, residual=True,
                            normalize=True, tanh=True,
@@ -74,13 +86,15 @@ VARIANTS = {
 
 @pytest.mark.parametrize('vname', sorted(VARIANTS))
 def test_grads_vs_oracle_autograd(vname):
-    kw = dict(dim_input=13, dim_output=1, graphnorm=False, **VARIANTS[vname])
+    kw = dict(dim_input=13, dim_output=1, **{'graphnorm': False, **VARIANTS[vname]})
     model = gh.build_model(kw, seed=7, coord_gain=1.0)
     gen = torch.Generator().manual_seed(3)
     with torch.no_grad():
         for pname, p in model.named_parameters():
             if 'gate_parameter' in pname:
                 p.copy_(torch.rand(1, generator=gen).cuda() * 0.8 + 0.1)
+            if '.node_mlp.1.' in pname:     # GraphNorm weight / bias / mean_scale
+                p.copy_((torch.rand(p.shape, generator=gen) + 0.5).cuda())
     model.train()
     radii = (4.0, 2.0) if vname == 'k48_relu_att_noresid' else (4.0, 4.0)
     graph = gh.synthetic_graph(900, 3, 250, 15, radii=radii, ragged=True)
@@ -149,9 +163,37 @@ def test_training_step_reduces_loss():
     assert losses[-1] < losses[0]
 
 
-def test_graphnorm_training_fails_loudly():
-    kw = dict(dim_input=13, dim_output=1, k=32, num_layers=1, graphnorm=True)
-    model = gh.build_model(kw).train()
-    out = model(gh.synthetic_graph(1, 2, 100, 10))
-    with pytest.raises(NotImplementedError):
-        out.sum().backward()
+def test_hub_node_softmax_backward():
+    """Softmax attention over a destination with > 128 incoming edges (several
+    chunks) differentiates correctly."""
+    from oracle import egnn_oracle
+    from pointvs_b200 import EGNNLayer
+    torch.manual_seed(5)
+    n = 300
+    layer = EGNNLayer(32, 32, 32, edges_in_d=3, edge_attention=True,
+                      normalize=True, tanh=True, softmax_attention=True).cuda()
+    with torch.no_grad():
+        layer.coord_mlp[2].weight.mul_(1000.0)
+    hub = torch.zeros(n - 1, dtype=torch.long)
+    others = torch.arange(1, n)
+    ei = torch.cat([torch.stack([hub, others]), torch.stack([others, hub])], 1)
+    gen = torch.Generator().manual_seed(2)
+    ea = torch.nn.functional.one_hot(
+        torch.randint(0, 3, (ei.shape[1],), generator=gen), 3)
+    h = torch.randn(n, 32, generator=gen)
+    x = torch.randn(n, 3, generator=gen) * 3
+    hc = h.cuda().requires_grad_(True)
+    h2, x2, _, m2 = layer(hc, ei.cuda(), x.clone().cuda(), ea.cuda())
+    (h2.sum() + x2.sum()).backward()
+    sd = {'l.' + k: v.detach().cpu().clone().requires_grad_(True)
+          for k, v in layer.state_dict().items()}
+    cfg = egnn_oracle.LayerConfig(residual=True, edge_attention=True,
+                                  normalize=True, tanh=True,
+                                  softmax_attention=True)
+    hr = h.clone().requires_grad_(True)
+    ho, xo, mo, _ = egnn_oracle.layer_forward(sd, 'l.', cfg, hr, ei[0], ei[1],
+                                              x, ea)
+    (ho.sum() + xo.sum()).backward()
+    _close(hc.grad.cpu().numpy(), hr.grad.numpy(), 'h')
+    for pname, p in layer.named_parameters():
+        _close(p.grad.cpu().numpy(), sd['l.' + pname].grad.numpy(), pname)
