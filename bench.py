@@ -380,12 +380,21 @@ def run_ours(args):
     # 1-element adds per step) and read once after the timed region
     edges_dev = torch.zeros(1, dtype=torch.int64, device=dev)
     overflow_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    # at most 3 steps in flight: the host otherwise runs ~6 steps ahead and the
+    # caching allocator has to cudaMalloc (a device-wide sync) inside the timed
+    # region; the GPU always has >= 2 queued steps, so it never waits for the host
+    in_flight = []
     t_host0 = time.perf_counter()
     for i in range(args.steps):
+        if len(in_flight) >= 3:
+            in_flight.pop(0).synchronize()
         _, csr = step_device(args.warmup + i)
         edges_dev += csr.n_edges_dev
         overflow_dev += csr._overflow
         del csr
+        done = torch.cuda.Event()
+        done.record()
+        in_flight.append(done)
     ev1.record()
     host_submit_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
     barrier()
