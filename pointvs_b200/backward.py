@@ -31,9 +31,18 @@ def egnn_layer_backward(ctx, d_h, d_x, d_m):
 
     pstruct = _cabi.LayerParams(*[
         ptr(None if p is None else p.detach().contiguous()) for p in params])
+    # one zero-filled flat buffer for every parameter gradient of the layer
     by_name = dict(zip(_cabi.PARAM_FIELDS, params))
-    grads = {name: _zeros_like_or_none(by_name[name])
+    sizes = {name: (0 if by_name[name] is None else by_name[name].numel())
              for name in _cabi.GRAD_FIELDS}
+    flat = torch.zeros(sum(sizes.values()), dtype=torch.float32, device=dev)
+    grads, off = {}, 0
+    for name in _cabi.GRAD_FIELDS:
+        if sizes[name]:
+            grads[name] = flat[off:off + sizes[name]]
+            off += sizes[name]
+        else:
+            grads[name] = None
     gstruct = _cabi.LayerGrads(*[ptr(grads[name]) for name in _cabi.GRAD_FIELDS])
 
     d_h_in = torch.empty_like(h)

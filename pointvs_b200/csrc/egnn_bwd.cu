@@ -111,7 +111,9 @@ __global__ void wgrad_reduce_kernel(const float *__restrict__ partial, int n_cta
 }
 
 static int wgrad_ctas(int rows) {
-    int g = (rows + 63) / 64;
+    // >= 256 rows per CTA: the partials (one [64 x 128] block per CTA) are what
+    // the reduce kernel has to read back
+    int g = (rows + 255) / 256;
     int cap = num_sms() * 2;
     if (g > cap) g = cap;
     return g < 1 ? 1 : g;
