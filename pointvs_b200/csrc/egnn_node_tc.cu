@@ -65,29 +65,6 @@ __device__ __forceinline__ float4 *stage_ptr(float *stage, int r, int c4) {
     return reinterpret_cast<float4 *>(stage + r * 64 + ((c4 ^ (r & 15)) << 2));
 }
 
-// cooperative copy of the staging tile to dst rows [row0, ...) (pitch ld, `cols`
-// valid columns): each half warp writes one full row.
-__device__ __forceinline__ void store_stage(const float *stage, float *__restrict__ dst,
-                                            int ld, int cols, int row0, int n_rows, int tid) {
-    const int c4 = tid & 15, slot = tid >> 4;
-    const bool vec = (ld & 3) == 0;
-#pragma unroll 4
-    for (int p = 0; p < NT_ROWS / 8; ++p) {
-        const int r = p * 8 + slot;
-        if (row0 + r >= n_rows) continue;
-        const float4 v = *stage_ptr(const_cast<float *>(stage), r, c4);
-        float *d = dst + (size_t)(row0 + r) * ld + 4 * c4;
-        if (vec && 4 * c4 + 3 < cols) {
-            *reinterpret_cast<float4 *>(d) = v;
-        } else {
-            if (4 * c4 < cols) d[0] = v.x;
-            if (4 * c4 + 1 < cols) d[1] = v.y;
-            if (4 * c4 + 2 < cols) d[2] = v.z;
-            if (4 * c4 + 3 < cols) d[3] = v.w;
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------
 // node_pre: P, Q
 // ---------------------------------------------------------------------------

@@ -385,3 +385,64 @@ def test_one_call_path_sees_in_place_parameter_updates():
         c = model(gh.synthetic_graph(3, 2, 150, 10))
     assert not torch.equal(a, b)
     assert torch.equal(b, c)
+
+
+@pytest.mark.parametrize('math', ['fp32', 'bf16x3'])
+def test_edgeless_and_tiny_graphs(math):
+    """Graphs with no edges at all, single atoms, and fewer nodes than a tile."""
+    from pointvs_b200.graph import PackedBatch
+    kw = dict(dim_input=13, dim_output=1, k=64, num_layers=2,
+              edge_attention=True, node_attention=True, residual=True,
+              normalize=True, tanh=True, graphnorm=False)
+    model = gh.build_model(kw, seed=2, coord_gain=1.0)
+    model.set_math(math)
+    rng = np.random.default_rng(0)
+    # complex 0: three atoms 50 A apart (no edges); complex 1: one atom;
+    # complex 2: a 5-atom cluster
+    coords = np.concatenate([np.eye(3) * 50.0, np.zeros((1, 3)) + 200.0,
+                             rng.normal(size=(5, 3)) + 400.0])
+    coords = coords.astype(np.float32).astype(np.float64)
+    bp = np.array([0, 1, 1, 1, 0, 0, 1, 1, 1])
+    feats = np.zeros((9, 13), dtype=np.float32)
+    feats[np.arange(9), rng.integers(0, 12, 9)] = 1.0
+    batch = PackedBatch.from_arrays(coords, bp, feats, [0, 3, 4, 9], 4.0, 4.0)
+    pos0 = batch.pos.clone()
+    with torch.no_grad():
+        out = model(batch)
+    assert out.shape == (3, 1) and bool(torch.isfinite(out).all())
+    graph_cpu = SimpleNamespace(x=batch.x, pos=pos0, edge_index=batch.edge_index,
+                                edge_attr=batch.edge_attr, batch=batch.batch)
+    want, x_want = gh.oracle_forward(model, kw, graph_cpu)
+    assert helpers.rel_err(out.cpu().numpy().reshape(-1),
+                           want.numpy().reshape(-1)) < SCORE_RTOL
+    # atoms without neighbours do not move
+    assert torch.equal(batch.pos[:4], pos0[:4])
+    assert helpers.scaled_err(batch.pos.cpu().numpy(), x_want.numpy()) < 1e-5
+
+
+def test_val_writes_reference_prediction_file(tmp_path):
+    """PointNeuralNetworkBase.val on a list of packed batches: file name and
+    line format of the reference (point_neural_network_base.py:208-325)."""
+    import pointvs_b200 as pv
+    from pointvs_b200.synthetic import synthetic_batch
+    kw = dict(dim_input=13, dim_output=1, k=32, num_layers=2, graphnorm=False)
+    torch.manual_seed(0)
+    model = pv.SartorrasEGNN(tmp_path, 0, 0, None, None, **kw).cuda()
+    loader = []
+    for b in range(3):
+        coords, bp, feats, cptr = synthetic_batch(10 * b, 2, 120, 10)
+        batch = pv.PackedBatch.from_arrays(
+            coords, bp, feats, cptr, 4.0, 4.0,
+            y=torch.tensor([1.0, 0.0]),
+            lig_fname=[f'lig_{b}_0.parquet', f'lig_{b}_1.parquet'],
+            rec_fname=[f'rec_{b}.parquet'] * 2)
+        loader.append(batch)
+    model.val(loader, tmp_path / 'predictions_test.txt')
+    lines = (tmp_path / 'pose_predictions_test.txt').read_text().splitlines()
+    assert len(lines) == 6
+    for i, line in enumerate(lines):
+        y_true, rest = line.split(' | ')
+        y_pred, rec, lig = rest.split(' ')
+        assert y_true == ('1.000' if i % 2 == 0 else '0.000')
+        assert 0.0 <= float(y_pred) <= 1.0 and len(y_pred.split('.')[1]) == 3
+        assert rec == f'rec_{i // 2}.parquet' and lig == f'lig_{i // 2}_{i % 2}.parquet'
