@@ -1,0 +1,511 @@
+"""Types-file / parquet complex loader feeding the device graph builder (N2).
+
+Host-side mirror of the scoring-relevant part of the reference's
+`PygPointCloudDataset` + `get_data_loader`
+(/root/reference/point_vs/preprocessing/data_loaders.py:33-520) and the
+preprocessing helpers it calls (`concat_structs`, `make_box`,
+`make_bit_vector`, preprocessing/preprocessing.py:165-300): parse the types
+file, read the receptor/ligand parquets, crop the receptor to the atoms within
+`radius` of any ligand atom, drop hydrogens, type the atoms, one-hot them.
+
+Where the reference then calls `generate_edges` per complex on the CPU and lets
+PyG collate the graphs, this loader packs the whole mini-batch into flat host
+arrays and hands them to K1 once (`PackedBatch.from_arrays`), so the radius
+graph of the batch is built on the device in destination-sorted CSR form.
+
+Reference features that only make sense for augmentation-heavy training are
+refused loudly rather than approximated (`augmented_active_count`,
+`p_remove_entity`, `p_noise`, `bp`, `include_strain_info`, `prune`: with
+`prune=True` the reference itself returns node features for the unpruned
+structure and edges indexed into the pruned one).  `rot=True` draws a rotation
+with the same distribution (Arvo 1992) from this module's own RNG stream; EGNN
+scores are invariant to it.
+"""
+import math
+import threading
+from collections import OrderedDict, deque
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .graph import PackedBatch
+
+_COLUMNS = ('x', 'y', 'z', 'atomic_number', 'types', 'bp')
+
+
+# --------------------------------------------------------------------------
+# types files
+# --------------------------------------------------------------------------
+def parse_classification_types(types_fname):
+    """`classifiaction_types_to_lists` (data_loaders.py:560-642) without the
+    strain columns: -> (labels, rmsds, receptors, ligands).
+
+    Line format `<label> <...> <rmsd> <receptor> <ligand> <...>`; a two-column
+    line is `<receptor> <ligand>` with label None.  The first token that is
+    not a number is the receptor (the token before it is the rmsd), the next
+    one the ligand; tokens starting with '#' are skipped."""
+    labels, rmsds, recs, ligs = [], [], [], []
+    with open(Path(types_fname).expanduser(), 'r', encoding='utf-8') as f:
+        for line in f:
+            chunks = line.strip().split()
+            if not chunks:
+                continue
+            if len(chunks) == 2:
+                label, rmsd, rec, lig = None, None, chunks[0], chunks[1]
+            else:
+                try:
+                    label = int(chunks[0])
+                except ValueError:
+                    label = None
+                rmsd = rec = lig = None
+                for idx, chunk in enumerate(chunks):
+                    if chunk.startswith('#'):
+                        continue
+                    try:
+                        float(chunk)
+                    except ValueError:
+                        if rec is None:
+                            rec = chunk
+                            rmsd = float(chunks[idx - 1])
+                        else:
+                            # the reference keeps overwriting: last one wins
+                            lig = chunk
+            if rec is not None and lig is not None:
+                labels.append(label)
+                rmsds.append(rmsd)
+                recs.append(rec)
+                ligs.append(lig)
+    return labels, rmsds, recs, ligs
+
+
+def parse_regression_types(data_root, types_fname):
+    """`regression_types_to_lists` (data_loaders.py:523-557): whitespace
+    separated `<pki> <pkd> <ic50> <receptor> <ligand>` (or the two paths
+    only); entries whose files are missing under `data_root` are dropped."""
+    rows = []
+    with open(Path(types_fname).expanduser(), 'r', encoding='utf-8') as f:
+        for line in f:
+            chunks = line.strip().split()
+            if chunks:
+                rows.append(chunks)
+    if not rows:
+        return [], [], [], [], []
+    n_cols = len(rows[0])
+    pki, pkd, ic50, recs, ligs = [], [], [], [], []
+    for chunks in rows:
+        if n_cols >= 5:
+            a, b, c, rec, lig = chunks[:5]
+            a, b, c = float(a), float(b), float(c)
+        else:
+            a = b = c = None
+            rec, lig = chunks[-2], chunks[-1]
+        if Path(data_root, rec).is_file() and Path(data_root, lig).is_file():
+            pki.append(a)
+            pkd.append(b)
+            ic50.append(c)
+            recs.append(rec)
+            ligs.append(lig)
+    return pki, pkd, ic50, recs, ligs
+
+
+# --------------------------------------------------------------------------
+# one complex
+# --------------------------------------------------------------------------
+def read_structure(path):
+    """Parquet -> dict of numpy columns (x, y, z f64; atomic_number, types, bp
+    i64), as `pd.read_parquet` gives the reference."""
+    import pyarrow.parquet as pq   # noqa: PLC0415 (keeps import torch-light)
+    table = pq.read_table(str(path), columns=list(_COLUMNS))
+    out = {}
+    for name in _COLUMNS:
+        col = table.column(name).to_numpy()
+        out[name] = np.ascontiguousarray(
+            col, dtype=np.float64 if name in 'xyz' else np.int64)
+    return out
+
+
+def atomic_number_table(polar_hydrogens):
+    """`PointCloudDataset.__init__` (data_loaders.py:199-223): index of each
+    recognised element, elements sharing valence properties grouped, every
+    other element mapped to `n_features` itself.  -> (dict, n_features)."""
+    recognised = (6, 7, 8, 9, 15, 16, 17)
+    groupings = ((35, 53), (3, 11, 19), (4, 12, 20), (26, 29, 30))
+    table = {num: idx for idx, num in enumerate(recognised)}
+    for grouping in groupings:
+        nxt = max(table.values()) + 1
+        table.update({elem: nxt for elem in grouping})
+    if polar_hydrogens:
+        table[1] = max(table.values()) + 1
+    return table, max(table.values()) + 1
+
+
+def make_box(lig_xyz, rec_xyz, radius):
+    """Indices of the receptor atoms closer than `radius` to any ligand atom
+    (`make_box(relative_to_ligand=True)`, preprocessing.py:165-195).  Same
+    fp64 arithmetic as scipy's euclidean `cdist`: sqrt(dx²+dy²+dz²) < radius."""
+    if len(lig_xyz) == 0 or len(rec_xyz) == 0:
+        return np.zeros(0, dtype=np.int64)
+    d = lig_xyz[:, None, :] - rec_xyz[None, :, :]
+    dist = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]
+                   + d[..., 2] * d[..., 2])
+    return np.nonzero((dist < radius).any(axis=0))[0]
+
+
+def make_bit_vector(atom_types, n_atom_types, compact=True):
+    """`make_bit_vector` (preprocessing.py:214-239) -> float32 [N, F].
+    compact: one-hot of `type % n` over n + 1 columns, the last column then
+    overwritten with `type // n` (0 ligand, 1 receptor)."""
+    atom_types = np.asarray(atom_types, dtype=np.int64)
+    n = len(atom_types)
+    if compact:
+        out = np.zeros((n, n_atom_types + 1), dtype=np.float32)
+        out[np.arange(n), atom_types % n_atom_types] = 1.0
+        out[:, -1] = (atom_types // n_atom_types).astype(np.float32)
+    else:
+        if n and (atom_types.min() < 0 or atom_types.max() >= 2 * n_atom_types):
+            raise ValueError('atom type outside the one-hot range')
+        out = np.zeros((n, 2 * n_atom_types), dtype=np.float32)
+        out[np.arange(n), atom_types] = 1.0
+    return out
+
+
+def uniform_random_rotation(x, rng):
+    """Arvo's fast random rotation, as preprocessing.py:30-53, drawing from
+    `rng` (a numpy Generator) instead of the global numpy state."""
+    x1, x2, x3 = rng.random(), 2 * np.pi * rng.random(), rng.random()
+    rot = np.eye(3)
+    rot[0, 0] = rot[1, 1] = np.cos(2 * np.pi * x1)
+    rot[0, 1] = -np.sin(2 * np.pi * x1)
+    rot[1, 0] = np.sin(2 * np.pi * x1)
+    v = np.array([np.cos(x2) * np.sqrt(x3), np.sin(x2) * np.sqrt(x3),
+                  np.sqrt(1 - x3)])
+    m = -((np.eye(3) - 2 * np.outer(v, v)) @ rot)
+    mean = x.mean(axis=0)
+    return ((x - mean) @ m) + mean @ m
+
+
+class Complex:
+    """One preprocessed complex on the host."""
+    __slots__ = ('coords', 'bp', 'feats', 'types', 'atomic_number')
+
+    def __init__(self, coords, bp, feats, types, atomic_number):
+        self.coords, self.bp, self.feats = coords, bp, feats
+        self.types, self.atomic_number = types, atomic_number
+
+    def __len__(self):
+        return len(self.bp)
+
+
+def build_complex(rec, lig, n_features, radius, polar_hydrogens=False,
+                  use_atomic_numbers=False, compact=True,
+                  atomic_number_to_index=None):
+    """`parquets_to_inputs` (data_loaders.py:259-310) on column dicts:
+    concat [ligand; receptor] with receptor types shifted by n_features, box,
+    hydrogen filter, optional atomic-number typing, one-hot."""
+    cols = {}
+    for name in _COLUMNS:
+        cols[name] = np.concatenate([lig[name], rec[name]])
+    cols['types'] = cols['types'].copy()
+    cols['types'][len(lig['types']):] += n_features
+    xyz = np.stack([cols['x'], cols['y'], cols['z']], axis=1)
+    lig_idx = np.nonzero(cols['bp'] == 0)[0]
+    rec_idx = np.nonzero(cols['bp'] == 1)[0]
+    keep_rec = rec_idx[make_box(xyz[lig_idx], xyz[rec_idx], radius)]
+    keep = np.concatenate([lig_idx, keep_rec])
+    if not polar_hydrogens:
+        keep = keep[cols['atomic_number'][keep] > 1]
+    bp = cols['bp'][keep]
+    anum = cols['atomic_number'][keep]
+    if use_atomic_numbers:
+        idx = np.array([atomic_number_to_index.get(int(a), n_features)
+                        for a in anum], dtype=np.int64).reshape(len(anum))
+        types = idx + bp * n_features
+    else:
+        types = cols['types'][keep]
+    feats = make_bit_vector(types, n_features, compact)
+    return Complex(np.ascontiguousarray(xyz[keep]), bp.astype(np.int32), feats,
+                   types, anum)
+
+
+# --------------------------------------------------------------------------
+# dataset + loader
+# --------------------------------------------------------------------------
+class ComplexDataset:
+    """Mirror of `PygPointCloudDataset` (constructor argument names and
+    defaults of data_loaders.py:36-47).  `dataset[i]` is a one-complex
+    `PackedBatch`; `dataset.load(i)` the host-side `Complex`."""
+
+    def __init__(self, base_path, radius=12, polar_hydrogens=True,
+                 use_atomic_numbers=False, compact=True, rot=False,
+                 augmented_active_count=0, augmented_active_min_angle=90,
+                 max_active_rms_distance=None, min_inactive_rms_distance=None,
+                 max_inactive_rms_distance=None, fname_suffix='parquet',
+                 model_task='classification', types_fname=None,
+                 edge_radius=None, estimate_bonds=False, prune=False, bp=None,
+                 p_remove_entity=0, extended_atom_types=False, p_noise=-1,
+                 include_strain_info=False, device=None, seed=None,
+                 receptor_cache=8, **kwargs):
+        del augmented_active_min_angle, fname_suffix, kwargs
+        if (max_active_rms_distance is None) != (
+                min_inactive_rms_distance is None):
+            raise AssertionError('max_active_rms_distance and '
+                                 'min_inactive_rms_distance go together')
+        for name, bad in (('augmented_active_count', augmented_active_count),
+                          ('p_remove_entity', p_remove_entity > 0),
+                          ('p_noise', p_noise > 0), ('bp', bp is not None),
+                          ('include_strain_info', include_strain_info),
+                          ('prune', prune)):
+            if bad:
+                raise NotImplementedError(
+                    f'{name} is not supported by the packed-batch loader')
+        if types_fname is None:
+            raise ValueError('types_fname is required')
+        self.base_path = Path(base_path).expanduser()
+        if not self.base_path.exists():
+            raise FileNotFoundError(
+                f'Dataset {self.base_path} does not exist.')
+        self.radius, self.edge_radius = radius, edge_radius
+        self.estimate_bonds = estimate_bonds
+        self.polar_hydrogens = polar_hydrogens
+        self.use_atomic_numbers, self.compact = use_atomic_numbers, compact
+        self.model_task, self.rot = model_task, rot
+        self.device = device
+        self.use_types = True
+        self._rng = np.random.default_rng(seed)
+        self._cache = OrderedDict()
+        self._cache_size = receptor_cache
+        self._cache_lock = threading.Lock()
+
+        self.sampler = None
+        if model_task.endswith('regression'):
+            (self.pki, self.pkd, self.ic50, self.receptor_fnames,
+             self.ligand_fnames) = parse_regression_types(
+                 self.base_path, types_fname)
+            labels = []
+        else:
+            labels, rmsds, recs, ligs = parse_classification_types(types_fname)
+            label_by_rmsd = (max_active_rms_distance is not None
+                             or min_inactive_rms_distance is not None
+                             or max_inactive_rms_distance is not None)
+            if label_by_rmsd:
+                # pose selection: relabel by rmsd from the crystal pose
+                # (data_loaders.py:137-154)
+                hi_act = np.inf if max_active_rms_distance is None \
+                    else max_active_rms_distance
+                hi_inact = np.inf if max_inactive_rms_distance is None \
+                    else max_inactive_rms_distance
+                lo_inact = 0 if min_inactive_rms_distance is None \
+                    else min_inactive_rms_distance
+                keep_labels, keep_recs, keep_ligs = [], [], []
+                for rmsd, rec, lig in zip(rmsds, recs, ligs):
+                    if rmsd < 0:
+                        continue
+                    if rmsd < hi_act:
+                        lab = 1
+                    elif rmsd >= hi_inact:
+                        continue
+                    elif rmsd >= lo_inact:
+                        lab = 0
+                    else:
+                        continue
+                    keep_labels.append(lab)
+                    keep_recs.append(rec)
+                    keep_ligs.append(lig)
+                labels, recs, ligs = keep_labels, keep_recs, keep_ligs
+            self.receptor_fnames, self.ligand_fnames = recs, ligs
+            labels = np.array(labels)
+            if len(labels) and labels[0] is not None:
+                active = np.sum(labels)
+                if 0 < active < len(labels):
+                    weights = 1.0 / np.array([len(labels) - active, active])
+                    self.sample_weights = torch.from_numpy(
+                        np.array([weights[i] for i in labels]))
+                    self.sampler = torch.utils.data.WeightedRandomSampler(
+                        self.sample_weights, len(self.sample_weights))
+        self.labels = labels
+        self.pre_aug_ds_len = len(self.ligand_fnames)
+
+        if use_atomic_numbers:
+            self.atomic_number_to_index, self.n_features = \
+                atomic_number_table(polar_hydrogens)
+        elif polar_hydrogens:
+            raise NotImplementedError('Hydrogens temporarily disabled.')
+        else:
+            self.atomic_number_to_index = None
+            self.n_features = 11 + 8 * bool(extended_atom_types)
+        self.feature_dim = self.n_features + 1 if compact \
+            else self.n_features * 2
+
+    def __len__(self):
+        return len(self.ligand_fnames)
+
+    # edge radii exactly as PygPointCloudDataset.__getitem__ (:356-357)
+    @property
+    def inter_radius(self):
+        return self.edge_radius if (self.edge_radius or 0) > 0 else 4
+
+    @property
+    def intra_radius(self):
+        return 2.0 if self.estimate_bonds else self.inter_radius
+
+    def label(self, item):
+        """`index_to_parquets` label (:229-237)."""
+        if self.model_task == 'classification':
+            return self.labels[item]
+        trio = (self.pki[item], self.pkd[item], self.ic50[item])
+        if self.model_task == 'multi_regression':
+            return trio
+        return None if trio[0] is None else max(trio)
+
+    def _receptor(self, path):
+        with self._cache_lock:
+            hit = self._cache.get(path)
+            if hit is not None:
+                self._cache.move_to_end(path)
+                return hit
+        cols = read_structure(path)
+        with self._cache_lock:
+            self._cache[path] = cols
+            while len(self._cache) > self._cache_size:
+                self._cache.popitem(last=False)
+        return cols
+
+    def load(self, item):
+        """Host-side preprocessing of complex `item` -> Complex."""
+        rec_path = self.base_path / self.receptor_fnames[item]
+        lig_path = self.base_path / self.ligand_fnames[item]
+        if not lig_path.is_file():
+            raise FileNotFoundError(lig_path, 'does not exist.')
+        if not rec_path.is_file():
+            raise FileNotFoundError(rec_path, 'does not exist')
+        return build_complex(
+            self._receptor(rec_path), read_structure(lig_path),
+            self.n_features, self.radius, self.polar_hydrogens,
+            self.use_atomic_numbers, self.compact, self.atomic_number_to_index)
+
+    def pack(self, items, complexes=None, edge_capacity=None):
+        """Complexes `items` -> one PackedBatch with the batch's radius graph
+        built on the device."""
+        if complexes is None:
+            complexes = [self.load(i) for i in items]
+        sizes = [len(c) for c in complexes]
+        cptr = np.zeros(len(complexes) + 1, dtype=np.int32)
+        np.cumsum(sizes, out=cptr[1:])
+        if complexes:
+            coords = np.concatenate([c.coords for c in complexes])
+            bp = np.concatenate([c.bp for c in complexes])
+            feats = np.concatenate([c.feats for c in complexes])
+        else:
+            coords = np.zeros((0, 3))
+            bp = np.zeros(0, dtype=np.int32)
+            feats = np.zeros((0, self.feature_dim), dtype=np.float32)
+        labels = [self.label(i) for i in items]
+        if not labels or labels[0] is None or (
+                isinstance(labels[0], tuple) and labels[0][0] is None):
+            y = None
+        elif self.model_task == 'classification':
+            y = torch.tensor([int(v) for v in labels], dtype=torch.long)
+        else:   # PyG concatenates the per-complex label vectors
+            y = torch.tensor(np.array(labels, dtype=np.float64).reshape(-1),
+                             dtype=torch.float32)
+        batch = PackedBatch.from_arrays(
+            coords, bp, feats, cptr, inter_radius=self.inter_radius,
+            intra_radius=self.intra_radius, y=y, device=self.device,
+            lig_fname=[Path(self.ligand_fnames[i]) for i in items],
+            rec_fname=[Path(self.receptor_fnames[i]) for i in items],
+            edge_capacity=edge_capacity)
+        if self.rot:
+            # the reference rotates `pos` only; edges come from the unrotated
+            # structure (data_loaders.py:303-305 vs :365)
+            pos = coords.copy()
+            for b in range(len(complexes)):
+                s, e = cptr[b], cptr[b + 1]
+                if e > s:
+                    pos[s:e] = uniform_random_rotation(pos[s:e], self._rng)
+            batch.pos = torch.as_tensor(pos, dtype=torch.float32).to(
+                batch.x.device)
+        return batch
+
+    def __getitem__(self, item):
+        return self.pack([item])
+
+
+class PackedLoader:
+    """Iterates a ComplexDataset in mini-batches of PackedBatch (the role of
+    `GeoDataLoader(ds, batch_size, False, sampler=..., drop_last=False)`,
+    data_loaders.py:514-519).  Parquet reading and cropping run on
+    `num_workers` host threads, `prefetch` batches ahead of the device."""
+
+    def __init__(self, dataset, batch_size=32, sampler=None, num_workers=4,
+                 prefetch=2, edge_capacity=None):
+        self.dataset, self.batch_size, self.sampler = dataset, batch_size, sampler
+        self.num_workers, self.prefetch = num_workers, max(1, prefetch)
+        self.edge_capacity = edge_capacity
+
+    def __len__(self):
+        return math.ceil(len(self.dataset) / self.batch_size)
+
+    def _batches(self):
+        order = list(self.sampler) if self.sampler is not None \
+            else list(range(len(self.dataset)))
+        return [order[i:i + self.batch_size]
+                for i in range(0, len(order), self.batch_size)]
+
+    def __iter__(self):
+        batches = self._batches()
+        ds = self.dataset
+        if self.num_workers <= 0:
+            for items in batches:
+                yield ds.pack(items, edge_capacity=self.edge_capacity)
+            return
+        with ThreadPoolExecutor(self.num_workers) as pool:
+            pending, nxt = deque(), 0
+            while nxt < len(batches) or pending:
+                while nxt < len(batches) and len(pending) < self.prefetch:
+                    items = batches[nxt]
+                    pending.append(
+                        (items, [pool.submit(ds.load, i) for i in items]))
+                    nxt += 1
+                items, futures = pending.popleft()
+                yield ds.pack(items, [f.result() for f in futures],
+                              edge_capacity=self.edge_capacity)
+
+
+def get_data_loader(data_root, dataset_class=None, receptors=None,
+                    batch_size=32, compact=True, use_atomic_numbers=False,
+                    radius=6, rot=True, augmented_actives=0, min_aug_angle=30,
+                    polar_hydrogens=True, mode='train',
+                    model_task='classification', max_active_rms_distance=None,
+                    fname_suffix='parquet', min_inactive_rms_distance=None,
+                    types_fname=None, edge_radius=None, prune=False,
+                    estimate_bonds=False, bp=None, p_noise=-1, num_workers=4,
+                    device=None, **kwargs):
+    """Signature of the reference's `get_data_loader` (data_loaders.py:483-520).
+    `dataset_class` is accepted for call compatibility and ignored: there is
+    one dataset here.  As in the reference, classification training draws
+    complexes with the class-balancing weighted sampler and every other mode
+    walks the types file in order."""
+    del dataset_class, receptors
+    ds = ComplexDataset(
+        data_root, compact=compact, augmented_active_count=augmented_actives,
+        augmented_active_min_angle=min_aug_angle,
+        polar_hydrogens=polar_hydrogens,
+        max_active_rms_distance=max_active_rms_distance,
+        min_inactive_rms_distance=min_inactive_rms_distance,
+        use_atomic_numbers=use_atomic_numbers, fname_suffix=fname_suffix,
+        types_fname=types_fname, edge_radius=edge_radius,
+        estimate_bonds=estimate_bonds, prune=prune, bp=bp, radius=radius,
+        rot=rot, model_task=model_task, p_noise=p_noise, device=device,
+        **kwargs)
+    sampler = ds.sampler if (ds.model_task == 'classification'
+                             and mode == 'train') else None
+    return PackedLoader(ds, batch_size, sampler=sampler,
+                        num_workers=num_workers)
+
+
+__all__ = ['ComplexDataset', 'PackedLoader', 'get_data_loader',
+           'parse_classification_types', 'parse_regression_types',
+           'read_structure', 'build_complex', 'make_box', 'make_bit_vector',
+           'atomic_number_table', 'Complex']

@@ -5,9 +5,10 @@
 
 Loads a reference-format checkpoint into the CUDA-backed model, scores the
 types file and writes `predictions_<types>-<ckpt>.txt` next to the checkpoint
-in the reference's line format.  The parquet/types-file data loader is the
-reference's own (`point_vs.preprocessing.data_loaders`, outside the hot path):
-it must be importable, or a loader factory can be passed programmatically.
+in the reference's line format.  Complexes come from `pointvs_b200.data`
+(types file + parquets -> packed batches whose radius graph is built on the
+device); `--reference_loader` feeds the reference's own PyG data loader through
+the same model instead, if PointVS is importable.
 """
 import argparse
 from pathlib import Path
@@ -21,9 +22,8 @@ def _reference_loader_factory():
             get_data_loader, PygPointCloudDataset)
     except ImportError as exc:   # pragma: no cover - depends on environment
         raise ImportError(
-            'pointvs_b200.inference uses PointVS\'s own parquet/types data '
-            'loader (point_vs.preprocessing.data_loaders); install PointVS or '
-            'pass loader_factory=...') from exc
+            '--reference_loader needs PointVS itself '
+            '(point_vs.preprocessing.data_loaders) to be importable') from exc
 
     def factory(data_root, **kwargs):
         return get_data_loader(data_root, dataset_class=PygPointCloudDataset,
@@ -31,8 +31,14 @@ def _reference_loader_factory():
     return factory
 
 
+def _packed_loader_factory():
+    from .data import get_data_loader   # noqa: PLC0415
+    return get_data_loader
+
+
 def get_model_and_test_dl(checkpoint_path, test_types, test_data_root,
-                          model_task=None, loader_factory=None):
+                          model_task=None, loader_factory=None,
+                          batch_size=None):
     """Same contract as inference.py:35-74 of the reference."""
     checkpoint_path, model, model_kwargs, cmd_line_args = load_model(
         checkpoint_path, silent=False, model_task=model_task)
@@ -47,17 +53,19 @@ def get_model_and_test_dl(checkpoint_path, test_types, test_data_root,
         if is_multi and model_task_ == 'regression':
             model_task_ = 'multi_regression'
     model.set_task(model_task_)
-    factory = loader_factory or _reference_loader_factory()
+    factory = loader_factory or _packed_loader_factory()
     test_dl = factory(
-        test_data_root, receptors=None, compact=cmd_line_args['compact'],
-        use_atomic_numbers=cmd_line_args['use_atomic_numbers'],
-        radius=cmd_line_args['radius'],
-        polar_hydrogens=cmd_line_args['hydrogens'],
-        batch_size=cmd_line_args['batch_size'], types_fname=test_types,
-        edge_radius=cmd_line_args['edge_radius'],
+        test_data_root, receptors=None,
+        compact=cmd_line_args.get('compact', False),
+        use_atomic_numbers=cmd_line_args.get('use_atomic_numbers', False),
+        radius=cmd_line_args.get('radius', 10),
+        polar_hydrogens=cmd_line_args.get('hydrogens', False),
+        batch_size=batch_size or cmd_line_args.get('batch_size', 32),
+        types_fname=test_types,
+        edge_radius=cmd_line_args.get('edge_radius', 4),
         estimate_bonds=cmd_line_args.get('estimate_bonds', False),
         prune=cmd_line_args.get('prune', False), rot=False, mode='val',
-        fname_suffix=cmd_line_args['input_suffix'],
+        fname_suffix=cmd_line_args.get('input_suffix', 'parquet'),
         extended_atom_types=cmd_line_args.get('extended_atom_types', False),
         model_task=model_task_)
     return checkpoint_path, model, model_kwargs, cmd_line_args, test_dl
@@ -73,10 +81,17 @@ def main(argv=None):
     parser.add_argument('--math', default='fp32',
                         choices=['fp32', 'bf16x3', 'bf16'],
                         help='arithmetic of the per-edge contractions')
+    parser.add_argument('--reference_loader', action='store_true',
+                        help="use PointVS's own PyG data loader")
+    parser.add_argument('--batch_size', type=int, default=None,
+                        help='complexes per packed batch (default: the '
+                             'value the model was trained with)')
     args = parser.parse_args(argv)
     checkpoint_path, model, _, _, test_dl = get_model_and_test_dl(
         Path(args.model_checkpoint).expanduser(), args.test_types,
-        args.test_data_root, args.model_task)
+        args.test_data_root, args.model_task,
+        loader_factory=_reference_loader_factory()
+        if args.reference_loader else None, batch_size=args.batch_size)
     if args.model_task is not None:
         model.set_task({'pose': 'classification',
                         'affinity': 'regression'}[args.model_task])

@@ -1,0 +1,156 @@
+"""Row N2 on the GPU: types file + parquets -> packed batch -> K1 -> scores,
+against what the reference's own data loader returned for the same files
+(tests/golden/loader.npz) and the CPU oracle run on those reference graphs."""
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from tests import helpers
+from tests import gpu_helpers as gh
+from tests.golden.loader_configs import CONFIGS, ROOT
+from oracle import radius_graph as rg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def gold():
+    return helpers.load_npz('loader.npz')
+
+
+def _reference_batch(gold, cfg, items):
+    """Concatenate the reference loader's per-complex graphs as PyG would."""
+    xs, ps, rows, cols, attrs, batch, off = [], [], [], [], [], [], 0
+    for b, i in enumerate(items):
+        x = gold[f'{cfg}/{i}/x'].astype(np.float32)
+        ei = gold[f'{cfg}/{i}/edge_index'].astype(np.int64)
+        xs.append(x)
+        ps.append(gold[f'{cfg}/{i}/pos'])
+        rows.append(ei[0] + off)
+        cols.append(ei[1] + off)
+        attrs.append(gold[f'{cfg}/{i}/edge_attr'])
+        batch.append(np.full(len(x), b))
+        off += len(x)
+    return (np.concatenate(xs), np.concatenate(ps), np.concatenate(rows),
+            np.concatenate(cols), np.concatenate(attrs), np.concatenate(batch))
+
+
+@pytest.mark.parametrize('cfg', sorted(CONFIGS))
+@pytest.mark.parametrize('workers', [0, 3])
+def test_packed_loader_graph_is_the_reference_graph(cfg, workers, gold):
+    from pointvs_b200 import data
+    ds = data.ComplexDataset(ROOT, types_fname=ROOT / 'pose.types', rot=False,
+                             device='cuda', **CONFIGS[cfg])
+    n = len(ds)
+    seen = 0
+    for batch in data.PackedLoader(ds, batch_size=4, num_workers=workers):
+        items = list(range(seen, min(n, seen + 4)))
+        seen += len(items)
+        x, pos, row, col, attr, _ = _reference_batch(gold, cfg, items)
+        np.testing.assert_array_equal(batch.x.cpu().numpy(), x)
+        np.testing.assert_array_equal(batch.pos.cpu().numpy(), pos)
+        assert batch.num_graphs == len(items)
+        order = rg.csr_order(row, col, attr)
+        want = (row[order], col[order], attr[order])
+        ei = batch.edge_index.cpu().numpy()
+        np.testing.assert_array_equal(ei[0], want[0])
+        np.testing.assert_array_equal(ei[1], want[1])
+        np.testing.assert_array_equal(
+            batch.edge_attr.argmax(dim=1).cpu().numpy(), want[2])
+        np.testing.assert_array_equal(
+            batch.y.numpy(), [int(gold[f'{cfg}/{i}/y']) for i in items])
+        assert [str(p) for p in batch.lig_fname] == [
+            str(gold[f'{cfg}/{i}/lig']) for i in items]
+    assert seen == n
+
+
+def _write_run(tmp_path, kw, cfg, model_type='egnn'):
+    import pointvs_b200 as pv
+    run = tmp_path / 'run'
+    (run / 'checkpoints').mkdir(parents=True)
+    torch.manual_seed(11)
+    C = pv.MultitaskSatorrasEGNN if model_type == 'multitask' \
+        else pv.SartorrasEGNN
+    model = C(run, 1e-3, 1e-4, None, None, silent=True, **kw)
+    with open(run / 'model_kwargs.yaml', 'w') as f:
+        yaml.dump(kw, f)
+    c = CONFIGS[cfg]
+    with open(run / 'cmd_args.yaml', 'w') as f:
+        yaml.dump({'model': model_type, 'learning_rate': 1e-3,
+                   'weight_decay': 1e-4, 'save_path': str(run),
+                   'compact': c['compact'], 'radius': c['radius'],
+                   'use_atomic_numbers': c['use_atomic_numbers'],
+                   'hydrogens': c['polar_hydrogens'], 'batch_size': 3,
+                   'edge_radius': c['edge_radius'],
+                   'estimate_bonds': c.get('estimate_bonds', False),
+                   'input_suffix': 'parquet', 'egnn_attention': True,
+                   'model_task': 'classification'}, f)
+    torch.save({'model_state_dict': model.state_dict(),
+                'optimiser_state_dict': {}, 'p_epoch': 1},
+               run / 'checkpoints' / 'pose_ckpt_epoch_1.pt')
+    return run, model
+
+
+@pytest.mark.parametrize('cfg,math', [('smina_r10_e4', 'fp32'),
+                                      ('atomic_h_r6_e3', 'bf16x3'),
+                                      ('smina_wide_r7_bonds', 'fp32')])
+def test_inference_cli_scores_match_oracle_on_reference_graphs(
+        tmp_path, gold, cfg, math):
+    """`python -m pointvs_b200.inference ckpt types root`: every line of the
+    predictions file against the oracle evaluated on the graphs the REFERENCE
+    loader produced for the same complexes."""
+    from pointvs_b200 import inference
+    dim = int(gold[f'{cfg}/feature_dim'])
+    kw = dict(dim_input=dim, dim_output=1, k=48, num_layers=3,
+              graphnorm=True, edge_attention=True, node_attention=True,
+              residual=True, normalize=True, tanh=True)
+    run, model = _write_run(tmp_path, kw, cfg)
+    out = inference.main([str(run), str(ROOT / 'pose.types'), str(ROOT),
+                          '--math', math])
+    pose = out.parent / ('pose_' + out.name)
+    lines = pose.read_text().splitlines()
+    n = int(gold[f'{cfg}/n'])
+    assert len(lines) == n
+    from oracle import egnn_oracle
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    for start in range(0, n, 3):      # GraphNorm statistics are per batch
+        items = list(range(start, min(n, start + 3)))
+        x, pos, row, col, attr, batch = _reference_batch(gold, cfg, items)
+        want, _ = egnn_oracle.model_forward(
+            sd, torch.from_numpy(x), torch.from_numpy(np.stack([row, col])),
+            torch.from_numpy(pos),
+            torch.nn.functional.one_hot(
+                torch.from_numpy(attr.astype(np.int64)), 3),
+            torch.from_numpy(batch), num_layers=3, multitask=False,
+            model_task='classification', **helpers.oracle_kwargs(kw))
+        want = torch.sigmoid(want).reshape(-1).numpy()
+        for j, i in enumerate(items):
+            y_true, rest = lines[i].split(' | ')
+            y_pred, rec, lig = rest.split(' ')
+            assert float(y_true) == float(gold[f'{cfg}/{i}/y'])
+            assert abs(float(y_pred) - want[j]) <= 6e-4 + 1e-4 * abs(want[j])
+            assert lig == str(gold[f'{cfg}/{i}/lig'])
+            assert rec == str(gold[f'{cfg}/{i}/rec'])
+
+
+def test_regression_batches_and_rotation(gold):
+    from pointvs_b200 import data
+    dl = data.get_data_loader(
+        ROOT, types_fname=ROOT / 'affinity.types', batch_size=4, mode='val',
+        model_task='multi_regression', rot=True, seed=5, device='cuda',
+        **CONFIGS['smina_r10_e4'])
+    b0 = next(iter(dl))
+    want = np.concatenate([gold[f'multi_regression/{i}/y'] for i in range(4)])
+    np.testing.assert_array_equal(b0.y.numpy(), want)
+    # positions are rotated per complex about its centroid image; the graph is
+    # that of the unrotated structure
+    x, pos, row, col, attr, batch = _reference_batch(
+        gold, 'smina_r10_e4', range(4))
+    assert not np.allclose(b0.pos.cpu().numpy(), pos)
+    got = b0.pos.cpu().numpy()
+    first = batch == 0
+    d_ref = np.linalg.norm(pos[first][:, None] - pos[first][None], axis=-1)
+    d_got = np.linalg.norm(got[first][:, None] - got[first][None], axis=-1)
+    np.testing.assert_allclose(d_ref, d_got, atol=2e-4)
+    assert b0.edge_index.shape[1] == len(row)
