@@ -117,7 +117,9 @@ def read_structure(path):
     """Parquet -> dict of numpy columns (x, y, z f64; atomic_number, types, bp
     i64), as `pd.read_parquet` gives the reference."""
     import pyarrow.parquet as pq   # noqa: PLC0415 (keeps import torch-light)
-    table = pq.read_table(str(path), columns=list(_COLUMNS))
+    # ParquetFile skips the dataset/filesystem discovery of pq.read_table
+    table = pq.ParquetFile(str(path)).read(columns=list(_COLUMNS),
+                                           use_threads=False)
     out = {}
     for name in _COLUMNS:
         col = table.column(name).to_numpy()
@@ -147,10 +149,15 @@ def make_box(lig_xyz, rec_xyz, radius):
     fp64 arithmetic as scipy's euclidean `cdist`: sqrt(dx²+dy²+dz²) < radius."""
     if len(lig_xyz) == 0 or len(rec_xyz) == 0:
         return np.zeros(0, dtype=np.int64)
-    d = lig_xyz[:, None, :] - rec_xyz[None, :, :]
+    # exact prefilter: an atom outside the ligand's bounding box grown by
+    # `radius` (plus slack for rounding) cannot pass the distance test
+    lo = lig_xyz.min(axis=0) - radius * (1 + 1e-9) - 1e-9
+    hi = lig_xyz.max(axis=0) + radius * (1 + 1e-9) + 1e-9
+    near = np.nonzero(((rec_xyz >= lo) & (rec_xyz <= hi)).all(axis=1))[0]
+    d = lig_xyz[:, None, :] - rec_xyz[None, near, :]
     dist = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]
                    + d[..., 2] * d[..., 2])
-    return np.nonzero((dist < radius).any(axis=0))[0]
+    return near[(dist < radius).any(axis=0)]
 
 
 def make_bit_vector(atom_types, n_atom_types, compact=True):

@@ -1,0 +1,102 @@
+"""Row N2 measurement: types file + parquets on disk -> scores, complexes/s.
+
+Repeats the seven sample complexes under tests/golden/complexes into a types
+file of `--n` lines (the page cache serves the files, so this measures parsing,
+cropping, packing, H2D and the device path, not the disk) and scores them with
+the 8 x 64 `egnn` through `PackedLoader`.  Prints one JSON line; beside it the
+host-only rate of the loader threads and, for a bounded sample, the CPU oracle's
+`generate_edges` restatement per complex (what the reference's loader spends in
+its `__getitem__` besides the same parquet work).
+"""
+import argparse
+import json
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from pointvs_b200 import data, SartorrasEGNN  # noqa: E402
+from tests.golden.loader_configs import CONFIGS, ROOT as COMPLEXES  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--n', type=int, default=2048)
+    ap.add_argument('--batch_size', type=int, default=128)
+    ap.add_argument('--workers', type=int, default=8)
+    ap.add_argument('--math', default='bf16x3')
+    ap.add_argument('--cpu-sample', type=int, default=14)
+    args = ap.parse_args()
+    lines = [ln for ln in (COMPLEXES / 'pose.types').read_text().splitlines()
+             if ln.strip()]
+    cfg = CONFIGS['smina_r10_e4']
+    with tempfile.TemporaryDirectory() as tmp:
+        types = Path(tmp) / 'many.types'
+        types.write_text('\n'.join(lines[i % len(lines)]
+                                   for i in range(args.n)) + '\n')
+        dl = data.get_data_loader(
+            COMPLEXES, types_fname=types, batch_size=args.batch_size,
+            mode='val', rot=False, num_workers=args.workers, device='cuda',
+            **cfg)
+        ds = dl.dataset
+        torch.manual_seed(0)
+        model = SartorrasEGNN(
+            Path(tmp), 0, 0, None, None, silent=True, dim_input=ds.feature_dim,
+            dim_output=1, k=64, num_layers=8, graphnorm=False,
+            edge_attention=True, node_attention=True, residual=True,
+            normalize=True, tanh=True).cuda().eval()
+        model.set_math(args.math)
+        model.set_record_side_channels(False)
+        model.record_embed_coords = False
+
+        def run():
+            outs, atoms = [], 0
+            with torch.no_grad():
+                for batch in dl:
+                    outs.append(model(batch))
+                    atoms += int(batch.x.shape[0])
+            scores = torch.cat(outs).cpu()
+            return scores, atoms
+
+        run()                                   # warm-up (page cache, JIT-free)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        scores, atoms = run()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+
+        # host-only: the loader threads without the device
+        t0 = time.perf_counter()
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max(1, args.workers)) as pool:
+            list(pool.map(ds.load, range(len(ds))))
+        host = time.perf_counter() - t0
+
+        # CPU oracle generate_edges on a bounded sample
+        from oracle import radius_graph as rg
+        t0 = time.perf_counter()
+        for i in range(args.cpu_sample):
+            c = ds.load(i)
+            rg.radius_graph(c.coords, c.bp, ds.inter_radius, ds.intra_radius)
+        cpu_edges = (time.perf_counter() - t0) / args.cpu_sample
+
+    print(json.dumps({
+        'metric': 'complexes scored per second from types file + parquets',
+        'value': round(args.n / wall, 1), 'unit': 'complexes/s',
+        'n_complexes': args.n, 'atoms_per_complex': round(atoms / args.n, 1),
+        'batch_size': args.batch_size, 'loader_threads': args.workers,
+        'math': args.math,
+        'host_loader_only_complexes_per_s': round(args.n / host, 1),
+        'cpu_oracle_load_plus_generate_edges_ms_per_complex':
+            round(cpu_edges * 1e3, 2),
+        'scores_finite': bool(torch.isfinite(scores).all())}))
+
+
+if __name__ == '__main__':
+    main()
