@@ -9,7 +9,9 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_C', 'libpvs_b200.so')
+# PVS_B200_LIB selects another build of the same sources (profiling variants)
+LIB_PATH = os.environ.get('PVS_B200_LIB') or os.path.join(
+    _HERE, '_C', 'libpvs_b200.so')
 
 # flags / enums (mirror include/pvs_b200.h)
 F_RESIDUAL = 0x001

@@ -31,11 +31,30 @@
 namespace pvs {
 
 constexpr int TC_GROUP_THREADS = 128;
-constexpr int TC_GROUPS = 5;
+#ifndef PVS_EXP_GROUPS
+#define PVS_EXP_GROUPS 5
+#endif
+constexpr int TC_GROUPS = PVS_EXP_GROUPS;
 constexpr int TC_THREADS = TC_GROUP_THREADS * TC_GROUPS;
 constexpr int TC_K = 64;          // padded hidden width of the tile
 constexpr uint32_t TC_TMEM_COLS = 512;   // whole TMEM: one CTA per SM
 constexpr uint32_t TC_GROUP_COLS = 64;   // D1 and D2 alias (never live together)
+
+#ifdef PVS_PHASE_PROF
+// Debug build only (scripts/phase_prof.py): cycles each group spends between
+// the phase boundaries of a tile, summed over all groups and tiles.
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE_MARK(i)                                                         \
+    do {                                                                      \
+        if (tid == 0) {                                                       \
+            const long long now_ = clock64();                                 \
+            atomicAdd(&g_phase_cycles[i], (unsigned long long)(now_ - t_prev_)); \
+            t_prev_ = now_;                                                   \
+        }                                                                     \
+    } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#endif
 
 struct TcGroupMisc {
     float e_rad[TE], e_dx[TE], e_dy[TE], e_dz[TE], e_z[TE], e_c[TE];
@@ -136,6 +155,9 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
     float gate = 1.0f;
     if (f_eres && a.edge_gate) gate = a.edge_gate[0];
     const int n_tiles = *a.n_tiles;
+#ifdef PVS_PHASE_PROF
+    long long t_prev_ = clock64();
+#endif
 
     for (int t = blockIdx.x * TC_GROUPS + g; t < n_tiles; t += gridDim.x * TC_GROUPS) {
         const int n0 = a.tile_ptr[t], n1 = a.tile_ptr[t + 1];
@@ -174,54 +196,75 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                     Gm.e_dx[tid] = dx; Gm.e_dy[tid] = dy; Gm.e_dz[tid] = dz;
                 }
                 group_sync(g);
+                PHASE_MARK(0);
                 // ---- stage 1: s1 = silu(P_i + Q_j + w_r r + T[a]) -> A tile.
                 // 8 lanes per edge row (one 16-byte chunk each), 16 rows a pass:
                 // every LDG.128 warp instruction reads 4 full 256-byte rows.
+                // The loads are unconditional (rows past the chunk end repeat
+                // its last row; nobody reads what they produce) and run three
+                // passes ahead of the arithmetic, so a pass never waits for
+                // its own gather.
                 {
                     const int c = tid & 7, slot = tid >> 3;
                     float2 wr2[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         wr2[i] = *reinterpret_cast<const float2 *>(&S.wr[8 * c + 2 * i]);
-#pragma unroll 4
-                    for (int p = 0; p < TE / 16; ++p) {
+                    constexpr int DEPTH = 3, PASSES = TE / 16;
+                    float4 buf[DEPTH][4];
+                    float radv[DEPTH];
+                    int attv[DEPTH];
+                    auto issue = [&](int p, float4 (&bq)[4], float &rad, int &at) {
+                        const int r = min(p * 16 + slot, ne - 1);
+                        const float4 *pp = reinterpret_cast<const float4 *>(
+                            a.P + (size_t)(n0 + Gm.e_rowl[r]) * TC_K + 8 * c);
+#ifdef PVS_EXP_NOGATHER
+                        const float4 *qq = reinterpret_cast<const float4 *>(
+                            a.Q + (size_t)(n0 + Gm.e_rowl[r]) * TC_K + 8 * c);
+#else
+                        const float4 *qq = reinterpret_cast<const float4 *>(
+                            a.Q + (size_t)Gm.e_col[r] * TC_K + 8 * c);
+#endif
+                        bq[0] = __ldg(pp); bq[1] = __ldg(pp + 1);
+                        bq[2] = __ldg(qq); bq[3] = __ldg(qq + 1);
+                        rad = Gm.e_rad[r];
+                        at = Gm.e_attr[r];
+                    };
+                    auto finish = [&](int p, const float4 (&bq)[4], float rad, int at) {
                         const int r = p * 16 + slot;
+                        const float2 rad2 = make_float2(rad, rad);
+                        const float4 *t4 = reinterpret_cast<const float4 *>(&S.T[at][8 * c]);
+                        const float4 ta = t4[0], tb = t4[1];
+                        const float2 pv[4] = {make_float2(bq[0].x, bq[0].y), make_float2(bq[0].z, bq[0].w),
+                                              make_float2(bq[1].x, bq[1].y), make_float2(bq[1].z, bq[1].w)};
+                        const float2 qv[4] = {make_float2(bq[2].x, bq[2].y), make_float2(bq[2].z, bq[2].w),
+                                              make_float2(bq[3].x, bq[3].y), make_float2(bq[3].z, bq[3].w)};
+                        const float2 tv[4] = {make_float2(ta.x, ta.y), make_float2(ta.z, ta.w),
+                                              make_float2(tb.x, tb.y), make_float2(tb.z, tb.w)};
                         float2 v[4];
-                        if (r < ne) {
-                            const float4 *pp = reinterpret_cast<const float4 *>(
-                                a.P + (size_t)(n0 + Gm.e_rowl[r]) * TC_K + 8 * c);
-                            const float4 *qq = reinterpret_cast<const float4 *>(
-                                a.Q + (size_t)Gm.e_col[r] * TC_K + 8 * c);
-                            const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
-                            const float4 q0 = __ldg(qq), q1 = __ldg(qq + 1);
-                            const float rad = Gm.e_rad[r];
-                            const float2 rad2 = make_float2(rad, rad);
-                            const float4 *t4 = reinterpret_cast<const float4 *>(
-                                &S.T[Gm.e_attr[r]][8 * c]);
-                            const float4 ta = t4[0], tb = t4[1];
-                            const float2 pv[4] = {make_float2(p0.x, p0.y), make_float2(p0.z, p0.w),
-                                                  make_float2(p1.x, p1.y), make_float2(p1.z, p1.w)};
-                            const float2 qv[4] = {make_float2(q0.x, q0.y), make_float2(q0.z, q0.w),
-                                                  make_float2(q1.x, q1.y), make_float2(q1.z, q1.w)};
-                            const float2 tv[4] = {make_float2(ta.x, ta.y), make_float2(ta.z, ta.w),
-                                                  make_float2(tb.x, tb.y), make_float2(tb.z, tb.w)};
 #pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                v[i] = silu2_mode<X3>(ffma2(
-                                    wr2[i], rad2, fadd2(fadd2(pv[i], qv[i]), tv[i])));
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) v[i] = make_float2(0.0f, 0.0f);
-                        }
+                        for (int i = 0; i < 4; ++i)
+                            v[i] = ffma2(wr2[i], rad2, fadd2(fadd2(pv[i], qv[i]), tv[i]));
+                        silu4_mode<X3>(v[0], v[1]);
+                        silu4_mode<X3>(v[2], v[3]);
                         uint4 hi, lo;
                         split8p<X3>(v, hi, lo);
                         *reinterpret_cast<uint4 *>(A_hi + swz(r, c)) = hi;
                         if (X3) *reinterpret_cast<uint4 *>(A_lo + swz(r, c)) = lo;
+                    };
+#pragma unroll
+                    for (int p = 0; p < DEPTH; ++p) issue(p, buf[p], radv[p], attv[p]);
+#pragma unroll
+                    for (int p = 0; p < PASSES; ++p) {
+                        finish(p, buf[p % DEPTH], radv[p % DEPTH], attv[p % DEPTH]);
+                        if (p + DEPTH < PASSES)
+                            issue(p + DEPTH, buf[p % DEPTH], radv[p % DEPTH], attv[p % DEPTH]);
                     }
                 }
                 fence_proxy_async();
                 tc_fence_before();
                 group_sync(g);
+                PHASE_MARK(1);
                 // ---- GEMM 1: t2 = s1 . W2^T ----
                 if (tid == 0) {
                     tc_fence_after();
@@ -230,6 +273,7 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                 mbar_wait(&Gm.mbar, phase);
                 phase ^= 1;
                 tc_fence_after();
+                PHASE_MARK(2);
                 // ---- epilogue 1: m = silu(t2 + b2) (+ edge residual), the
                 // attention logit, and m back into the A tile for GEMM 2 ----
                 {
@@ -255,9 +299,11 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                             float2 mv[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i)
-                                mv[i] = silu2_mode<X3>(fadd2(
+                                mv[i] = fadd2(
                                     make_float2(acc[8 * hlf + 2 * i], acc[8 * hlf + 2 * i + 1]),
-                                    bias[i]));
+                                    bias[i]);
+                            silu4_mode<X3>(mv[0], mv[1]);
+                            silu4_mode<X3>(mv[2], mv[3]);
                             if (f_eres && r < ne) {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
@@ -296,6 +342,7 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                 fence_proxy_async();
                 tc_fence_before();
                 group_sync(g);
+                PHASE_MARK(3);
                 // ---- GEMM 2 (coordinate MLP; reuses the D columns, which
                 // epilogue 1 has fully read) runs while the messages are
                 // reduced below ----
@@ -352,11 +399,13 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                     if (2 * w + 1 < a.ld_m) dst[2 * w + 1] = m1;
                 }
             }
+            PHASE_MARK(4);
             if (ne > 0 && f_coords) {
                 // ---- epilogue 2: c = [tanh](wc2 . silu(Wc1 m + bc1)) ----
                 mbar_wait(&Gm.mbar, phase);
                 phase ^= 1;
                 tc_fence_after();
+                PHASE_MARK(5);
                 float2 d2 = make_float2(0.0f, 0.0f);
 #pragma unroll 1
                 for (int q = 0; q < 4; ++q) {
@@ -366,12 +415,13 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                     for (int v4 = 0; v4 < 4; ++v4) {
                         const float4 bb = *reinterpret_cast<const float4 *>(&S.bc1[16 * q + 4 * v4]);
                         const float4 ww = *reinterpret_cast<const float4 *>(&S.wc2[16 * q + 4 * v4]);
-                        d2 = ffma2(make_float2(ww.x, ww.y),
-                                   silu2_mode<X3>(fadd2(make_float2(acc[4 * v4], acc[4 * v4 + 1]),
-                                                        make_float2(bb.x, bb.y))), d2);
-                        d2 = ffma2(make_float2(ww.z, ww.w),
-                                   silu2_mode<X3>(fadd2(make_float2(acc[4 * v4 + 2], acc[4 * v4 + 3]),
-                                                        make_float2(bb.z, bb.w))), d2);
+                        float2 s0 = fadd2(make_float2(acc[4 * v4], acc[4 * v4 + 1]),
+                                          make_float2(bb.x, bb.y));
+                        float2 s1 = fadd2(make_float2(acc[4 * v4 + 2], acc[4 * v4 + 3]),
+                                          make_float2(bb.z, bb.w));
+                        silu4_mode<X3>(s0, s1);
+                        d2 = ffma2(make_float2(ww.x, ww.y), s0, d2);
+                        d2 = ffma2(make_float2(ww.z, ww.w), s1, d2);
                     }
                 }
                 const float dot = d2.x + d2.y;
@@ -379,6 +429,7 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                 tc_fence_before();
             }
             group_sync(g);
+            PHASE_MARK(6);
             // ---- coordinate messages summed per node ----
             if (f_coords && tid < nn) {
                 const int lo = max(Gm.rp[tid], c0) - c0;
@@ -395,6 +446,7 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                 Gm.xsum[tid][2] += sz;
             }
             group_sync(g);
+            PHASE_MARK(7);
         }
         if (a.x_out != nullptr && tid < nn) {
             const int i = n0 + tid;
@@ -416,6 +468,18 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
     __syncthreads();
     if (threadIdx.x < 32) tmem_dealloc<TC_TMEM_COLS>(tmem_base);
 }
+
+#ifdef PVS_PHASE_PROF
+extern "C" int pvs_debug_phase_cycles(unsigned long long *out, int reset) {
+    cudaDeviceSynchronize();
+    if (out) cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(g_phase_cycles));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 int launch_edge_tc(const EdgeArgs &a, int n_tiles_cap, int mode, cudaStream_t st) {
     const size_t smem = sizeof(TcSmem);

@@ -87,6 +87,22 @@ __device__ __forceinline__ float2 silu2_(float2 v) {
     e = fadd2(e, make_float2(1.0f, 1.0f));
     return fmul2(v, make_float2(rcp_approx(e.x), rcp_approx(e.y)));
 }
+// Four SiLUs with 6 MUFU instead of 8: the two denominators a = 1 + e^-u and
+// b = 1 + e^-v of a lane share one reciprocal, 1/a = b * rcp(a b).  Inputs are
+// clamped at -43 (silu(-43) = -9e-18) so that a b stays finite.  Error ~3 ulp.
+__device__ __forceinline__ void silu4_(float2 &u, float2 &v) {
+    const float2 nl2e = make_float2(-1.4426950408889634f, -1.4426950408889634f);
+    const float2 one = make_float2(1.0f, 1.0f);
+    u = make_float2(fmaxf(u.x, -43.0f), fmaxf(u.y, -43.0f));
+    v = make_float2(fmaxf(v.x, -43.0f), fmaxf(v.y, -43.0f));
+    const float2 tu = fmul2(u, nl2e), tv = fmul2(v, nl2e);
+    const float2 a = fadd2(make_float2(ex2_approx(tu.x), ex2_approx(tu.y)), one);
+    const float2 b = fadd2(make_float2(ex2_approx(tv.x), ex2_approx(tv.y)), one);
+    const float2 p = fmul2(a, b);
+    const float2 r = make_float2(rcp_approx(p.x), rcp_approx(p.y));
+    u = fmul2(fmul2(u, b), r);
+    v = fmul2(fmul2(v, a), r);
+}
 __device__ __forceinline__ float2 silu2_fast_(float2 v) {
     const float2 h = fmul2(v, make_float2(0.5f, 0.5f));
     return ffma2(h, make_float2(tanh_approx(h.x), tanh_approx(h.y)), h);

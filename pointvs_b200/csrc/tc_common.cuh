@@ -148,6 +148,19 @@ template <bool X3>
 __device__ __forceinline__ float2 silu2_mode(float2 v) {
     return X3 ? silu2_(v) : silu2_fast_(v);
 }
+// in-place SiLU of two packed pairs (shared reciprocal in the fp32-class mode)
+template <bool X3>
+__device__ __forceinline__ void silu4_mode(float2 &u, float2 &v) {
+#ifdef PVS_EXP_NOSILU
+    return;
+#endif
+    if (X3) {
+        silu4_(u, v);
+    } else {
+        u = silu2_fast_(u);
+        v = silu2_fast_(v);
+    }
+}
 
 // split 4 fp32 pairs into bf16 hi (round-to-nearest) and bf16 lo = bf16(x - hi),
 // packed arithmetic: per pair 1 cvt + 2 ALU + 1 FFMA2 + 1 cvt

@@ -1,0 +1,84 @@
+"""Where a tile's time goes inside the tcgen05 edge kernel.
+
+Builds the library with -DPVS_PHASE_PROF (clock64 at the phase boundaries of
+each 4-warp group, summed in a device array) into
+pointvs_b200/_C/libpvs_b200_prof.so, runs a few scoring passes of the bench
+workload and prints the share of group-cycles per phase.  Debug tool: the
+shipped library has none of this code.
+
+    python scripts/phase_prof.py --build        # here (no GPU needed)
+    python scripts/phase_prof.py --run          # on the GPU box
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+PROF_LIB = Path(os.environ.get('PVS_PROF_LIB') or ROOT / 'pointvs_b200' / '_C' / 'libpvs_b200_prof.so')
+PHASES = ['0 rp+geometry', '1 gather+SiLU -> A', '2 GEMM1 wait',
+          '3 epilogue 1', '4 M-reduce + m_out', '5 GEMM2 wait',
+          '6 epilogue 2', '7 coord sums']
+
+
+def build():
+    sys.path.insert(0, str(ROOT))
+    from pointvs_b200 import build as b
+    flags = [f for f in b.NVCC_FLAGS if not f.startswith('--use_fast_math')]
+    cmd = ['nvcc'] + flags + ['-DPVS_PHASE_PROF', '-I', str(ROOT / 'include'),
+                              '-I', b.CSRC, '-o', str(PROF_LIB)] + b.sources()
+    subprocess.run(cmd, check=True)
+    print(PROF_LIB)
+
+
+def run(math, steps):
+    os.environ['PVS_B200_LIB'] = str(PROF_LIB)
+    sys.path.insert(0, str(ROOT))
+    import torch
+    import bench
+    import pointvs_b200 as pv
+    from pointvs_b200 import _cabi
+    from pointvs_b200.synthetic import synthetic_batch
+    torch.manual_seed(0)
+    model = pv.SartorrasEGNN(Path('/tmp/pvs_bench'), 0, 0, None, None,
+                             silent=True, **bench.MODEL_KW).cuda().eval()
+    model.set_math(math)
+    model.set_record_side_channels(False)
+    model.record_embed_coords = False
+    batches = []
+    for s_ in range(2):
+        coords, bp, feats, cptr = synthetic_batch(10_000 * s_, 128, 1000, 30)
+        batches.append(pv.PackedBatch.from_arrays(
+            coords, bp, feats, cptr, bench.EDGE_RADIUS, bench.EDGE_RADIUS,
+            device='cuda'))
+    lib = _cabi.lib()
+    lib.pvs_debug_phase_cycles.argtypes = [C.c_void_p, C.c_int]
+    with torch.no_grad():
+        for b in batches[:2]:
+            model(b)
+        lib.pvs_debug_phase_cycles(None, 1)
+        for i in range(steps):
+            model(batches[i % len(batches)])
+    out = (C.c_ulonglong * 16)()
+    lib.pvs_debug_phase_cycles(C.cast(out, C.c_void_p), 0)
+    cyc = [int(out[i]) for i in range(8)]
+    tot = sum(cyc)
+    res = {PHASES[i]: round(cyc[i] / tot, 4) for i in range(8)}
+    res['total_group_cycles_per_step'] = tot // steps
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--build', action='store_true')
+    ap.add_argument('--run', action='store_true')
+    ap.add_argument('--math', default='bf16x3')
+    ap.add_argument('--steps', type=int, default=3)
+    a = ap.parse_args()
+    if a.build:
+        build()
+    if a.run:
+        run(a.math, a.steps)
