@@ -207,6 +207,38 @@ int pvs_prune_mask(const int32_t *row_ptr, const int32_t *col,
                    int32_t n_complexes, int32_t n_nodes, uint8_t *keep,
                    void *stream);
 
+/* ---- K0: receptor crop + atom typing in front of K1 (row N2) ---------------
+ * Replaces: make_box(relative_to_ligand=True) + the hydrogen filter + atom
+ *           typing + make_bit_vector of PointCloudDataset.parquets_to_inputs
+ *           (preprocessing/data_loaders.py:259-309, preprocessing.py:165-239)
+ *           for a batch of poses whose receptors are resident on the device.
+ * lig_xyz fp64 [L][3], lig_emit u8 [L] (0 = atom only takes part in the box
+ * test, e.g. a filtered hydrogen), lig_ptr int32 [B+1]; rec_xyz / rec_emit
+ * likewise for the concatenated receptors, rec_ptr int32 [R+1], rec_of_pose
+ * int32 [B] (NULL = receptor 0 for every pose).  mask: B * mask_words uint32
+ * keep-bits, mask_words >= ceil(largest receptor / 32).  counts[b] = atoms of
+ * complex b (emitted ligand atoms + kept receptor atoms); the caller scans
+ * them into complex_ptr (pvs_exclusive_scan) and calls pvs_crop_fill, which
+ * writes each complex as [ligand atoms; kept receptor atoms] in file order:
+ * coords fp64 [N][3], bp int32 [N] (0/1), feats fp32 [N][F] with F =
+ * n_atom_types + 1 (compact) or 2 * n_atom_types.  *_code int16: the atom
+ * `types` value the reference would one-hot (receptor codes already shifted
+ * by n_atom_types). */
+int pvs_crop_count(const double *lig_xyz, const uint8_t *lig_emit,
+                   const int32_t *lig_ptr, int32_t n_poses,
+                   const double *rec_xyz, const uint8_t *rec_emit,
+                   const int32_t *rec_ptr, const int32_t *rec_of_pose,
+                   int32_t mask_words, double radius, uint32_t *mask,
+                   int32_t *counts, void *stream);
+int pvs_crop_fill(const double *lig_xyz, const uint8_t *lig_emit,
+                  const int16_t *lig_code, const int32_t *lig_ptr,
+                  int32_t n_poses, const double *rec_xyz,
+                  const int16_t *rec_code, const int32_t *rec_ptr,
+                  const int32_t *rec_of_pose, const uint32_t *mask,
+                  int32_t mask_words, const int32_t *complex_ptr,
+                  int32_t n_atom_types, int32_t compact, double *coords,
+                  int32_t *bp, float *feats, void *stream);
+
 int64_t pvs_scan_scratch_bytes(int32_t n);
 /* row_ptr[0..n] = exclusive scan of deg[0..n-1] */
 int pvs_exclusive_scan(const int32_t *deg, int32_t n, int32_t *row_ptr,

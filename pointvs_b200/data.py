@@ -193,6 +193,35 @@ def uniform_random_rotation(x, rng):
     return ((x - mean) @ m) + mean @ m
 
 
+class Ligand:
+    """Host-side half of a complex for the device crop: every ligand atom
+    (hydrogens included: they take part in the box test), which of them are
+    emitted, and the type code of each."""
+    __slots__ = ('coords', 'emit', 'code')
+
+    def __init__(self, coords, emit, code):
+        self.coords, self.emit, self.code = coords, emit, code
+
+    def __len__(self):
+        return len(self.emit)
+
+
+def atom_codes(cols, n_features, is_receptor, polar_hydrogens,
+               use_atomic_numbers, atomic_number_to_index):
+    """(emit u8, code i16) per atom of one parquet: what parquets_to_inputs
+    (data_loaders.py:285-292) does to `types` after the box."""
+    anum = cols['atomic_number']
+    emit = np.ones(len(anum), dtype=np.uint8) if polar_hydrogens \
+        else (anum > 1).astype(np.uint8)
+    if use_atomic_numbers:
+        code = np.array([atomic_number_to_index.get(int(a), n_features)
+                         for a in anum], dtype=np.int64).reshape(len(anum))
+        code = code + (n_features if is_receptor else 0)
+    else:
+        code = cols['types'] + (n_features if is_receptor else 0)
+    return emit, code.astype(np.int16)
+
+
 class Complex:
     """One preprocessed complex on the host."""
     __slots__ = ('coords', 'bp', 'feats', 'types', 'atomic_number')
@@ -253,7 +282,7 @@ class ComplexDataset:
                  edge_radius=None, estimate_bonds=False, prune=False, bp=None,
                  p_remove_entity=0, extended_atom_types=False, p_noise=-1,
                  include_strain_info=False, device=None, seed=None,
-                 receptor_cache=8, **kwargs):
+                 receptor_cache=8, device_crop=False, **kwargs):
         del augmented_active_min_angle, fname_suffix, kwargs
         if (max_active_rms_distance is None) != (
                 min_inactive_rms_distance is None):
@@ -279,6 +308,10 @@ class ComplexDataset:
         self.use_atomic_numbers, self.compact = use_atomic_numbers, compact
         self.model_task, self.rot = model_task, rot
         self.device = device
+        # device_crop: receptors stay resident in HBM and the box / hydrogen
+        # filter / typing / one-hot of every pose run on the GPU (K0)
+        self.device_crop = bool(device_crop)
+        self._rec_dev = OrderedDict()
         self.use_types = True
         self._rng = np.random.default_rng(seed)
         self._cache = OrderedDict()
@@ -392,9 +425,143 @@ class ComplexDataset:
             self.n_features, self.radius, self.polar_hydrogens,
             self.use_atomic_numbers, self.compact, self.atomic_number_to_index)
 
+    # -- device crop (K0) -----------------------------------------------------
+    def load_ligand(self, item):
+        """Host-side half of the device-crop path: the ligand parquet only."""
+        lig_path = self.base_path / self.ligand_fnames[item]
+        if not lig_path.is_file():
+            raise FileNotFoundError(lig_path, 'does not exist.')
+        cols = read_structure(lig_path)
+        if cols['bp'].any():
+            raise ValueError(f'{lig_path}: ligand file with bp != 0 rows; use '
+                             'device_crop=False')
+        emit, code = atom_codes(cols, self.n_features, False,
+                                self.polar_hydrogens, self.use_atomic_numbers,
+                                self.atomic_number_to_index)
+        xyz = np.stack([cols['x'], cols['y'], cols['z']], axis=1)
+        return Ligand(np.ascontiguousarray(xyz), emit, code)
+
+    def receptor_on_device(self, rec_fname, device):
+        """(xyz f64 [n,3], emit u8 [n], code i16 [n]) resident on `device`."""
+        key = (str(rec_fname), str(device))
+        with self._cache_lock:
+            hit = self._rec_dev.get(key)
+            if hit is not None:
+                self._rec_dev.move_to_end(key)
+                return hit
+        rec_path = self.base_path / rec_fname
+        if not rec_path.is_file():
+            raise FileNotFoundError(rec_path, 'does not exist')
+        cols = self._receptor(rec_path)
+        if not cols['bp'].all():
+            raise ValueError(f'{rec_path}: receptor file with bp != 1 rows; '
+                             'use device_crop=False')
+        emit, code = atom_codes(cols, self.n_features, True,
+                                self.polar_hydrogens, self.use_atomic_numbers,
+                                self.atomic_number_to_index)
+        xyz = np.stack([cols['x'], cols['y'], cols['z']], axis=1)
+        entry = (torch.from_numpy(np.ascontiguousarray(xyz)).to(device),
+                 torch.from_numpy(emit).to(device),
+                 torch.from_numpy(code).to(device))
+        with self._cache_lock:
+            self._rec_dev[key] = entry
+            while len(self._rec_dev) > max(1, self._cache_size):
+                self._rec_dev.popitem(last=False)
+        return entry
+
+    def _check_codes(self, code):
+        if not self.compact and len(code) and (
+                code.min() < 0 or code.max() >= 2 * self.n_features):
+            raise ValueError('atom type outside the one-hot range')
+
+    def crop_on_device(self, items, ligands=None):
+        """K0 for the complexes `items`: -> (coords f64 [N,3], bp i32 [N],
+        feats f32 [N,F]) on the device and the host complex_ptr [B+1].  One
+        host read-back (the B+1 offsets) sizes the outputs."""
+        import ctypes as C   # noqa: PLC0415
+        from . import _cabi   # noqa: PLC0415
+        from ._cabi import check, lib, ptr, stream   # noqa: PLC0415
+        device = torch.device(self.device or 'cuda')
+        if ligands is None:
+            ligands = [self.load_ligand(i) for i in items]
+        n_poses = len(items)
+        if n_poses == 0:
+            return (torch.zeros((0, 3), dtype=torch.float64, device=device),
+                    torch.zeros(0, dtype=torch.int32, device=device),
+                    torch.zeros((0, self.feature_dim), device=device),
+                    np.zeros(1, dtype=np.int32))
+        # receptors of this batch, each uploaded once and kept
+        rec_names, rec_index = [], {}
+        rec_of_pose = np.zeros(n_poses, dtype=np.int32)
+        for b, i in enumerate(items):
+            name = str(self.receptor_fnames[i])
+            if name not in rec_index:
+                rec_index[name] = len(rec_names)
+                rec_names.append(name)
+            rec_of_pose[b] = rec_index[name]
+        recs = [self.receptor_on_device(name, device) for name in rec_names]
+        rec_sizes = [int(r[0].shape[0]) for r in recs]
+        rec_ptr = np.zeros(len(recs) + 1, dtype=np.int32)
+        np.cumsum(rec_sizes, out=rec_ptr[1:])
+        if len(recs) == 1:
+            rec_xyz, rec_emit, rec_code = recs[0]
+        else:
+            rec_xyz = torch.cat([r[0] for r in recs])
+            rec_emit = torch.cat([r[1] for r in recs])
+            rec_code = torch.cat([r[2] for r in recs])
+        lig_ptr = np.zeros(n_poses + 1, dtype=np.int32)
+        np.cumsum([len(l) for l in ligands], out=lig_ptr[1:])
+        lig_code_h = np.concatenate([l.code for l in ligands])
+        self._check_codes(lig_code_h)
+        lig_xyz = torch.from_numpy(
+            np.concatenate([l.coords for l in ligands])).to(device)
+        lig_emit = torch.from_numpy(
+            np.concatenate([l.emit for l in ligands])).to(device)
+        lig_code = torch.from_numpy(lig_code_h).to(device)
+        lig_ptr_d = torch.from_numpy(lig_ptr).to(device)
+        rec_ptr_d = torch.from_numpy(rec_ptr).to(device)
+        rec_of_pose_d = torch.from_numpy(rec_of_pose).to(device)
+        words = (max(rec_sizes) + 31) // 32 if rec_sizes else 0
+        words = max(words, 1)
+        h = lib()
+        mask = _cabi.scratch('k0_mask', n_poses * words * 4, device)
+        counts = torch.empty(n_poses, dtype=torch.int32, device=device)
+        cptr = torch.empty(n_poses + 1, dtype=torch.int32, device=device)
+        scan_ws = _cabi.scratch(
+            'k0_scan', int(h.pvs_scan_scratch_bytes(n_poses)) + 256, device)
+        with torch.cuda.device(device):
+            check(h.pvs_crop_count(
+                ptr(lig_xyz), ptr(lig_emit), ptr(lig_ptr_d), n_poses,
+                ptr(rec_xyz), ptr(rec_emit), ptr(rec_ptr_d),
+                ptr(rec_of_pose_d), words, C.c_double(float(self.radius)),
+                ptr(mask), ptr(counts), stream()), 'pvs_crop_count')
+            check(h.pvs_exclusive_scan(ptr(counts), n_poses, ptr(cptr),
+                                       ptr(scan_ws), stream()),
+                  'pvs_exclusive_scan')
+            cptr_host = cptr.cpu().numpy()          # the one host sync
+            n = int(cptr_host[-1])
+            coords = torch.empty((max(n, 1), 3), dtype=torch.float64,
+                                 device=device)
+            bp = torch.empty(max(n, 1), dtype=torch.int32, device=device)
+            feats = torch.empty((max(n, 1), self.feature_dim),
+                                dtype=torch.float32, device=device)
+            check(h.pvs_crop_fill(
+                ptr(lig_xyz), ptr(lig_emit), ptr(lig_code), ptr(lig_ptr_d),
+                n_poses, ptr(rec_xyz), ptr(rec_code), ptr(rec_ptr_d),
+                ptr(rec_of_pose_d), ptr(mask), words, ptr(cptr),
+                self.n_features, int(bool(self.compact)), ptr(coords), ptr(bp),
+                ptr(feats), stream()), 'pvs_crop_fill')
+        return coords[:n], bp[:n], feats[:n], cptr_host
+
+    def prepare(self, item):
+        """What a loader thread does ahead of the device for one complex."""
+        return self.load_ligand(item) if self.device_crop else self.load(item)
+
     def pack(self, items, complexes=None, edge_capacity=None):
         """Complexes `items` -> one PackedBatch with the batch's radius graph
         built on the device."""
+        if self.device_crop:
+            return self._pack_device(items, complexes, edge_capacity)
         if complexes is None:
             complexes = [self.load(i) for i in items]
         sizes = [len(c) for c in complexes]
@@ -408,15 +575,7 @@ class ComplexDataset:
             coords = np.zeros((0, 3))
             bp = np.zeros(0, dtype=np.int32)
             feats = np.zeros((0, self.feature_dim), dtype=np.float32)
-        labels = [self.label(i) for i in items]
-        if not labels or labels[0] is None or (
-                isinstance(labels[0], tuple) and labels[0][0] is None):
-            y = None
-        elif self.model_task == 'classification':
-            y = torch.tensor([int(v) for v in labels], dtype=torch.long)
-        else:   # PyG concatenates the per-complex label vectors
-            y = torch.tensor(np.array(labels, dtype=np.float64).reshape(-1),
-                             dtype=torch.float32)
+        y = self._labels(items)   # PyG concatenates per-complex label vectors
         batch = PackedBatch.from_arrays(
             coords, bp, feats, cptr, inter_radius=self.inter_radius,
             intra_radius=self.intra_radius, y=y, device=self.device,
@@ -434,6 +593,36 @@ class ComplexDataset:
             batch.pos = torch.as_tensor(pos, dtype=torch.float32).to(
                 batch.x.device)
         return batch
+
+    def _labels(self, items):
+        labels = [self.label(i) for i in items]
+        if not labels or labels[0] is None or (
+                isinstance(labels[0], tuple) and labels[0][0] is None):
+            return None
+        if self.model_task == 'classification':
+            return torch.tensor([int(v) for v in labels], dtype=torch.long)
+        return torch.tensor(np.array(labels, dtype=np.float64).reshape(-1),
+                            dtype=torch.float32)
+
+    def _pack_device(self, items, ligands, edge_capacity):
+        from .graph import radius_graph_batch   # noqa: PLC0415
+        coords, bp, feats, cptr_host = self.crop_on_device(items, ligands)
+        csr = radius_graph_batch(coords, bp, cptr_host, self.inter_radius,
+                                 self.intra_radius, device=coords.device,
+                                 edge_capacity=edge_capacity)
+        pos = coords.float()
+        if self.rot:
+            pos_h = coords.cpu().numpy().copy()
+            for b in range(len(items)):
+                s_, e_ = cptr_host[b], cptr_host[b + 1]
+                if e_ > s_:
+                    pos_h[s_:e_] = uniform_random_rotation(pos_h[s_:e_],
+                                                           self._rng)
+            pos = torch.as_tensor(pos_h, dtype=torch.float32).to(coords.device)
+        return PackedBatch(
+            feats, pos, csr, csr.complex_ptr, y=self._labels(items),
+            lig_fname=[Path(self.ligand_fnames[i]) for i in items],
+            rec_fname=[Path(self.receptor_fnames[i]) for i in items])
 
     def __getitem__(self, item):
         return self.pack([item])
@@ -473,7 +662,7 @@ class PackedLoader:
                 while nxt < len(batches) and len(pending) < self.prefetch:
                     items = batches[nxt]
                     pending.append(
-                        (items, [pool.submit(ds.load, i) for i in items]))
+                        (items, [pool.submit(ds.prepare, i) for i in items]))
                     nxt += 1
                 items, futures = pending.popleft()
                 yield ds.pack(items, [f.result() for f in futures],
@@ -488,7 +677,7 @@ def get_data_loader(data_root, dataset_class=None, receptors=None,
                     fname_suffix='parquet', min_inactive_rms_distance=None,
                     types_fname=None, edge_radius=None, prune=False,
                     estimate_bonds=False, bp=None, p_noise=-1, num_workers=4,
-                    device=None, **kwargs):
+                    device=None, device_crop=False, **kwargs):
     """Signature of the reference's `get_data_loader` (data_loaders.py:483-520).
     `dataset_class` is accepted for call compatibility and ignored: there is
     one dataset here.  As in the reference, classification training draws
@@ -505,7 +694,7 @@ def get_data_loader(data_root, dataset_class=None, receptors=None,
         types_fname=types_fname, edge_radius=edge_radius,
         estimate_bonds=estimate_bonds, prune=prune, bp=bp, radius=radius,
         rot=rot, model_task=model_task, p_noise=p_noise, device=device,
-        **kwargs)
+        device_crop=device_crop, **kwargs)
     sampler = ds.sampler if (ds.model_task == 'classification'
                              and mode == 'train') else None
     return PackedLoader(ds, batch_size, sampler=sampler,
@@ -515,4 +704,4 @@ def get_data_loader(data_root, dataset_class=None, receptors=None,
 __all__ = ['ComplexDataset', 'PackedLoader', 'get_data_loader',
            'parse_classification_types', 'parse_regression_types',
            'read_structure', 'build_complex', 'make_box', 'make_bit_vector',
-           'atomic_number_table', 'Complex']
+           'atomic_number_table', 'atom_codes', 'Complex', 'Ligand']

@@ -38,7 +38,7 @@ def _packed_loader_factory():
 
 def get_model_and_test_dl(checkpoint_path, test_types, test_data_root,
                           model_task=None, loader_factory=None,
-                          batch_size=None):
+                          batch_size=None, device_crop=False):
     """Same contract as inference.py:35-74 of the reference."""
     checkpoint_path, model, model_kwargs, cmd_line_args = load_model(
         checkpoint_path, silent=False, model_task=model_task)
@@ -67,7 +67,8 @@ def get_model_and_test_dl(checkpoint_path, test_types, test_data_root,
         prune=cmd_line_args.get('prune', False), rot=False, mode='val',
         fname_suffix=cmd_line_args.get('input_suffix', 'parquet'),
         extended_atom_types=cmd_line_args.get('extended_atom_types', False),
-        model_task=model_task_)
+        model_task=model_task_, **({'device_crop': True} if device_crop
+                                   else {}))
     return checkpoint_path, model, model_kwargs, cmd_line_args, test_dl
 
 
@@ -83,6 +84,9 @@ def main(argv=None):
                         help='arithmetic of the per-edge contractions')
     parser.add_argument('--reference_loader', action='store_true',
                         help="use PointVS's own PyG data loader")
+    parser.add_argument('--host_crop', action='store_true',
+                        help='crop / type the complexes on the host instead '
+                             'of on the device (K0)')
     parser.add_argument('--batch_size', type=int, default=None,
                         help='complexes per packed batch (default: the '
                              'value the model was trained with)')
@@ -91,7 +95,8 @@ def main(argv=None):
         Path(args.model_checkpoint).expanduser(), args.test_types,
         args.test_data_root, args.model_task,
         loader_factory=_reference_loader_factory()
-        if args.reference_loader else None, batch_size=args.batch_size)
+        if args.reference_loader else None, batch_size=args.batch_size,
+        device_crop=not (args.host_crop or args.reference_loader))
     if args.model_task is not None:
         model.set_task({'pose': 'classification',
                         'affinity': 'regression'}[args.model_task])

@@ -32,6 +32,7 @@ def main():
     ap.add_argument('--workers', type=int, default=8)
     ap.add_argument('--math', default='bf16x3')
     ap.add_argument('--cpu-sample', type=int, default=14)
+    ap.add_argument('--host-crop', action='store_true')
     args = ap.parse_args()
     lines = [ln for ln in (COMPLEXES / 'pose.types').read_text().splitlines()
              if ln.strip()]
@@ -43,7 +44,7 @@ def main():
         dl = data.get_data_loader(
             COMPLEXES, types_fname=types, batch_size=args.batch_size,
             mode='val', rot=False, num_workers=args.workers, device='cuda',
-            **cfg)
+            device_crop=not args.host_crop, **cfg)
         ds = dl.dataset
         torch.manual_seed(0)
         model = SartorrasEGNN(
@@ -75,7 +76,7 @@ def main():
         t0 = time.perf_counter()
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max(1, args.workers)) as pool:
-            list(pool.map(ds.load, range(len(ds))))
+            list(pool.map(ds.prepare, range(len(ds))))
         host = time.perf_counter() - t0
 
         # CPU oracle generate_edges on a bounded sample
@@ -91,7 +92,7 @@ def main():
         'value': round(args.n / wall, 1), 'unit': 'complexes/s',
         'n_complexes': args.n, 'atoms_per_complex': round(atoms / args.n, 1),
         'batch_size': args.batch_size, 'loader_threads': args.workers,
-        'math': args.math,
+        'math': args.math, 'crop': 'host' if args.host_crop else 'device',
         'host_loader_only_complexes_per_s': round(args.n / host, 1),
         'cpu_oracle_load_plus_generate_edges_ms_per_complex':
             round(cpu_edges * 1e3, 2),

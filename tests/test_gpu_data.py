@@ -37,11 +37,16 @@ def _reference_batch(gold, cfg, items):
 
 
 @pytest.mark.parametrize('cfg', sorted(CONFIGS))
-@pytest.mark.parametrize('workers', [0, 3])
-def test_packed_loader_graph_is_the_reference_graph(cfg, workers, gold):
+@pytest.mark.parametrize('workers,device_crop', [(0, False), (3, False),
+                                                 (0, True), (3, True)])
+def test_packed_loader_graph_is_the_reference_graph(cfg, workers, device_crop,
+                                                    gold):
+    """Host crop (numpy) and device crop (K0) both reproduce the reference
+    loader's nodes, features and edges bit for bit."""
     from pointvs_b200 import data
     ds = data.ComplexDataset(ROOT, types_fname=ROOT / 'pose.types', rot=False,
-                             device='cuda', **CONFIGS[cfg])
+                             device='cuda', device_crop=device_crop,
+                             **CONFIGS[cfg])
     n = len(ds)
     seen = 0
     for batch in data.PackedLoader(ds, batch_size=4, num_workers=workers):
@@ -154,3 +159,47 @@ def test_regression_batches_and_rotation(gold):
     d_got = np.linalg.norm(got[first][:, None] - got[first][None], axis=-1)
     np.testing.assert_allclose(d_ref, d_got, atol=2e-4)
     assert b0.edge_index.shape[1] == len(row)
+
+
+def test_device_crop_equals_host_crop_arrays():
+    """K0 output (coords fp64, bp, features, offsets) against build_complex on
+    the host, two receptors interleaved in one batch, small and large radii."""
+    from pointvs_b200 import data
+    for cfg, radius in (('smina_r10_e4', 10), ('atomic_h_r6_e3', 2.5),
+                        ('atomic_h_r6_e3', 60.0), ('smina_wide_r7_bonds', 7)):
+        kw = dict(CONFIGS[cfg], radius=radius)
+        ds = data.ComplexDataset(ROOT, types_fname=ROOT / 'pose.types',
+                                 rot=False, device='cuda', device_crop=True,
+                                 **kw)
+        items = [0, 1, 2, 4, 6, 3, 5]
+        coords, bp, feats, cptr = ds.crop_on_device(items)
+        host = [ds.load(i) for i in items]
+        sizes = [len(c) for c in host]
+        np.testing.assert_array_equal(np.diff(cptr), sizes)
+        np.testing.assert_array_equal(
+            coords.cpu().numpy(), np.concatenate([c.coords for c in host]))
+        np.testing.assert_array_equal(
+            bp.cpu().numpy(), np.concatenate([c.bp for c in host]))
+        np.testing.assert_array_equal(
+            feats.cpu().numpy(), np.concatenate([c.feats for c in host]))
+
+
+def test_device_crop_long_ligand_and_empty_batch():
+    """A 'ligand' longer than the shared-memory staging chunk (the receptor
+    file used as the ligand), and an empty batch."""
+    from pointvs_b200 import data
+    ds = data.ComplexDataset(ROOT, types_fname=ROOT / 'pose.types', rot=False,
+                             device='cuda', device_crop=True,
+                             **CONFIGS['smina_r10_e4'])
+    coords, bp, feats, cptr = ds.crop_on_device([])
+    assert coords.shape[0] == 0 and list(cptr) == [0]
+    rec = data.read_structure(ROOT / 'rec_0.parquet')
+    big = {k: v[:700].copy() for k, v in rec.items()}
+    big['bp'][:] = 0
+    emit, code = data.atom_codes(big, ds.n_features, False, False, False, None)
+    lig = data.Ligand(np.stack([big['x'], big['y'], big['z']], 1), emit, code)
+    coords, bp, feats, cptr = ds.crop_on_device([6], [lig])
+    want = data.build_complex(rec, big, ds.n_features, ds.radius)
+    np.testing.assert_array_equal(coords.cpu().numpy(), want.coords)
+    np.testing.assert_array_equal(bp.cpu().numpy(), want.bp)
+    np.testing.assert_array_equal(feats.cpu().numpy(), want.feats)
