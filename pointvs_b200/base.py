@@ -130,17 +130,34 @@ class PointNeuralNetworkBase(nn.Module):
     def sync_gradients(self):
         """Hook for data-parallel training (pointvs_b200.parallel)."""
 
-    def backprop(self, y_true, y_pred):
+    def backprop(self, y_true, y_pred, sync=True):
+        """loss -> backward -> (all-reduce) -> clip -> optimiser step
+        (point_neural_network_base.py:417-429).  sync=True returns the loss as
+        a float and raises on NaN at once, as the reference does; sync=False
+        returns the loss as a device tensor and leaves the NaN check to the
+        caller, so the host can run ahead of the device (N1)."""
         loss = self.get_loss(y_true, y_pred)
         self.optimiser.zero_grad()
         loss.backward()
         self.sync_gradients()
         torch.nn.utils.clip_grad_value_(self.parameters(), 1.0)
         self.optimiser.step()
+        if not sync:
+            return loss.detach()
         loss_ = float(loss.detach())
         if math.isnan(loss_):
             raise FloatingPointError('We have hit a NaN loss value.')
         return loss_
+
+    @staticmethod
+    def _drain_losses(pending, losses):
+        """One device->host transfer for the losses of the last few steps."""
+        if pending:
+            vals = torch.stack(pending).cpu().tolist()
+            pending.clear()
+            if any(math.isnan(v) for v in vals):
+                raise FloatingPointError('We have hit a NaN loss value.')
+            losses.extend(vals)
 
     def training_setup(self, data_loader, epochs, model_task=None):
         if self.use_1cycle:
@@ -160,15 +177,20 @@ class PointNeuralNetworkBase(nn.Module):
     def train_model(self, data_loader, epochs=1, epoch_end_validation_set=None,
                     top1_on_end=False):
         init_epoch, _ = self.training_setup(data_loader, epochs)
-        losses = []
+        losses, pending = [], []
         for _ in range(init_epoch, epochs):
             self.train()
             for self.batch, graph in enumerate(data_loader):
                 y_pred, y_true, _, _ = self.unpack_input_data_and_predict(graph)
-                losses.append(self.backprop(y_true, y_pred))
+                pending.append(self.backprop(y_true, y_pred, sync=False))
+                # losses (and the NaN check) come back once per log interval,
+                # not once per step
+                if len(pending) >= self.log_interval:
+                    self._drain_losses(pending, losses)
                 if self.scheduler is not None:
                     self.scheduler.step()
                 self.global_iter += 1
+            self._drain_losses(pending, losses)
             self.eval()
             self.on_epoch_end(epoch_end_validation_set, epochs, top1_on_end)
         return losses

@@ -60,7 +60,7 @@ def main():
                                            y=y, device=dev)
         batch.lig_fname = batch.rec_fname = [''] * args.batch
         y_pred, y_true, _, _ = model.unpack_input_data_and_predict(batch)
-        return model.backprop(y_true, y_pred)
+        return model.backprop(y_true, y_pred, sync=False)
 
     losses = [step(i) for i in range(args.warmup)]
     if world > 1:
@@ -88,8 +88,8 @@ def main():
             'value': args.batch * world * args.steps / (float(ms) * 1e-3),
             'unit': 'complexes/s', 'n_gpus': world, 'steps': args.steps,
             'ms_per_step': float(ms) / args.steps, 'math': args.math,
-            'batch_per_gpu': args.batch, 'first_loss': losses[0],
-            'last_loss': losses[-1], 'replicas_identical': same,
+            'batch_per_gpu': args.batch, 'first_loss': float(losses[0]),
+            'last_loss': float(losses[-1]), 'replicas_identical': same,
             'allreduce_floats': sum(p.numel() for p in model.parameters())}),
             flush=True)
     assert same, 'replicas diverged'

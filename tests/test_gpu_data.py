@@ -203,3 +203,58 @@ def test_device_crop_long_ligand_and_empty_batch():
     np.testing.assert_array_equal(coords.cpu().numpy(), want.coords)
     np.testing.assert_array_equal(bp.cpu().numpy(), want.bp)
     np.testing.assert_array_equal(feats.cpu().numpy(), want.feats)
+
+
+def test_training_on_packed_loader_matches_oracle_autograd(tmp_path, gold):
+    """train_model over the packed loader (device crop -> K1 -> K2 -> K3 ->
+    clip -> Adam) against the same three steps done on the CPU with the oracle
+    forward, torch autograd and torch Adam on the reference loader's graphs."""
+    import pointvs_b200 as pv
+    from oracle import egnn_oracle
+    from pointvs_b200 import data
+    cfg = 'smina_r10_e4'
+    kw = dict(dim_input=int(gold[f'{cfg}/feature_dim']), dim_output=1, k=32,
+              num_layers=3, graphnorm=False, edge_attention=True,
+              node_attention=True, residual=True, normalize=True, tanh=True)
+    torch.manual_seed(3)
+    model = pv.SartorrasEGNN(tmp_path, 2e-3, 1e-4, None, None, silent=True,
+                             **kw).cuda()
+    with torch.no_grad():          # make the coordinate path count
+        for n, p in model.named_parameters():
+            if n.endswith('coord_mlp.2.weight'):
+                p.mul_(300.0)
+    sd = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point())
+          for k, v in model.state_dict().items()}
+    params = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.Adam(params, lr=2e-3, weight_decay=1e-4)
+    n = int(gold[f'{cfg}/n'])
+    want = []
+    for start in range(0, n, 3):
+        items = list(range(start, min(n, start + 3)))
+        x, pos, row, col, attr, batch = _reference_batch(gold, cfg, items)
+        out, _ = egnn_oracle.model_forward(
+            sd, torch.from_numpy(x), torch.from_numpy(np.stack([row, col])),
+            torch.from_numpy(pos),
+            torch.nn.functional.one_hot(
+                torch.from_numpy(attr.astype(np.int64)), 3),
+            torch.from_numpy(batch), num_layers=3, multitask=False,
+            model_task='classification', **helpers.oracle_kwargs(kw))
+        y = torch.tensor([float(gold[f'{cfg}/{i}/y']) for i in items])
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(
+            out.reshape(-1), y)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_value_(params, 1.0)
+        opt.step()
+        want.append(float(loss))
+    dl = data.get_data_loader(
+        ROOT, types_fname=ROOT / 'pose.types', batch_size=3, mode='val',
+        rot=False, device='cuda', device_crop=True, **CONFIGS[cfg])
+    model.only_save_best_models = True
+    got = model.train_model(dl, epochs=1)
+    assert len(got) == len(want) == 3
+    np.testing.assert_allclose(got, want, rtol=2e-4)
+    for k, v in model.state_dict().items():
+        if v.is_floating_point():
+            ref = sd[k].detach()
+            assert helpers.scaled_err(v.cpu().numpy(), ref.numpy()) < 5e-3, k
