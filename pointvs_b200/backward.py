@@ -25,6 +25,7 @@ def egnn_layer_backward(ctx, d_h, d_x, d_m):
     n, e, k = csr.n_nodes, csr.n_edges, layer.hidden_nf
     dev = h.device
     d_h = torch.zeros_like(h) if d_h is None else d_h.contiguous().float()
+    no_dx = d_x is None
     d_x = None if d_x is None else d_x.contiguous().float()
     d_m = None if d_m is None else d_m.contiguous().float()
     csc_ptr, csc_eid = csr.csc()
@@ -60,9 +61,20 @@ def egnn_layer_backward(ctx, d_h, d_x, d_m):
             'pvs_egnn_layer_bwd')
     # inputs of _EGNNLayerFn.forward: layer, csr, want_m, want_side, h, x,
     # m_prev, *params
+    # Parameters that cannot influence the loss get no gradient at all (None),
+    # as under the reference's autograd: an optimiser with weight decay skips
+    # them instead of decaying them.  That is the coordinate MLP of a layer
+    # whose output coordinates nobody consumes (the last layer), or which does
+    # not update coordinates.
+    unused = set()
+    if no_dx or not layer.use_coords:
+        unused.update(('coord_w1', 'coord_b1', 'coord_w2'))
+    if m_prev is None:          # first layer: no incoming messages to gate
+        unused.add('edge_gate')
     param_grads = []
     for name, p in zip(_cabi.PARAM_FIELDS, params):
-        if p is None or name not in grads or grads[name] is None:
+        if p is None or name not in grads or grads[name] is None \
+                or name in unused:
             param_grads.append(None)
         else:
             param_grads.append(grads[name].reshape(p.shape))

@@ -80,6 +80,10 @@ class _EGNNLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, layer, csr, want_m, want_side, h, x, m_prev, *params):
+        # outputs nobody consumes (the last layer's coordinates) reach
+        # backward as None, so their parameters get no gradient -- as under
+        # the reference's autograd
+        ctx.set_materialize_grads(False)
         cfg = layer.c_config()
         n, e, k = csr.n_nodes, csr.n_edges, layer.hidden_nf
         dev = h.device

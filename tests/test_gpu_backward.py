@@ -121,6 +121,10 @@ def test_grads_vs_oracle_autograd(vname):
     for pname, p in model.named_parameters():
         ref = sd[pname].grad
         if ref is None:
+            # parameters autograd leaves untouched (e.g. the last layer's
+            # coordinate MLP) must stay untouched here too: Adam with weight
+            # decay would otherwise move them
+            assert p.grad is None, pname
             continue
         assert p.grad is not None, pname
         _close(p.grad.cpu().numpy(), ref.numpy(), pname)
