@@ -148,28 +148,24 @@ def screen(model, complexes, batch_size=128, inter_radius=4.0,
     """Score a list of complexes [(coords f64 [N,3], bp [N], feats [N,F]), ...]
     sharded by complex across the ranks of `group`.  Returns the dense score
     array (same on every rank)."""
-    from .graph import PackedBatch
+    from .pipeline import ScoreStream
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     sizes = [len(c[0]) for c in complexes]
     mine = shard_by_size(sizes, world)[rank]
-    device = next(model.parameters()).device
-    scores = []
     model.eval()
-    with torch.no_grad():
-        for lo in range(0, len(mine), batch_size):
-            idx = mine[lo:lo + batch_size]
-            coords = np.concatenate([complexes[i][0] for i in idx])
-            bp = np.concatenate([complexes[i][1] for i in idx])
-            feats = np.concatenate([complexes[i][2] for i in idx])
-            cptr = np.concatenate([[0], np.cumsum([sizes[i] for i in idx])])
-            batch = PackedBatch.from_arrays(coords, bp, feats, cptr,
-                                            inter_radius, intra_radius,
-                                            device=device)
-            out = model(batch).reshape(len(idx), -1)
-            if activation == 'sigmoid':
-                out = torch.sigmoid(out)
-            scores.append(out)
-    local = torch.cat(scores).cpu().numpy() if scores else \
+    # exact edge lists (one 4-byte read-back per batch): callers' complexes
+    # may be denser than the capacity heuristic assumes
+    stream = ScoreStream(model, inter_radius, intra_radius, depth=3,
+                         edge_capacity=None, activation=activation)
+    for lo in range(0, len(mine), batch_size):
+        idx = mine[lo:lo + batch_size]
+        coords = np.concatenate([complexes[i][0] for i in idx])
+        bp = np.concatenate([complexes[i][1] for i in idx])
+        feats = np.concatenate([complexes[i][2] for i in idx])
+        cptr = np.concatenate([[0], np.cumsum([sizes[i] for i in idx])])
+        stream.submit(coords, bp, feats, cptr)
+    scores = [sc for _, sc in stream.drain()]
+    local = np.concatenate(scores) if scores else \
         np.zeros((0, 1), dtype=np.float32)
     return gather_scores(mine, local, len(complexes), group)
