@@ -180,8 +180,9 @@ int64_t pvs_launch_count(void);
  *          the reference's (PyG-collated) edge order.  edge_capacity = size of
  *          col/attr in edges: a caller that wants NO host sync between the
  *          passes allocates an upper bound instead of reading row_ptr[N];
- *          edges beyond the capacity are dropped and *overflow (device int,
- *          may be NULL) is set non-zero.
+ *          edges beyond the capacity are dropped, *overflow (device int,
+ *          may be NULL) is set non-zero and row_ptr is cut at the capacity
+ *          so that no consumer of the CSR indexes past col/attr.
  * coords: fp64 [N][3]; bp: int32 [N] (0 ligand, 1 receptor; :106);
  * complex_ptr: int32 [B+1] node offsets.  scratch: pvs_scan_scratch_bytes(N). */
 int64_t pvs_radius_graph_mask_bytes(int32_t n_nodes, int32_t max_complex_nodes);
@@ -195,7 +196,7 @@ int pvs_radius_graph_fill(const double *coords, const int32_t *bp,
                           const int32_t *complex_ptr, int32_t n_complexes,
                           int32_t n_nodes, int32_t max_complex_nodes,
                           double inter_radius, double intra_radius,
-                          const int32_t *n_inter, const int32_t *row_ptr,
+                          const int32_t *n_inter, int32_t *row_ptr,
                           const uint32_t *mask_scratch, int32_t edge_capacity,
                           int32_t *col, uint8_t *attr, int32_t *ref_pos,
                           int32_t *overflow, void *stream);

@@ -708,11 +708,23 @@ int pvs_radius_graph_count(const double *coords, const int32_t *bp,
     return exclusive_scan(deg, n_nodes, row_ptr, scratch, st);
 }
 
+// After a capacity-bounded fill: no consumer may index past col/attr, so the
+// offsets are cut at the capacity (a no-op unless *overflow was raised).
+__global__ void clamp_row_ptr_kernel(int32_t *row_ptr, int n, int cap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && row_ptr[i] > cap) row_ptr[i] = cap;
+}
+
+static int clamp_row_ptr(int32_t *row_ptr, int n_nodes, int cap, cudaStream_t st) {
+    clamp_row_ptr_kernel<<<(n_nodes + 1 + 255) / 256, 256, 0, st>>>(row_ptr, n_nodes + 1, cap);
+    return check_launch();
+}
+
 int pvs_radius_graph_fill(const double *coords, const int32_t *bp,
                           const int32_t *complex_ptr, int32_t n_complexes,
                           int32_t n_nodes, int32_t max_complex_nodes,
                           double inter_radius, double intra_radius,
-                          const int32_t *n_inter, const int32_t *row_ptr,
+                          const int32_t *n_inter, int32_t *row_ptr,
                           const uint32_t *mask_scratch, int32_t edge_capacity,
                           int32_t *col, uint8_t *attr, int32_t *ref_pos,
                           int32_t *overflow, void *stream) {
@@ -726,7 +738,9 @@ int pvs_radius_graph_fill(const double *coords, const int32_t *bp,
         radius_graph_emit_kernel<<<(n_nodes + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
             mask_scratch, words, bp, complex_ptr, n_complexes, n_nodes, row_ptr, col, attr,
             edge_capacity, overflow);
-        return check_launch();
+        rc = check_launch();
+        if (rc) return rc;
+        return clamp_row_ptr(row_ptr, n_nodes, edge_capacity, (cudaStream_t)stream);
     }
     int stage = 1;
     size_t smem = rg_smem_bytes(max_complex_nodes, ref_pos != nullptr, true);
@@ -742,7 +756,9 @@ int pvs_radius_graph_fill(const double *coords, const int32_t *bp,
         coords, bp, complex_ptr, inter_radius, intra_radius, nullptr, nullptr,
         n_inter, row_ptr, col, attr, ref_pos, max_complex_nodes, stage, nullptr,
         edge_capacity, overflow);
-    return check_launch();
+    rc = check_launch();
+    if (rc) return rc;
+    return clamp_row_ptr(row_ptr, n_nodes, edge_capacity, (cudaStream_t)stream);
 }
 
 int pvs_prune_mask(const int32_t *row_ptr, const int32_t *col,
