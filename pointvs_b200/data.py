@@ -265,6 +265,82 @@ def build_complex(rec, lig, n_features, radius, polar_hydrogens=False,
                    types, anum)
 
 
+def crop_batch(ligands, receptors, rec_of_pose, radius, n_features, compact,
+               device):
+    """K0 (pvs_crop_count / pvs_crop_fill) for one batch of poses.
+
+    ligands: list of `Ligand`; receptors: list of (xyz f64 [n,3], emit u8 [n],
+    code i16 [n]) tensors already on `device`; rec_of_pose[b] indexes them.
+    -> (coords f64 [N,3], bp i32 [N], feats f32 [N,F]) on the device and the
+    host complex_ptr [B+1].  One host read-back (the B+1 offsets) sizes the
+    outputs; everything else stays on the device."""
+    import ctypes as C   # noqa: PLC0415
+    from . import _cabi   # noqa: PLC0415
+    from ._cabi import check, lib, ptr, stream   # noqa: PLC0415
+    device = torch.device(device)
+    n_poses = len(ligands)
+    feature_dim = n_features + 1 if compact else 2 * n_features
+    if n_poses == 0:
+        return (torch.zeros((0, 3), dtype=torch.float64, device=device),
+                torch.zeros(0, dtype=torch.int32, device=device),
+                torch.zeros((0, feature_dim), device=device),
+                np.zeros(1, dtype=np.int32))
+    rec_sizes = [int(r[0].shape[0]) for r in receptors]
+    rec_ptr = np.zeros(len(receptors) + 1, dtype=np.int32)
+    np.cumsum(rec_sizes, out=rec_ptr[1:])
+    if len(receptors) == 1:
+        rec_xyz, rec_emit, rec_code = receptors[0]
+    else:
+        rec_xyz = torch.cat([r[0] for r in receptors])
+        rec_emit = torch.cat([r[1] for r in receptors])
+        rec_code = torch.cat([r[2] for r in receptors])
+    lig_ptr = np.zeros(n_poses + 1, dtype=np.int32)
+    np.cumsum([len(l) for l in ligands], out=lig_ptr[1:])
+    lig_code_h = np.concatenate([l.code for l in ligands])
+    if not compact and len(lig_code_h) and (
+            lig_code_h.min() < 0 or lig_code_h.max() >= 2 * n_features):
+        raise ValueError('atom type outside the one-hot range')
+    lig_xyz = torch.from_numpy(
+        np.concatenate([l.coords for l in ligands])).to(device)
+    lig_emit = torch.from_numpy(
+        np.concatenate([l.emit for l in ligands])).to(device)
+    lig_code = torch.from_numpy(lig_code_h).to(device)
+    lig_ptr_d = torch.from_numpy(lig_ptr).to(device)
+    rec_ptr_d = torch.from_numpy(rec_ptr).to(device)
+    rec_of_pose_d = torch.from_numpy(
+        np.ascontiguousarray(rec_of_pose, dtype=np.int32)).to(device)
+    words = max((max(rec_sizes) + 31) // 32 if rec_sizes else 0, 1)
+    h = lib()
+    mask = _cabi.scratch('k0_mask', n_poses * words * 4, device)
+    counts = torch.empty(n_poses, dtype=torch.int32, device=device)
+    cptr = torch.empty(n_poses + 1, dtype=torch.int32, device=device)
+    scan_ws = _cabi.scratch(
+        'k0_scan', int(h.pvs_scan_scratch_bytes(n_poses)) + 256, device)
+    with torch.cuda.device(device):
+        check(h.pvs_crop_count(
+            ptr(lig_xyz), ptr(lig_emit), ptr(lig_ptr_d), n_poses,
+            ptr(rec_xyz), ptr(rec_emit), ptr(rec_ptr_d), ptr(rec_of_pose_d),
+            words, C.c_double(float(radius)), ptr(mask), ptr(counts),
+            stream()), 'pvs_crop_count')
+        check(h.pvs_exclusive_scan(ptr(counts), n_poses, ptr(cptr),
+                                   ptr(scan_ws), stream()),
+              'pvs_exclusive_scan')
+        cptr_host = cptr.cpu().numpy()          # the one host sync
+        n = int(cptr_host[-1])
+        coords = torch.empty((max(n, 1), 3), dtype=torch.float64,
+                             device=device)
+        bp = torch.empty(max(n, 1), dtype=torch.int32, device=device)
+        feats = torch.empty((max(n, 1), feature_dim), dtype=torch.float32,
+                            device=device)
+        check(h.pvs_crop_fill(
+            ptr(lig_xyz), ptr(lig_emit), ptr(lig_code), ptr(lig_ptr_d),
+            n_poses, ptr(rec_xyz), ptr(rec_code), ptr(rec_ptr_d),
+            ptr(rec_of_pose_d), ptr(mask), words, ptr(cptr), n_features,
+            int(bool(compact)), ptr(coords), ptr(bp), ptr(feats), stream()),
+            'pvs_crop_fill')
+    return coords[:n], bp[:n], feats[:n], cptr_host
+
+
 # --------------------------------------------------------------------------
 # dataset + loader
 # --------------------------------------------------------------------------
@@ -469,30 +545,15 @@ class ComplexDataset:
                 self._rec_dev.popitem(last=False)
         return entry
 
-    def _check_codes(self, code):
-        if not self.compact and len(code) and (
-                code.min() < 0 or code.max() >= 2 * self.n_features):
-            raise ValueError('atom type outside the one-hot range')
-
     def crop_on_device(self, items, ligands=None):
         """K0 for the complexes `items`: -> (coords f64 [N,3], bp i32 [N],
-        feats f32 [N,F]) on the device and the host complex_ptr [B+1].  One
-        host read-back (the B+1 offsets) sizes the outputs."""
-        import ctypes as C   # noqa: PLC0415
-        from . import _cabi   # noqa: PLC0415
-        from ._cabi import check, lib, ptr, stream   # noqa: PLC0415
+        feats f32 [N,F]) on the device and the host complex_ptr [B+1]."""
         device = torch.device(self.device or 'cuda')
         if ligands is None:
             ligands = [self.load_ligand(i) for i in items]
-        n_poses = len(items)
-        if n_poses == 0:
-            return (torch.zeros((0, 3), dtype=torch.float64, device=device),
-                    torch.zeros(0, dtype=torch.int32, device=device),
-                    torch.zeros((0, self.feature_dim), device=device),
-                    np.zeros(1, dtype=np.int32))
         # receptors of this batch, each uploaded once and kept
         rec_names, rec_index = [], {}
-        rec_of_pose = np.zeros(n_poses, dtype=np.int32)
+        rec_of_pose = np.zeros(len(items), dtype=np.int32)
         for b, i in enumerate(items):
             name = str(self.receptor_fnames[i])
             if name not in rec_index:
@@ -500,58 +561,8 @@ class ComplexDataset:
                 rec_names.append(name)
             rec_of_pose[b] = rec_index[name]
         recs = [self.receptor_on_device(name, device) for name in rec_names]
-        rec_sizes = [int(r[0].shape[0]) for r in recs]
-        rec_ptr = np.zeros(len(recs) + 1, dtype=np.int32)
-        np.cumsum(rec_sizes, out=rec_ptr[1:])
-        if len(recs) == 1:
-            rec_xyz, rec_emit, rec_code = recs[0]
-        else:
-            rec_xyz = torch.cat([r[0] for r in recs])
-            rec_emit = torch.cat([r[1] for r in recs])
-            rec_code = torch.cat([r[2] for r in recs])
-        lig_ptr = np.zeros(n_poses + 1, dtype=np.int32)
-        np.cumsum([len(l) for l in ligands], out=lig_ptr[1:])
-        lig_code_h = np.concatenate([l.code for l in ligands])
-        self._check_codes(lig_code_h)
-        lig_xyz = torch.from_numpy(
-            np.concatenate([l.coords for l in ligands])).to(device)
-        lig_emit = torch.from_numpy(
-            np.concatenate([l.emit for l in ligands])).to(device)
-        lig_code = torch.from_numpy(lig_code_h).to(device)
-        lig_ptr_d = torch.from_numpy(lig_ptr).to(device)
-        rec_ptr_d = torch.from_numpy(rec_ptr).to(device)
-        rec_of_pose_d = torch.from_numpy(rec_of_pose).to(device)
-        words = (max(rec_sizes) + 31) // 32 if rec_sizes else 0
-        words = max(words, 1)
-        h = lib()
-        mask = _cabi.scratch('k0_mask', n_poses * words * 4, device)
-        counts = torch.empty(n_poses, dtype=torch.int32, device=device)
-        cptr = torch.empty(n_poses + 1, dtype=torch.int32, device=device)
-        scan_ws = _cabi.scratch(
-            'k0_scan', int(h.pvs_scan_scratch_bytes(n_poses)) + 256, device)
-        with torch.cuda.device(device):
-            check(h.pvs_crop_count(
-                ptr(lig_xyz), ptr(lig_emit), ptr(lig_ptr_d), n_poses,
-                ptr(rec_xyz), ptr(rec_emit), ptr(rec_ptr_d),
-                ptr(rec_of_pose_d), words, C.c_double(float(self.radius)),
-                ptr(mask), ptr(counts), stream()), 'pvs_crop_count')
-            check(h.pvs_exclusive_scan(ptr(counts), n_poses, ptr(cptr),
-                                       ptr(scan_ws), stream()),
-                  'pvs_exclusive_scan')
-            cptr_host = cptr.cpu().numpy()          # the one host sync
-            n = int(cptr_host[-1])
-            coords = torch.empty((max(n, 1), 3), dtype=torch.float64,
-                                 device=device)
-            bp = torch.empty(max(n, 1), dtype=torch.int32, device=device)
-            feats = torch.empty((max(n, 1), self.feature_dim),
-                                dtype=torch.float32, device=device)
-            check(h.pvs_crop_fill(
-                ptr(lig_xyz), ptr(lig_emit), ptr(lig_code), ptr(lig_ptr_d),
-                n_poses, ptr(rec_xyz), ptr(rec_code), ptr(rec_ptr_d),
-                ptr(rec_of_pose_d), ptr(mask), words, ptr(cptr),
-                self.n_features, int(bool(self.compact)), ptr(coords), ptr(bp),
-                ptr(feats), stream()), 'pvs_crop_fill')
-        return coords[:n], bp[:n], feats[:n], cptr_host
+        return crop_batch(ligands, recs, rec_of_pose, self.radius,
+                          self.n_features, self.compact, device)
 
     def prepare(self, item):
         """What a loader thread does ahead of the device for one complex."""
@@ -704,4 +715,5 @@ def get_data_loader(data_root, dataset_class=None, receptors=None,
 __all__ = ['ComplexDataset', 'PackedLoader', 'get_data_loader',
            'parse_classification_types', 'parse_regression_types',
            'read_structure', 'build_complex', 'make_box', 'make_bit_vector',
-           'atomic_number_table', 'atom_codes', 'Complex', 'Ligand']
+           'atomic_number_table', 'atom_codes', 'crop_batch', 'Complex',
+           'Ligand']
