@@ -265,15 +265,34 @@ def build_complex(rec, lig, n_features, radius, polar_hydrogens=False,
                    types, anum)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One high-priority stream per device for the K0 counting pass."""
+    key = (device.type, device.index if device.index is not None
+           else torch.cuda.current_device())
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device, priority=-1)
+    return _SIDE_STREAMS[key]
+
+
 def crop_batch(ligands, receptors, rec_of_pose, radius, n_features, compact,
-               device):
+               device, receptors_pending=False):
     """K0 (pvs_crop_count / pvs_crop_fill) for one batch of poses.
 
     ligands: list of `Ligand`; receptors: list of (xyz f64 [n,3], emit u8 [n],
     code i16 [n]) tensors already on `device`; rec_of_pose[b] indexes them.
     -> (coords f64 [N,3], bp i32 [N], feats f32 [N,F]) on the device and the
-    host complex_ptr [B+1].  One host read-back (the B+1 offsets) sizes the
-    outputs; everything else stays on the device."""
+    host complex_ptr [B+1].
+
+    One host read-back (the B+1 offsets) sizes the outputs.  The ligand
+    upload, the counting pass and that read-back run on a side stream, so the
+    host does not wait for whatever the caller's stream is still doing (the
+    previous batch's layers); the fill joins the caller's stream.  The
+    receptor tensors must already be complete on the device (synchronise once
+    after uploading them), or pass receptors_pending=True to order the side
+    stream after the caller's stream."""
     import ctypes as C   # noqa: PLC0415
     from . import _cabi   # noqa: PLC0415
     from ._cabi import check, lib, ptr, stream   # noqa: PLC0415
@@ -288,45 +307,51 @@ def crop_batch(ligands, receptors, rec_of_pose, radius, n_features, compact,
     rec_sizes = [int(r[0].shape[0]) for r in receptors]
     rec_ptr = np.zeros(len(receptors) + 1, dtype=np.int32)
     np.cumsum(rec_sizes, out=rec_ptr[1:])
-    if len(receptors) == 1:
-        rec_xyz, rec_emit, rec_code = receptors[0]
-    else:
-        rec_xyz = torch.cat([r[0] for r in receptors])
-        rec_emit = torch.cat([r[1] for r in receptors])
-        rec_code = torch.cat([r[2] for r in receptors])
     lig_ptr = np.zeros(n_poses + 1, dtype=np.int32)
     np.cumsum([len(l) for l in ligands], out=lig_ptr[1:])
     lig_code_h = np.concatenate([l.code for l in ligands])
     if not compact and len(lig_code_h) and (
             lig_code_h.min() < 0 or lig_code_h.max() >= 2 * n_features):
         raise ValueError('atom type outside the one-hot range')
-    lig_xyz = torch.from_numpy(
-        np.concatenate([l.coords for l in ligands])).to(device)
-    lig_emit = torch.from_numpy(
-        np.concatenate([l.emit for l in ligands])).to(device)
-    lig_code = torch.from_numpy(lig_code_h).to(device)
-    lig_ptr_d = torch.from_numpy(lig_ptr).to(device)
-    rec_ptr_d = torch.from_numpy(rec_ptr).to(device)
-    rec_of_pose_d = torch.from_numpy(
-        np.ascontiguousarray(rec_of_pose, dtype=np.int32)).to(device)
     words = max((max(rec_sizes) + 31) // 32 if rec_sizes else 0, 1)
     h = lib()
-    mask = _cabi.scratch('k0_mask', n_poses * words * 4, device)
-    counts = torch.empty(n_poses, dtype=torch.int32, device=device)
-    cptr = torch.empty(n_poses + 1, dtype=torch.int32, device=device)
-    scan_ws = _cabi.scratch(
-        'k0_scan', int(h.pvs_scan_scratch_bytes(n_poses)) + 256, device)
-    with torch.cuda.device(device):
+    main = torch.cuda.current_stream(device)
+    side = _side_stream(device)
+    if receptors_pending:
+        side.wait_stream(main)
+    with torch.cuda.device(device), torch.cuda.stream(side):
+        if len(receptors) == 1:
+            rec_xyz, rec_emit, rec_code = receptors[0]
+        else:
+            rec_xyz = torch.cat([r[0] for r in receptors])
+            rec_emit = torch.cat([r[1] for r in receptors])
+            rec_code = torch.cat([r[2] for r in receptors])
+        lig_xyz = torch.from_numpy(
+            np.concatenate([l.coords for l in ligands])).to(device)
+        lig_emit = torch.from_numpy(
+            np.concatenate([l.emit for l in ligands])).to(device)
+        lig_code = torch.from_numpy(lig_code_h).to(device)
+        lig_ptr_d = torch.from_numpy(lig_ptr).to(device)
+        rec_ptr_d = torch.from_numpy(rec_ptr).to(device)
+        rec_of_pose_d = torch.from_numpy(
+            np.ascontiguousarray(rec_of_pose, dtype=np.int32)).to(device)
+        mask = torch.empty(n_poses * words, dtype=torch.int32, device=device)
+        counts = torch.empty(n_poses, dtype=torch.int32, device=device)
+        cptr = torch.empty(n_poses + 1, dtype=torch.int32, device=device)
+        scan_ws = torch.empty(int(h.pvs_scan_scratch_bytes(n_poses)) + 256,
+                              dtype=torch.uint8, device=device)
+        sptr = C.c_void_p(side.cuda_stream)
         check(h.pvs_crop_count(
             ptr(lig_xyz), ptr(lig_emit), ptr(lig_ptr_d), n_poses,
             ptr(rec_xyz), ptr(rec_emit), ptr(rec_ptr_d), ptr(rec_of_pose_d),
-            words, C.c_double(float(radius)), ptr(mask), ptr(counts),
-            stream()), 'pvs_crop_count')
+            words, C.c_double(float(radius)), ptr(mask), ptr(counts), sptr),
+            'pvs_crop_count')
         check(h.pvs_exclusive_scan(ptr(counts), n_poses, ptr(cptr),
-                                   ptr(scan_ws), stream()),
-              'pvs_exclusive_scan')
-        cptr_host = cptr.cpu().numpy()          # the one host sync
-        n = int(cptr_host[-1])
+                                   ptr(scan_ws), sptr), 'pvs_exclusive_scan')
+        cptr_host = cptr.cpu().numpy()          # waits for the side stream only
+    n = int(cptr_host[-1])
+    with torch.cuda.device(device):
+        main.wait_stream(side)
         coords = torch.empty((max(n, 1), 3), dtype=torch.float64,
                              device=device)
         bp = torch.empty(max(n, 1), dtype=torch.int32, device=device)
@@ -338,6 +363,10 @@ def crop_batch(ligands, receptors, rec_of_pose, radius, n_features, compact,
             ptr(rec_of_pose_d), ptr(mask), words, ptr(cptr), n_features,
             int(bool(compact)), ptr(coords), ptr(bp), ptr(feats), stream()),
             'pvs_crop_fill')
+        # allocated on the side stream, last read on the caller's stream
+        for t in (lig_xyz, lig_emit, lig_code, lig_ptr_d, rec_ptr_d,
+                  rec_of_pose_d, mask, cptr, rec_xyz, rec_code):
+            t.record_stream(main)
     return coords[:n], bp[:n], feats[:n], cptr_host
 
 
@@ -539,6 +568,8 @@ class ComplexDataset:
         entry = (torch.from_numpy(np.ascontiguousarray(xyz)).to(device),
                  torch.from_numpy(emit).to(device),
                  torch.from_numpy(code).to(device))
+        # complete before any other stream (K0's side stream) reads them
+        torch.cuda.current_stream(device).synchronize()
         with self._cache_lock:
             self._rec_dev[key] = entry
             while len(self._rec_dev) > max(1, self._cache_size):

@@ -43,6 +43,7 @@ def main():
               torch.ones(n_pocket, dtype=torch.uint8, device=dev),
               torch.from_numpy((types[n_lig:per] + n_types).astype(np.int16)
                                ).to(dev))
+    torch.cuda.synchronize()   # the pocket is resident before K0's side stream reads it
     pool = [data.Ligand(coords[p * per:p * per + n_lig].copy(),
                         np.ones(n_lig, dtype=np.uint8),
                         types[p * per:p * per + n_lig].astype(np.int16))
