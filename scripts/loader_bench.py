@@ -4,9 +4,7 @@ Repeats the seven sample complexes under tests/golden/complexes into a types
 file of `--n` lines (the page cache serves the files, so this measures parsing,
 cropping, packing, H2D and the device path, not the disk) and scores them with
 the 8 x 64 `egnn` through `PackedLoader`.  Prints one JSON line; beside it the
-host-only rate of the loader threads and, for a bounded sample, the CPU oracle's
-`generate_edges` restatement per complex (what the reference's loader spends in
-its `__getitem__` besides the same parquet work).
+host-only rate of the loader threads.
 """
 import argparse
 import json
@@ -31,7 +29,6 @@ def main():
     ap.add_argument('--batch_size', type=int, default=128)
     ap.add_argument('--workers', type=int, default=8)
     ap.add_argument('--math', default='bf16x3')
-    ap.add_argument('--cpu-sample', type=int, default=14)
     ap.add_argument('--host-crop', action='store_true')
     args = ap.parse_args()
     lines = [ln for ln in (COMPLEXES / 'pose.types').read_text().splitlines()
@@ -79,13 +76,6 @@ def main():
             list(pool.map(ds.prepare, range(len(ds))))
         host = time.perf_counter() - t0
 
-        # CPU oracle generate_edges on a bounded sample
-        from oracle import radius_graph as rg
-        t0 = time.perf_counter()
-        for i in range(args.cpu_sample):
-            c = ds.load(i)
-            rg.radius_graph(c.coords, c.bp, ds.inter_radius, ds.intra_radius)
-        cpu_edges = (time.perf_counter() - t0) / args.cpu_sample
 
     print(json.dumps({
         'metric': 'complexes scored per second from types file + parquets',
@@ -94,8 +84,6 @@ def main():
         'batch_size': args.batch_size, 'loader_threads': args.workers,
         'math': args.math, 'crop': 'host' if args.host_crop else 'device',
         'host_loader_only_complexes_per_s': round(args.n / host, 1),
-        'cpu_oracle_load_plus_generate_edges_ms_per_complex':
-            round(cpu_edges * 1e3, 2),
         'scores_finite': bool(torch.isfinite(scores).all())}))
 
 
