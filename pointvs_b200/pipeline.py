@@ -36,8 +36,10 @@ class ScoreStream:
     """Pipelined scoring of host-resident packed batches.
 
     submit(coords f64 [N,3], bp [N], feats f32 [N,F], complex_ptr [B+1], tag)
-    queues one batch; results() / drain() give (tag, scores ndarray [B, out])
-    in submission order."""
+    queues one batch (host arrays / tensors, or tensors already on the
+    device); results() / drain() give (tag, scores ndarray [B, out]) in
+    submission order.  `edges_scored` (device int64) counts the edges of
+    everything submitted."""
 
     def __init__(self, model, inter_radius=4.0, intra_radius=4.0, depth=3,
                  edge_capacity='auto', activation=None):
@@ -56,6 +58,8 @@ class ScoreStream:
         self._pending = []     # slots in flight, oldest first
         self._ready = []       # finished (tag, scores)
         self._overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.edges_scored = torch.zeros(1, dtype=torch.int64,
+                                        device=self.device)
 
     # -- staging ---------------------------------------------------------------
     @staticmethod
@@ -66,7 +70,10 @@ class ScoreStream:
         return t.contiguous()
 
     def _stage(self, slot, name, src, dtype):
-        """src (host) -> slot's device buffer on the copy stream."""
+        """src (host) -> slot's device buffer on the copy stream.  A tensor
+        that already lives on the device is used where it is."""
+        if isinstance(src, torch.Tensor) and src.is_cuda:
+            return src if src.dtype == dtype else src.to(dtype)
         src = self._as_cpu_tensor(src, dtype)
         n = src.shape[0]
         dev = slot.dev.get(name)
@@ -116,6 +123,7 @@ class ScoreStream:
             scores = torch.sigmoid(scores)
         if self.edge_capacity is not None:
             self._overflow += batch.pvs_csr._overflow
+        self.edges_scored += batch.pvs_csr.n_edges_dev
         if slot.out is None or slot.out.shape[0] < n_graphs or \
                 slot.out.shape[1] != scores.shape[1]:
             slot.out = torch.empty((max(n_graphs, 1), scores.shape[1]),
