@@ -56,6 +56,7 @@ int launch_node_pre_tc(const float *h, const float *edge_w1, const float *edge_b
                        cudaStream_t st);
 int launch_node_tc(const float *h_in, const float *M, float *h_out, float *natt_out,
                    const pvs_layer_params *p, int n_nodes, int k, uint32_t flags, int att_act,
-                   int mode, cudaStream_t st);
+                   int mode, cudaStream_t st, int phase = 0, float *V = nullptr,
+                   const float *gn_a = nullptr, const float *gn_b = nullptr);
 
 }  // namespace pvs

@@ -690,6 +690,21 @@ static FwdWorkspace carve_workspace(void *base, int n, int e, int kp, uint32_t f
     return w;
 }
 
+// Batch-wide GraphNorm statistics of V (two passes: mean, then the centred
+// second moment) -> the per-channel affine gn_a * v + gn_b, mean and 1/std.
+static int graphnorm_stats(const FwdWorkspace &w, const pvs_layer_params *p, int n, int k,
+                           int kp, cudaStream_t st) {
+    gn_colsum_kernel<<<GN_BLOCKS, 256, 0, st>>>(w.V, n, kp, nullptr, 0, w.gn_partial);
+    gn_finalize_kernel<<<1, 64, 0, st>>>(w.gn_partial, GN_BLOCKS, n, k, 0, p->gn_weight,
+                                         p->gn_bias, p->gn_mean_scale, w.gn_shift, w.gn_a,
+                                         w.gn_b, w.gn_mean, w.gn_invstd);
+    gn_colsum_kernel<<<GN_BLOCKS, 256, 0, st>>>(w.V, n, kp, w.gn_shift, 1, w.gn_partial);
+    gn_finalize_kernel<<<1, 64, 0, st>>>(w.gn_partial, GN_BLOCKS, n, k, 1, p->gn_weight,
+                                         p->gn_bias, p->gn_mean_scale, w.gn_shift, w.gn_a,
+                                         w.gn_b, w.gn_mean, w.gn_invstd);
+    return check_launch(4);
+}
+
 int64_t fwd_recompute_bytes(int n, int e, uint32_t flags) {
     return carve_workspace(nullptr, n, e, 64, flags).bytes + 256;
 }
@@ -754,17 +769,11 @@ int fwd_recompute(const pvs_graph *g, const pvs_layer_config *cfg, const pvs_lay
         na.node_gate = p->node_gate;
         na.n_nodes = n; na.k = k; na.flags = f; na.att_act = cfg->att_act;
         na.phase = 1;
-        rc = launch_node<64>(na, st);
+        rc = tc ? launch_node_tc(h_in, w.M, nullptr, nullptr, p, n, k, f, cfg->att_act,
+                                 cfg->math, st, 1, w.V, nullptr, nullptr)
+                : launch_node<64>(na, st);
         if (rc) return rc;
-        gn_colsum_kernel<<<GN_BLOCKS, 256, 0, st>>>(w.V, n, 64, nullptr, 0, w.gn_partial);
-        gn_finalize_kernel<<<1, 64, 0, st>>>(w.gn_partial, GN_BLOCKS, n, k, 0, p->gn_weight,
-                                             p->gn_bias, p->gn_mean_scale, w.gn_shift, w.gn_a,
-                                             w.gn_b, w.gn_mean, w.gn_invstd);
-        gn_colsum_kernel<<<GN_BLOCKS, 256, 0, st>>>(w.V, n, 64, w.gn_shift, 1, w.gn_partial);
-        gn_finalize_kernel<<<1, 64, 0, st>>>(w.gn_partial, GN_BLOCKS, n, k, 1, p->gn_weight,
-                                             p->gn_bias, p->gn_mean_scale, w.gn_shift, w.gn_a,
-                                             w.gn_b, w.gn_mean, w.gn_invstd);
-        rc = check_launch(4);
+        rc = graphnorm_stats(w, p, n, k, 64, st);
         if (rc) return rc;
     }
     *out = w;
@@ -853,7 +862,7 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
     const int stages = (cfg->stages & PVS_STAGE_ALL) ? (cfg->stages & PVS_STAGE_ALL)
                                                      : PVS_STAGE_ALL;
     // node_pre: P = h W1a^T + b1 ; Q = h W1b^T (perm-invariant: Q = h W1a^T)
-    const bool tc_node = tc && !(f & PVS_F_GRAPHNORM);
+    const bool tc_node = tc;
     if ((stages & PVS_STAGE_NODE_PRE) && tc_node) {
         rc = launch_node_pre_tc(h_in, p->edge_w1, p->edge_b1, w.P, w.Q, n, k, in_e, perm ? 1 : 0,
                                 cfg->math, st);
@@ -907,8 +916,18 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
         cudaEventRecord((cudaEvent_t)cfg->ev_edge_end, st);
 
     if (!(stages & PVS_STAGE_NODE)) return PVS_OK;
-    if (tc_node)
+    if (tc_node && !(f & PVS_F_GRAPHNORM))
         return launch_node_tc(h_in, w.M, h_out, natt_out, p, n, k, f, cfg->att_act, cfg->math, st);
+    if (tc_node) {
+        // GraphNorm: Wn1 on the tensor cores -> V, batch statistics, resume from V
+        rc = launch_node_tc(h_in, w.M, nullptr, nullptr, p, n, k, f, cfg->att_act, cfg->math, st,
+                            1, w.V, nullptr, nullptr);
+        if (rc) return rc;
+        rc = graphnorm_stats(w, p, n, k, kp, st);
+        if (rc) return rc;
+        return launch_node_tc(h_in, w.M, h_out, natt_out, p, n, k, f, cfg->att_act, cfg->math, st,
+                              2, w.V, w.gn_a, w.gn_b);
+    }
     NodeArgs na{};
     na.h_in = h_in; na.M = w.M; na.h_out = h_out; na.V = w.V;
     na.natt_out = natt_out;
@@ -920,17 +939,7 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
         na.phase = 1;
         rc = kp == 32 ? launch_node<32>(na, st) : launch_node<64>(na, st);
         if (rc) return rc;
-        gn_colsum_kernel<<<GN_BLOCKS, 256, 0, st>>>(w.V, n, kp, nullptr, 0, w.gn_partial);
-        gn_finalize_kernel<<<1, 64, 0, st>>>(w.gn_partial, GN_BLOCKS, n, k, 0,
-                                             p->gn_weight, p->gn_bias,
-                                             p->gn_mean_scale, w.gn_shift, w.gn_a, w.gn_b,
-                                             w.gn_mean, w.gn_invstd);
-        gn_colsum_kernel<<<GN_BLOCKS, 256, 0, st>>>(w.V, n, kp, w.gn_shift, 1, w.gn_partial);
-        gn_finalize_kernel<<<1, 64, 0, st>>>(w.gn_partial, GN_BLOCKS, n, k, 1,
-                                             p->gn_weight, p->gn_bias,
-                                             p->gn_mean_scale, w.gn_shift, w.gn_a, w.gn_b,
-                                             w.gn_mean, w.gn_invstd);
-        rc = check_launch(4);
+        rc = graphnorm_stats(w, p, n, k, kp, st);
         if (rc) return rc;
         na.phase = 2;
         na.gn_a = w.gn_a; na.gn_b = w.gn_b;

@@ -187,7 +187,7 @@ struct __align__(1024) NmSmem {
     uint8_t W1h_hi[64 * 128], W1h_lo[64 * 128];   // node_w1[:, 0:k]   (h part)
     uint8_t W1m_hi[64 * 128], W1m_lo[64 * 128];   // node_w1[:, k:2k]  (M part)
     uint8_t W2_hi[64 * 128], W2_lo[64 * 128];
-    float b1[64], b2[64], wn[64];
+    float b1[64], b2[64], wn[64], ga[64], gb[64];
     uint64_t mbar[NM_GROUPS];
     uint32_t tmem_base;
 };
@@ -201,7 +201,43 @@ struct NodeTcArgs {
     int n_nodes, k;
     uint32_t flags;
     int att_act;
+    // GraphNorm (batch-wide statistics between the two Linears,
+    // egnn_satorras.py:84): phase 1 stops after Wn1 and writes the
+    // pre-activation V; phase 2 resumes from V with the affine gn_a * v + gn_b
+    float *V;            // [N][64]
+    const float *gn_a, *gn_b;
+    int phase;           // 0: whole node model
 };
+
+// V rows -> u = silu(ga * v + gb) -> bf16 hi/lo A tiles (phase 2 of GraphNorm)
+template <bool X3>
+__device__ __forceinline__ void load_block_gn(uint8_t *A_hi, uint8_t *A_lo,
+                                              const float *__restrict__ V, const float *ga,
+                                              const float *gb, int row0, int n_rows, int tid) {
+    const int c = tid & 7, slot = tid >> 3;
+    float a8[8], b8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a8[i] = ga[8 * c + i]; b8[i] = gb[8 * c + i]; }
+#pragma unroll 4
+    for (int p = 0; p < NT_ROWS / 16; ++p) {
+        const int r = p * 16 + slot;
+        float v[8];
+        if (row0 + r < n_rows) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(V + (size_t)(row0 + r) * 64 + 8 * c);
+            const float4 x = __ldg(s4), y = __ldg(s4 + 1);
+            const float in[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = silu_mode<X3>(fmaf(a8[i], in[i], b8[i]));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+        }
+        uint4 hi, lo;
+        split8<X3>(v, hi, lo);
+        *reinterpret_cast<uint4 *>(A_hi + swz(r, c)) = hi;
+        if (X3) *reinterpret_cast<uint4 *>(A_lo + swz(r, c)) = lo;
+    }
+}
 
 template <bool X3>
 __global__ void __launch_bounds__(NM_THREADS, 1)
@@ -220,6 +256,8 @@ node_tc_kernel(const NodeTcArgs a) {
         S.b1[n] = n < k ? a.node_b1[n] : 0.0f;
         S.b2[n] = n < k ? a.node_b2[n] : 0.0f;
         S.wn[n] = (n < k && a.natt_w) ? a.natt_w[n] : 0.0f;
+        S.ga[n] = (n < k && a.gn_a) ? a.gn_a[n] : 1.0f;
+        S.gb[n] = (n < k && a.gn_b) ? a.gn_b[n] : 0.0f;
     }
     if (tid == 0) mbar_init(&S.mbar[g], 1);
     if (threadIdx.x < 32) tmem_alloc<512>(&S.tmem_base);
@@ -239,50 +277,86 @@ node_tc_kernel(const NodeTcArgs a) {
     for (int t = blockIdx.x * NM_GROUPS + g; t < n_tiles; t += gridDim.x * NM_GROUPS) {
         const int row0 = t * NT_ROWS;
         nt_group_sync(g);
-        // ---- v = Wn1 [h ; M]: two K blocks through the same A tiles ----
-        load_block<X3>(A_hi, A_lo, a.h_in, k, k, row0, a.n_nodes, tid);
-        fence_proxy_async();
-        tc_fence_before();
-        nt_group_sync(g);
-        if (tid == 0) {
+        if (a.phase != 2) {
+            // ---- v = Wn1 [h ; M]: two K blocks through the same A tiles ----
+            load_block<X3>(A_hi, A_lo, a.h_in, k, k, row0, a.n_nodes, tid);
+            fence_proxy_async();
+            tc_fence_before();
+            nt_group_sync(g);
+            if (tid == 0) {
+                tc_fence_after();
+                issue_kblock<X3>(tmem_grp, tc_idesc(64), A_hi, A_lo, S.W1h_hi, S.W1h_lo, 0);
+                umma_commit(&S.mbar[g]);
+            }
+            mbar_wait(&S.mbar[g], phase);
+            phase ^= 1;
+            load_block<X3>(A_hi, A_lo, a.M, 64, 64, row0, a.n_nodes, tid);
+            fence_proxy_async();
+            tc_fence_before();
+            nt_group_sync(g);
+            if (tid == 0) {
+                tc_fence_after();
+                issue_kblock<X3>(tmem_grp, tc_idesc(64), A_hi, A_lo, S.W1m_hi, S.W1m_lo, 1);
+                umma_commit(&S.mbar[g]);
+            }
+            mbar_wait(&S.mbar[g], phase);
+            phase ^= 1;
             tc_fence_after();
-            issue_kblock<X3>(tmem_grp, tc_idesc(64), A_hi, A_lo, S.W1h_hi, S.W1h_lo, 0);
-            umma_commit(&S.mbar[g]);
         }
-        mbar_wait(&S.mbar[g], phase);
-        phase ^= 1;
-        load_block<X3>(A_hi, A_lo, a.M, 64, 64, row0, a.n_nodes, tid);
-        fence_proxy_async();
-        tc_fence_before();
-        nt_group_sync(g);
-        if (tid == 0) {
-            tc_fence_after();
-            issue_kblock<X3>(tmem_grp, tc_idesc(64), A_hi, A_lo, S.W1m_hi, S.W1m_lo, 1);
-            umma_commit(&S.mbar[g]);
-        }
-        mbar_wait(&S.mbar[g], phase);
-        phase ^= 1;
-        tc_fence_after();
-        // ---- u = silu(v + b1) -> A tiles ----
-        {
+        if (a.phase == 1) {
+            // ---- GraphNorm phase 1: V = v + b1 (fp32) -> staging -> HBM ----
             const int r = tid;
+            float *st = reinterpret_cast<float *>(r < 64 ? A_hi : A_lo);
+            const int rr = r & 63;
 #pragma unroll 1
             for (int q = 0; q < 4; ++q) {
                 float acc[16];
                 tmem_ld16(tmem_lane + 16 * q, acc);
 #pragma unroll
-                for (int hlf = 0; hlf < 2; ++hlf) {
-                    const int nb = 16 * q + 8 * hlf;
-                    const float4 ba = *reinterpret_cast<const float4 *>(&S.b1[nb]);
-                    const float4 bb = *reinterpret_cast<const float4 *>(&S.b1[nb + 4]);
-                    const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-                    float u[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) u[i] = silu_mode<X3>(acc[8 * hlf + i] + bias[i]);
-                    uint4 hi, lo;
-                    split8<X3>(u, hi, lo);
-                    *reinterpret_cast<uint4 *>(A_hi + swz(r, 2 * q + hlf)) = hi;
-                    if (X3) *reinterpret_cast<uint4 *>(A_lo + swz(r, 2 * q + hlf)) = lo;
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    const int n = 16 * q + 4 * v4;
+                    *stage_ptr(st, rr, 4 * q + v4) =
+                        make_float4(acc[4 * v4] + S.b1[n], acc[4 * v4 + 1] + S.b1[n + 1],
+                                    acc[4 * v4 + 2] + S.b1[n + 2], acc[4 * v4 + 3] + S.b1[n + 3]);
+                }
+            }
+            tc_fence_before();
+            nt_group_sync(g);
+            const int c4 = tid & 15, slot = tid >> 4;
+#pragma unroll 4
+            for (int p = 0; p < NT_ROWS / 8; ++p) {
+                const int row = p * 8 + slot;
+                if (row0 + row >= a.n_nodes) continue;
+                const float *sp = reinterpret_cast<const float *>(row < 64 ? A_hi : A_lo);
+                *reinterpret_cast<float4 *>(a.V + (size_t)(row0 + row) * 64 + 4 * c4) =
+                    *stage_ptr(const_cast<float *>(sp), row & 63, c4);
+            }
+            continue;
+        }
+        if (a.phase == 2) {
+            load_block_gn<X3>(A_hi, A_lo, a.V, S.ga, S.gb, row0, a.n_nodes, tid);
+        } else {
+            // ---- u = silu(v + b1) -> A tiles ----
+            {
+                const int r = tid;
+    #pragma unroll 1
+                for (int q = 0; q < 4; ++q) {
+                    float acc[16];
+                    tmem_ld16(tmem_lane + 16 * q, acc);
+    #pragma unroll
+                    for (int hlf = 0; hlf < 2; ++hlf) {
+                        const int nb = 16 * q + 8 * hlf;
+                        const float4 ba = *reinterpret_cast<const float4 *>(&S.b1[nb]);
+                        const float4 bb = *reinterpret_cast<const float4 *>(&S.b1[nb + 4]);
+                        const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                        float u[8];
+    #pragma unroll
+                        for (int i = 0; i < 8; ++i) u[i] = silu_mode<X3>(acc[8 * hlf + i] + bias[i]);
+                        uint4 hi, lo;
+                        split8<X3>(u, hi, lo);
+                        *reinterpret_cast<uint4 *>(A_hi + swz(r, 2 * q + hlf)) = hi;
+                        if (X3) *reinterpret_cast<uint4 *>(A_lo + swz(r, 2 * q + hlf)) = lo;
+                    }
                 }
             }
         }
@@ -407,8 +481,10 @@ int launch_node_pre_tc(const float *h, const float *edge_w1, const float *edge_b
 
 int launch_node_tc(const float *h_in, const float *M, float *h_out, float *natt_out,
                    const pvs_layer_params *p, int n_nodes, int k, uint32_t flags, int att_act,
-                   int mode, cudaStream_t st) {
+                   int mode, cudaStream_t st, int phase, float *V, const float *gn_a,
+                   const float *gn_b) {
     NodeTcArgs a{};
+    a.phase = phase; a.V = V; a.gn_a = gn_a; a.gn_b = gn_b;
     a.h_in = h_in; a.M = M; a.h_out = h_out; a.natt_out = natt_out;
     a.node_w1 = p->node_w1; a.node_b1 = p->node_b1; a.node_w2 = p->node_w2;
     a.node_b2 = p->node_b2; a.natt_w = p->natt_w; a.natt_b = p->natt_b;

@@ -114,3 +114,39 @@ def test_tc_deterministic():
         a = model(gh.synthetic_graph(300, 2, 1000, 30))
         b = model(gh.synthetic_graph(300, 2, 1000, 30))
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('k,ragged', [(64, False), (40, True)])
+def test_tc_graphnorm_node_stage_vs_oracle(k, ragged):
+    """GraphNorm models run the node MLP on the tensor cores too: Wn1 -> V,
+    batch statistics over all nodes, resume from V (egnn_satorras.py:84)."""
+    kw = dict(dim_input=13, dim_output=1, k=k, num_layers=3, graphnorm=True,
+              edge_attention=True, node_attention=True, residual=True,
+              normalize=True, tanh=True)
+    model = gh.build_model(kw, seed=9, coord_gain=1.0)
+    with torch.no_grad():          # non-trivial affine and mean scale
+        for name, p in model.named_parameters():
+            if 'node_mlp.1.' in name:
+                p.add_(0.3 * torch.randn_like(p))
+    graph = gh.synthetic_graph(700, 5, 260, 14, ragged=ragged)
+    pos0 = graph.pos.clone()
+    want, x_want = gh.oracle_forward(
+        model, kw, SimpleNamespace(x=graph.x, pos=pos0,
+                                   edge_index=graph.edge_index,
+                                   edge_attr=graph.edge_attr,
+                                   batch=graph.batch))
+    for math, tol in (('fp32', 1e-4), ('bf16x3', 1e-4), ('bf16', 3e-2)):
+        model.set_math(math)
+        graph.pos = pos0.clone()
+        with torch.no_grad():
+            out = model(graph)
+        assert helpers.rel_err(out.cpu().numpy().reshape(-1),
+                               want.numpy().reshape(-1)) < tol, math
+    # training-time recompute goes through the same kernels
+    model.set_math('bf16x3')
+    model.train()
+    graph.pos = pos0.clone()
+    out = model(graph).reshape(-1)
+    out.sum().backward()
+    g = model.layers[1].node_mlp[1].weight.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().max() > 0
