@@ -31,6 +31,8 @@
 namespace pvs {
 
 constexpr int TC_GROUP_THREADS = 128;
+// groups per CTA; -DPVS_EXP_GROUPS=n builds the concurrency experiment of
+// profiles/README.md (capture F)
 #ifndef PVS_EXP_GROUPS
 #define PVS_EXP_GROUPS 5
 #endif
@@ -218,13 +220,8 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                         const int r = min(p * 16 + slot, ne - 1);
                         const float4 *pp = reinterpret_cast<const float4 *>(
                             a.P + (size_t)(n0 + Gm.e_rowl[r]) * TC_K + 8 * c);
-#ifdef PVS_EXP_NOGATHER
-                        const float4 *qq = reinterpret_cast<const float4 *>(
-                            a.Q + (size_t)(n0 + Gm.e_rowl[r]) * TC_K + 8 * c);
-#else
                         const float4 *qq = reinterpret_cast<const float4 *>(
                             a.Q + (size_t)Gm.e_col[r] * TC_K + 8 * c);
-#endif
                         bq[0] = __ldg(pp); bq[1] = __ldg(pp + 1);
                         bq[2] = __ldg(qq); bq[3] = __ldg(qq + 1);
                         rad = Gm.e_rad[r];

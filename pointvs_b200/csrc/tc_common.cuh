@@ -151,9 +151,6 @@ __device__ __forceinline__ float2 silu2_mode(float2 v) {
 // in-place SiLU of two packed pairs (shared reciprocal in the fp32-class mode)
 template <bool X3>
 __device__ __forceinline__ void silu4_mode(float2 &u, float2 &v) {
-#ifdef PVS_EXP_NOSILU
-    return;
-#endif
     if (X3) {
         silu4_(u, v);
     } else {
