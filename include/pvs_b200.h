@@ -93,6 +93,14 @@ typedef struct pvs_graph {
     const int32_t *tile_ptr; /* [n_tiles+1] node boundaries of work tiles     */
     const int32_t *n_tiles;  /* device scalar written by pvs_build_tiles      */
     int32_t n_tiles_cap;     /* capacity of tile_ptr minus one                */
+    /* Edge-packed tiles (pvs_build_packed_tiles), used by the tcgen05 edge
+     * kernel (math != PVS_MATH_FP32): tile t owns edges [128 t, 128 t + 128),
+     * ptile_last[t] = node that holds its last edge.  A node whose edges
+     * cross a tile boundary is reduced through per-tile partial slots and a
+     * fixed-order fix-up pass.  NULL: math = PVS_MATH_FP32 only.            */
+    const int32_t *ptile_last; /* [n_ptiles_cap]                              */
+    const int32_t *n_ptiles;   /* device scalar = max(1, ceil(E / 128))       */
+    int32_t n_ptiles_cap;
 } pvs_graph;
 
 typedef struct pvs_layer_config {
@@ -254,6 +262,14 @@ int32_t pvs_tiles_capacity(int32_t n_nodes, int32_t n_edges);
 int64_t pvs_tiles_scratch_bytes(int32_t n_nodes);
 int pvs_build_tiles(const int32_t *row_ptr, int32_t n_nodes, int32_t *tile_ptr,
                     int32_t *n_tiles, void *scratch, void *stream);
+
+/* Edge-packed tile partition (see pvs_graph).  ptile_last needs
+ * pvs_packed_tiles_capacity(n_edges) ints; n_edges may be an upper bound (a
+ * capacity-bounded CSR): the true count is read from row_ptr[n_nodes]. */
+int32_t pvs_packed_tiles_capacity(int32_t n_edges);
+int pvs_build_packed_tiles(const int32_t *row_ptr, int32_t n_nodes,
+                           int32_t n_edges, int32_t *ptile_last,
+                           int32_t *n_ptiles, void *stream);
 
 /* Arbitrary-order edge_index (PyG [2][E] int64, edge_attr one-hot int64
  * [E][n_classes] or NULL) -> destination-sorted CSR, stable in the caller's

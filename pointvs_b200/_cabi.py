@@ -42,7 +42,9 @@ _fp = C.c_void_p
 class Graph(C.Structure):
     _fields_ = [('n_nodes', C.c_int32), ('n_edges', C.c_int32),
                 ('row_ptr', _fp), ('col', _fp), ('attr', _fp),
-                ('tile_ptr', _fp), ('n_tiles', _fp), ('n_tiles_cap', C.c_int32)]
+                ('tile_ptr', _fp), ('n_tiles', _fp), ('n_tiles_cap', C.c_int32),
+                ('ptile_last', _fp), ('n_ptiles', _fp),
+                ('n_ptiles_cap', C.c_int32)]
 
 
 class LayerConfig(C.Structure):

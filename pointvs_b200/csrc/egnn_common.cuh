@@ -11,6 +11,11 @@ struct EdgeArgs {
     // graph
     const int32_t *row_ptr, *col, *tile_ptr, *n_tiles;
     const uint8_t *attr;
+    // edge-packed tiles (tcgen05 kernel only): see pvs_graph
+    const int32_t *ptile_last, *n_ptiles;
+    int n_nodes;
+    float *Mpart;            // [n_ptiles_cap][2][64] partial message sums of split nodes
+    float *xpart;            // [n_ptiles_cap][2][4]  partial coordinate sums
     // activations
     const float *P, *Q;      // [N][KP]
     const float *x_in;       // [N][3]
@@ -30,7 +35,7 @@ struct EdgeArgs {
 
 
 // launches the tcgen05 edge kernel (egnn_edge_tc.cu); mode = pvs_math
-int launch_edge_tc(const EdgeArgs &a, int n_tiles_cap, int mode, cudaStream_t st);
+int launch_edge_tc(const EdgeArgs &a, int n_ptiles_cap, int mode, cudaStream_t st);
 // FFMA edge kernel with the 64-wide internal pitch (egnn_fwd.cu)
 int launch_edge_fp32_k64(const EdgeArgs &a, int n_tiles_cap, cudaStream_t st);
 // out = act(in . W^T + b) (w_in_major: out = in . W); accumulate: out += ...
@@ -44,6 +49,7 @@ int persistent_grid(int work_items, int blocks_per_sm);
 struct FwdWorkspace {
     float *P, *Q, *M, *V, *m_ws, *z_ws, *gn_partial, *gn_shift, *gn_a, *gn_b;
     float *gn_mean, *gn_invstd;
+    float *Mpart, *xpart;    // split-node partials of the edge-packed tiles
     int64_t bytes;
 };
 int64_t fwd_recompute_bytes(int n, int e, uint32_t flags);

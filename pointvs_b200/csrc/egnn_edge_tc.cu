@@ -64,6 +64,7 @@ struct TcGroupMisc {
     uint8_t e_rowl[TE], e_attr[TE];
     int rp[TN + 1];
     float xsum[TN][3];
+    int split_lo, split_hi;   // first / last node of the window crosses the tile's edge range
     uint64_t mbar;
 };
 
@@ -156,23 +157,42 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
     const float att_b = (f_att && a.att_b) ? a.att_b[0] : 0.0f;
     float gate = 1.0f;
     if (f_eres && a.edge_gate) gate = a.edge_gate[0];
-    const int n_tiles = *a.n_tiles;
+    const int n_tiles = *a.n_ptiles;
 #ifdef PVS_PHASE_PROF
     long long t_prev_ = clock64();
 #endif
 
+    // Edge-packed tiles: tile t owns edges [128 t, 128 t + 128) and the nodes
+    // from the one after the previous tile's last node (or that node itself
+    // when its edges continue here) to the node of its own last edge.  A node
+    // cut by a tile boundary leaves its partial sums in Mpart / xpart; the
+    // fix-up kernel adds them in tile order.  Runs of edgeless nodes can make
+    // the node range longer than the shared-memory window: it is then walked
+    // 128 nodes at a time.
+    const int E_total = a.row_ptr[a.n_nodes];
     for (int t = blockIdx.x * TC_GROUPS + g; t < n_tiles; t += gridDim.x * TC_GROUPS) {
-        const int n0 = a.tile_ptr[t], n1 = a.tile_ptr[t + 1];
-        const int nn = n1 - n0;
+        const int E0 = t * TE, E1 = min(E0 + TE, E_total);
+        int cover_lo = 0;
+        if (t > 0) {
+            const int na = a.ptile_last[t - 1];
+            cover_lo = a.row_ptr[na + 1] > E0 ? na : na + 1;
+        }
+        const int cover_hi = (t == n_tiles - 1) ? a.n_nodes - 1 : a.ptile_last[t];
+        for (int n0 = cover_lo; n0 <= cover_hi; n0 += TN) {
+        const int nn = min(TN, cover_hi - n0 + 1);
         group_sync(g);
-        for (int i = tid; i <= nn; i += TC_GROUP_THREADS) Gm.rp[i] = a.row_ptr[n0 + i];
+        for (int i = tid; i <= nn; i += TC_GROUP_THREADS) {
+            const int v = a.row_ptr[n0 + i];
+            Gm.rp[i] = min(max(v, E0), E1);
+            if (i == 0) Gm.split_lo = v < E0;
+            if (i == nn) Gm.split_hi = v > E1;
+        }
         for (int i = tid; i < nn * 3; i += TC_GROUP_THREADS) (&Gm.xsum[0][0])[i] = 0.0f;
         group_sync(g);
         const int e0 = Gm.rp[0], e1 = Gm.rp[nn];
-        const int n_chunks = max(1, (e1 - e0 + TE - 1) / TE);
-        for (int ch = 0; ch < n_chunks; ++ch) {
-            const int c0 = e0 + ch * TE;
-            const int ne = min(TE, e1 - c0);
+        {
+            const int c0 = e0;
+            const int ne = e1 - e0;      // <= 128: one MMA tile
             if (ne > 0) {
                 // ---- stage 0: geometry, one thread per edge ----
                 if (tid < ne) {
@@ -368,14 +388,10 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                         s0 = fmaf(al, m0, s0);
                         s1 = fmaf(al, m1, s1);
                     }
-                    float2 *dst = reinterpret_cast<float2 *>(
-                        a.M + (size_t)(n0 + nl) * TC_K + 2 * lane);
-                    if (ch == 0) {
-                        *dst = make_float2(s0, s1);
-                    } else if (hi > lo) {
-                        float2 old = *dst;
-                        *dst = make_float2(old.x + s0, old.y + s1);
-                    }
+                    float *row = a.M + (size_t)(n0 + nl) * TC_K;
+                    if (nl == 0 && Gm.split_lo) row = a.Mpart + ((size_t)t * 2) * TC_K;
+                    else if (nl == nn - 1 && Gm.split_hi) row = a.Mpart + ((size_t)t * 2 + 1) * TC_K;
+                    *reinterpret_cast<float2 *>(row + 2 * lane) = make_float2(s0, s1);
                 }
             }
             // ---- messages out (edge residual of the next layer / softmax) ----
@@ -447,23 +463,65 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
         }
         if (a.x_out != nullptr && tid < nn) {
             const int i = n0 + tid;
-            const int cnt = Gm.rp[tid + 1] - Gm.rp[tid];
-            const float inv = 1.0f / (float)(cnt > 0 ? cnt : 1);
-            float ax = 0.f, ay = 0.f, az = 0.f;
-            if (f_coords) {
-                ax = Gm.xsum[tid][0] * inv;
-                ay = Gm.xsum[tid][1] * inv;
-                az = Gm.xsum[tid][2] * inv;
+            const bool sp_lo = tid == 0 && Gm.split_lo;
+            const bool sp_hi = tid == nn - 1 && Gm.split_hi;
+            if (sp_lo || sp_hi) {
+                float *xp = a.xpart + ((size_t)t * 2 + (sp_lo ? 0 : 1)) * 4;
+                xp[0] = Gm.xsum[tid][0];
+                xp[1] = Gm.xsum[tid][1];
+                xp[2] = Gm.xsum[tid][2];
+            } else {
+                const int cnt = Gm.rp[tid + 1] - Gm.rp[tid];
+                const float inv = 1.0f / (float)(cnt > 0 ? cnt : 1);
+                float ax = 0.f, ay = 0.f, az = 0.f;
+                if (f_coords) {
+                    ax = Gm.xsum[tid][0] * inv;
+                    ay = Gm.xsum[tid][1] * inv;
+                    az = Gm.xsum[tid][2] * inv;
+                }
+                a.x_out[3 * i] = a.x_in[3 * i] + ax;
+                a.x_out[3 * i + 1] = a.x_in[3 * i + 1] + ay;
+                a.x_out[3 * i + 2] = a.x_in[3 * i + 2] + az;
             }
-            a.x_out[3 * i] = a.x_in[3 * i] + ax;
-            a.x_out[3 * i + 1] = a.x_in[3 * i + 1] + ay;
-            a.x_out[3 * i + 2] = a.x_in[3 * i + 2] + az;
         }
+        }   // node windows of the tile
     }
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32) tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+}
+
+// Nodes cut by tile boundaries: the tile where such a node STARTS owns its
+// reduction and adds the partials of the following tiles in tile order.
+__global__ void __launch_bounds__(256)
+edge_tile_fixup_kernel(const EdgeArgs a, int do_m, int do_x) {
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int n_tiles = *a.n_ptiles;
+    if (t >= n_tiles - 1) return;                  // the last tile has no successor
+    const int E_total = a.row_ptr[a.n_nodes];
+    const int E0 = t * TE, E1 = min(E0 + TE, E_total);
+    const int b = a.ptile_last[t];
+    const int eb0 = a.row_ptr[b], eb1 = a.row_ptr[b + 1];
+    if (eb1 <= E1) return;                         // the node ends in this tile
+    if (eb0 < E0) return;                          // it started earlier: not the owner
+    float2 s = make_float2(0.f, 0.f);
+    float xs = 0.f;
+    if (do_m) s = *reinterpret_cast<const float2 *>(a.Mpart + ((size_t)t * 2 + 1) * TC_K + 2 * lane);
+    if (do_x && lane < 3) xs = a.xpart[((size_t)t * 2 + 1) * 4 + lane];
+    for (int tt = t + 1; tt < n_tiles; ++tt) {
+        if (do_m) {
+            const float2 p = *reinterpret_cast<const float2 *>(
+                a.Mpart + ((size_t)tt * 2) * TC_K + 2 * lane);
+            s.x += p.x;
+            s.y += p.y;
+        }
+        if (do_x && lane < 3) xs += a.xpart[((size_t)tt * 2) * 4 + lane];
+        if (eb1 <= min((tt + 1) * TE, E_total)) break;
+    }
+    if (do_m) *reinterpret_cast<float2 *>(a.M + (size_t)b * TC_K + 2 * lane) = s;
+    if (do_x && lane < 3)
+        a.x_out[3 * b + lane] = a.x_in[3 * b + lane] + xs / (float)(eb1 - eb0);
 }
 
 #ifdef PVS_PHASE_PROF
@@ -478,10 +536,13 @@ extern "C" int pvs_debug_phase_cycles(unsigned long long *out, int reset) {
 }
 #endif
 
-int launch_edge_tc(const EdgeArgs &a, int n_tiles_cap, int mode, cudaStream_t st) {
+int launch_edge_tc(const EdgeArgs &a, int n_ptiles_cap, int mode, cudaStream_t st) {
+    if (a.ptile_last == nullptr || a.n_ptiles == nullptr || a.Mpart == nullptr ||
+        a.xpart == nullptr)
+        return PVS_ERR_INVALID_ARG;   // the tcgen05 kernel walks edge-packed tiles
     const size_t smem = sizeof(TcSmem);
     int grid = num_sms();   // one persistent CTA (5 groups) per SM
-    const int need = (n_tiles_cap + TC_GROUPS - 1) / TC_GROUPS;
+    const int need = (n_ptiles_cap + TC_GROUPS - 1) / TC_GROUPS;
     if (need < grid) grid = need;
     if (grid < 1) grid = 1;
     int rc;
@@ -494,7 +555,11 @@ int launch_edge_tc(const EdgeArgs &a, int n_tiles_cap, int mode, cudaStream_t st
         if (rc) return rc;
         egnn_edge_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(a);
     }
-    return check_launch();
+    const bool softmax = (a.flags & PVS_F_EDGE_ATTENTION) && (a.flags & PVS_F_SOFTMAX_ATTENTION);
+    const int do_m = softmax ? 0 : 1, do_x = a.x_out != nullptr ? 1 : 0;
+    if (do_m || do_x)
+        edge_tile_fixup_kernel<<<(n_ptiles_cap + 7) / 8, 256, 0, st>>>(a, do_m, do_x);
+    return check_launch(do_m || do_x ? 2 : 1);
 }
 
 }  // namespace pvs

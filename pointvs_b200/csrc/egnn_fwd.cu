@@ -686,6 +686,11 @@ static FwdWorkspace carve_workspace(void *base, int n, int e, int kp, uint32_t f
         w.m_ws = take((int64_t)e * kp);
         w.z_ws = take((int64_t)e);
     }
+    {
+        const int64_t tcap = pvs_packed_tiles_capacity(e);
+        w.Mpart = take(tcap * 2 * 64);
+        w.xpart = take(tcap * 2 * 4);
+    }
     w.bytes = p - (char *)base;
     return w;
 }
@@ -741,6 +746,8 @@ int fwd_recompute(const pvs_graph *g, const pvs_layer_config *cfg, const pvs_lay
     EdgeArgs ea{};
     ea.row_ptr = g->row_ptr; ea.col = g->col; ea.tile_ptr = g->tile_ptr;
     ea.n_tiles = g->n_tiles; ea.attr = cfg->n_edge_classes > 0 ? g->attr : nullptr;
+    ea.ptile_last = g->ptile_last; ea.n_ptiles = g->n_ptiles; ea.n_nodes = n;
+    ea.Mpart = w.Mpart; ea.xpart = w.xpart;
     ea.P = w.P; ea.Q = w.Q; ea.x_in = x_in; ea.m_prev = m_prev; ea.M = w.M;
     ea.x_out = nullptr;
     ea.m_out = softmax ? w.m_ws : nullptr; ea.ld_m = 64;
@@ -752,7 +759,7 @@ int fwd_recompute(const pvs_graph *g, const pvs_layer_config *cfg, const pvs_lay
     ea.att_w = p->att_w; ea.att_b = p->att_b; ea.edge_gate = p->edge_gate;
     ea.k = k; ea.in_e = in_e; ea.n_classes = cfg->n_edge_classes;
     ea.flags = f; ea.att_act = cfg->att_act;
-    rc = tc ? launch_edge_tc(ea, g->n_tiles_cap, cfg->math, st)
+    rc = tc ? launch_edge_tc(ea, g->n_ptiles_cap, cfg->math, st)
             : launch_edge<64>(ea, g->n_tiles_cap, st);
     if (rc) return rc;
     if (softmax) {
@@ -826,6 +833,8 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
         return PVS_ERR_INVALID_ARG;
     if (g->n_nodes < 0 || g->n_edges < 0) return PVS_ERR_INVALID_ARG;
     if (g->n_nodes == 0) return PVS_OK;
+    if (cfg->math != PVS_MATH_FP32 && (!g->ptile_last || !g->n_ptiles))
+        return PVS_ERR_INVALID_ARG;   // tcgen05 edge kernel: pvs_build_packed_tiles
     if (!g->row_ptr || !g->tile_ptr || !g->n_tiles || (g->n_edges > 0 && !g->col))
         return PVS_ERR_INVALID_ARG;
     if (cfg->n_edge_classes > 0 && g->n_edges > 0 && !g->attr) return PVS_ERR_INVALID_ARG;
@@ -883,6 +892,8 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
     EdgeArgs ea{};
     ea.row_ptr = g->row_ptr; ea.col = g->col; ea.tile_ptr = g->tile_ptr;
     ea.n_tiles = g->n_tiles; ea.attr = cfg->n_edge_classes > 0 ? g->attr : nullptr;
+    ea.ptile_last = g->ptile_last; ea.n_ptiles = g->n_ptiles; ea.n_nodes = n;
+    ea.Mpart = w.Mpart; ea.xpart = w.xpart;
     ea.P = w.P; ea.Q = w.Q; ea.x_in = x_in; ea.m_prev = m_prev; ea.M = w.M;
     ea.x_out = x_out;
     ea.m_out = m_out; ea.ld_m = k;
@@ -901,7 +912,7 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
     ea.flags = f; ea.att_act = cfg->att_act;
     if (stages & PVS_STAGE_EDGE) {
     if (cfg->ev_edge_begin) cudaEventRecord((cudaEvent_t)cfg->ev_edge_begin, st);
-    if (tc) rc = launch_edge_tc(ea, g->n_tiles_cap, cfg->math, st);
+    if (tc) rc = launch_edge_tc(ea, g->n_ptiles_cap, cfg->math, st);
     else rc = kp == 32 ? launch_edge<32>(ea, g->n_tiles_cap, st)
                        : launch_edge<64>(ea, g->n_tiles_cap, st);
     if (rc) return rc;

@@ -708,6 +708,29 @@ int pvs_radius_graph_count(const double *coords, const int32_t *bp,
     return exclusive_scan(deg, n_nodes, row_ptr, scratch, st);
 }
 
+// Edge-packed tiles: tile t owns edges [128 t, min(128 t + 128, E)); last[t] is
+// the node that holds its last edge (for E = 0 the single tile spans no edge and
+// last[0] = n_nodes - 1).  One thread per tile: binary search in row_ptr.
+__global__ void packed_tiles_kernel(const int32_t *__restrict__ row_ptr, int n_nodes, int cap,
+                                    int32_t *__restrict__ last, int32_t *__restrict__ n_ptiles) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int E = row_ptr[n_nodes];
+    int T = (E + PVS_TILE_EDGES - 1) / PVS_TILE_EDGES;
+    if (T < 1) T = 1;
+    if (T > cap) T = cap;
+    if (t == 0) *n_ptiles = T;
+    if (t >= T) return;
+    if (E == 0) { last[t] = n_nodes > 0 ? n_nodes - 1 : 0; return; }
+    const int e = min((t + 1) * PVS_TILE_EDGES, E) - 1;   // last edge of the tile
+    // largest node i with row_ptr[i] <= e
+    int lo = 0, hi = n_nodes;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (row_ptr[mid] <= e) lo = mid; else hi = mid;
+    }
+    last[t] = lo;
+}
+
 // After a capacity-bounded fill: no consumer may index past col/attr, so the
 // offsets are cut at the capacity (a no-op unless *overflow was raised).
 __global__ void clamp_row_ptr_kernel(int32_t *row_ptr, int n, int cap) {
@@ -770,6 +793,20 @@ int pvs_prune_mask(const int32_t *row_ptr, const int32_t *col,
     if (!row_ptr || !n_inter || !complex_ptr || !keep) return PVS_ERR_INVALID_ARG;
     prune_mask_kernel<<<n_complexes, 256, 0, (cudaStream_t)stream>>>(
         row_ptr, col, n_inter, complex_ptr, keep);
+    return check_launch();
+}
+
+int32_t pvs_packed_tiles_capacity(int32_t n_edges) {
+    return (int32_t)((int64_t)n_edges / PVS_TILE_EDGES + 2);
+}
+
+int pvs_build_packed_tiles(const int32_t *row_ptr, int32_t n_nodes, int32_t n_edges,
+                           int32_t *ptile_last, int32_t *n_ptiles, void *stream) {
+    if (n_nodes < 0 || n_edges < 0 || !row_ptr || !ptile_last || !n_ptiles)
+        return PVS_ERR_INVALID_ARG;
+    const int cap = pvs_packed_tiles_capacity(n_edges);
+    packed_tiles_kernel<<<(cap + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        row_ptr, n_nodes, cap, ptile_last, n_ptiles);
     return check_launch();
 }
 

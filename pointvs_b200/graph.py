@@ -79,11 +79,22 @@ class CSRGraph:
         check(h.pvs_build_tiles(ptr(self.row_ptr), self.n_nodes,
                                 ptr(self.tile_ptr), ptr(self.n_tiles),
                                 ptr(scratch), stream()), 'pvs_build_tiles')
+        # edge-packed tiles for the tcgen05 edge kernel
+        pcap = int(h.pvs_packed_tiles_capacity(self.n_edges))
+        self.n_ptiles_cap = pcap
+        self.ptile_last = torch.empty(pcap, dtype=torch.int32, device=dev)
+        self.n_ptiles = torch.empty(1, dtype=torch.int32, device=dev)
+        check(h.pvs_build_packed_tiles(
+            ptr(self.row_ptr), self.n_nodes, self.n_edges,
+            ptr(self.ptile_last), ptr(self.n_ptiles), stream()),
+            'pvs_build_packed_tiles')
 
     def c_struct(self):
         return _cabi.Graph(self.n_nodes, self.n_edges, ptr(self.row_ptr),
                            ptr(self.col), ptr(self.attr), ptr(self.tile_ptr),
-                           ptr(self.n_tiles), self.n_tiles_cap)
+                           ptr(self.n_tiles), self.n_tiles_cap,
+                           ptr(self.ptile_last), ptr(self.n_ptiles),
+                           self.n_ptiles_cap)
 
     # -- orderings -------------------------------------------------------
     def rows(self):

@@ -150,3 +150,54 @@ def test_tc_graphnorm_node_stage_vs_oracle(k, ragged):
     out.sum().backward()
     g = model.layers[1].node_mlp[1].weight.grad
     assert g is not None and torch.isfinite(g).all() and g.abs().max() > 0
+
+
+@pytest.mark.parametrize('softmax', [False, True])
+def test_tc_packed_tiles_split_nodes_and_edgeless_runs(softmax):
+    """The tcgen05 edge kernel walks edge-packed tiles: nodes cut by a tile
+    boundary (every 128 edges), hubs spanning several tiles, and runs of more
+    than 128 edgeless nodes inside a tile's node range."""
+    from oracle import egnn_oracle
+    from pointvs_b200 import EGNNLayer
+    torch.manual_seed(11)
+    gen = torch.Generator().manual_seed(3)
+    n = 900
+    rows, cols = [], []
+    # nodes 0..199: ring neighbourhoods of degree 6 (tile boundaries fall
+    # inside nodes); node 200: hub with 330 edges; 201..560 edgeless; then a
+    # second dense block, and an edgeless tail
+    for i in range(200):
+        for d in (1, 2, 3):
+            rows += [i, i]
+            cols += [(i + d) % 200, (i - d) % 200]
+    for j in range(330):
+        rows.append(200)
+        cols.append(561 + j % 300)
+    for i in range(561, 861):
+        for d in (1, 2, 5, 7, 11):
+            rows.append(i)
+            cols.append(561 + (i - 561 + d) % 300)
+    ei = torch.tensor([rows, cols], dtype=torch.long)
+    ei = ei[:, torch.randperm(ei.shape[1], generator=gen)]   # caller order
+    ea = torch.nn.functional.one_hot(
+        torch.randint(0, 3, (ei.shape[1],), generator=gen), 3)
+    h = torch.randn(n, 48, generator=gen)
+    x = torch.randn(n, 3, generator=gen) * 4
+    layer = EGNNLayer(48, 48, 48, edges_in_d=3, edge_attention=True,
+                      normalize=True, tanh=True, softmax_attention=softmax,
+                      math='bf16x3').cuda()
+    with torch.no_grad():
+        layer.coord_mlp[2].weight.mul_(300.0)
+        h2, x2, _, m2 = layer(h.cuda(), ei.cuda(), x.clone().cuda(), ea.cuda())
+    sd = {'l.' + k: v.detach().cpu() for k, v in layer.state_dict().items()}
+    cfg = egnn_oracle.LayerConfig(residual=True, edge_attention=True,
+                                  normalize=True, tanh=True,
+                                  softmax_attention=softmax)
+    ho, xo, mo, _ = egnn_oracle.layer_forward(sd, 'l.', cfg, h, ei[0], ei[1],
+                                              x, ea)
+    assert helpers.scaled_err(h2.cpu().numpy(), ho.numpy()) < 1e-4
+    assert helpers.scaled_err(x2.cpu().numpy(), xo.numpy()) < 1e-4
+    assert helpers.scaled_err(m2.cpu().numpy(), mo.numpy()) < 1e-4
+    # edgeless nodes keep their coordinates exactly
+    assert torch.equal(x2[201:561].cpu(), x[201:561])
+    assert torch.equal(x2[861:].cpu(), x[861:])
