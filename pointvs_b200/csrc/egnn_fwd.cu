@@ -835,7 +835,9 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
     if (g->n_nodes == 0) return PVS_OK;
     if (cfg->math != PVS_MATH_FP32 && (!g->ptile_last || !g->n_ptiles))
         return PVS_ERR_INVALID_ARG;   // tcgen05 edge kernel: pvs_build_packed_tiles
-    if (!g->row_ptr || !g->tile_ptr || !g->n_tiles || (g->n_edges > 0 && !g->col))
+    if (cfg->math == PVS_MATH_FP32 && (!g->tile_ptr || !g->n_tiles))
+        return PVS_ERR_INVALID_ARG;   // FFMA edge kernel: pvs_build_tiles
+    if (!g->row_ptr || (g->n_edges > 0 && !g->col))
         return PVS_ERR_INVALID_ARG;
     if (cfg->n_edge_classes > 0 && g->n_edges > 0 && !g->attr) return PVS_ERR_INVALID_ARG;
     if (!h_in || !x_in || !h_out || !workspace) return PVS_ERR_INVALID_ARG;

@@ -102,7 +102,8 @@ class _EGNNLayerFn(torch.autograd.Function):
         natt = torch.empty((n,), dtype=torch.float32, device=dev) \
             if (want_side and layer.node_attention) else None
         ws = _workspace(cfg, n, e, dev)
-        g = csr.c_struct()
+        tc = layer.math != 'fp32'
+        g = csr.c_struct(node_tiles=not tc, packed_tiles=tc)
         timer = STAGE_TIMER
         split = timer is not None and getattr(timer, 'split_stages', True)
         if timer is not None and not split:
@@ -497,7 +498,9 @@ class PNNGeometricBase(PointNeuralNetworkBase):
         ws = _cabi.scratch('model_fwd', nbytes, dev)
         scores = torch.empty((n_graphs, dim_out), dtype=torch.float32,
                              device=dev)
-        g = csr.c_struct()
+        maths = [l.math for l in self.layers if isinstance(l, EGNNLayer)]
+        g = csr.c_struct(node_tiles='fp32' in maths,
+                         packed_tiles=any(m != 'fp32' for m in maths))
         with torch.cuda.device(dev):
             check(h.pvs_egnn_model_fwd(
                 C.byref(g), C.byref(desc), ptr(feats), feats.shape[1],

@@ -43,7 +43,12 @@ class CSRGraph:
         self.exact_edge_count = True
         self.n_edges_dev = None
         self._overflow = None
-        self._build_tiles()
+        # work-tile partitions, built on first use: node-aligned tiles for the
+        # FFMA kernels and the backward, edge-packed tiles for tcgen05
+        self.tile_ptr = self.n_tiles = None
+        self.n_tiles_cap = 0
+        self.ptile_last = self.n_ptiles = None
+        self.n_ptiles_cap = 0
 
     def check_overflow(self):
         """Host sync: raise if a capacity-bounded build dropped edges."""
@@ -67,7 +72,7 @@ class CSRGraph:
             self.col, self.attr = self.col[:e], self.attr[:e]
             self.exact_edge_count = True
 
-    def _build_tiles(self):
+    def _build_node_tiles(self):
         h = lib()
         dev = self.device
         cap = h.pvs_tiles_capacity(self.n_nodes, self.n_edges)
@@ -76,20 +81,32 @@ class CSRGraph:
         self.n_tiles = torch.zeros(1, dtype=torch.int32, device=dev)
         scratch = _cabi.scratch(
             'tiles', max(1, int(h.pvs_tiles_scratch_bytes(self.n_nodes))), dev)
-        check(h.pvs_build_tiles(ptr(self.row_ptr), self.n_nodes,
-                                ptr(self.tile_ptr), ptr(self.n_tiles),
-                                ptr(scratch), stream()), 'pvs_build_tiles')
-        # edge-packed tiles for the tcgen05 edge kernel
+        with torch.cuda.device(dev):
+            check(h.pvs_build_tiles(ptr(self.row_ptr), self.n_nodes,
+                                    ptr(self.tile_ptr), ptr(self.n_tiles),
+                                    ptr(scratch), stream()), 'pvs_build_tiles')
+
+    def _build_packed_tiles(self):
+        h = lib()
+        dev = self.device
         pcap = int(h.pvs_packed_tiles_capacity(self.n_edges))
         self.n_ptiles_cap = pcap
         self.ptile_last = torch.empty(pcap, dtype=torch.int32, device=dev)
         self.n_ptiles = torch.empty(1, dtype=torch.int32, device=dev)
-        check(h.pvs_build_packed_tiles(
-            ptr(self.row_ptr), self.n_nodes, self.n_edges,
-            ptr(self.ptile_last), ptr(self.n_ptiles), stream()),
-            'pvs_build_packed_tiles')
+        with torch.cuda.device(dev):
+            check(h.pvs_build_packed_tiles(
+                ptr(self.row_ptr), self.n_nodes, self.n_edges,
+                ptr(self.ptile_last), ptr(self.n_ptiles), stream()),
+                'pvs_build_packed_tiles')
 
-    def c_struct(self):
+    def c_struct(self, node_tiles=True, packed_tiles=True):
+        """struct pvs_graph.  node_tiles / packed_tiles say which work-tile
+        partitions the callee needs (FFMA kernels and every backward: node
+        tiles; tcgen05 forward: packed tiles); each is built once."""
+        if node_tiles and self.tile_ptr is None:
+            self._build_node_tiles()
+        if packed_tiles and self.ptile_last is None:
+            self._build_packed_tiles()
         return _cabi.Graph(self.n_nodes, self.n_edges, ptr(self.row_ptr),
                            ptr(self.col), ptr(self.attr), ptr(self.tile_ptr),
                            ptr(self.n_tiles), self.n_tiles_cap,
