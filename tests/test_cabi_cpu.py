@@ -67,7 +67,7 @@ def test_structs_match_header_layout():
     assert C.sizeof(_cabi.LayerConfig) == 6 * 4 + 2 * 8
     assert C.sizeof(_cabi.LayerParams) == 20 * 8
     assert C.sizeof(_cabi.LayerGrads) == 20 * 8
-    assert C.sizeof(_cabi.Graph) == 8 + 5 * 8 + 8
+    assert C.sizeof(_cabi.Graph) == 8 + 5 * 8 + 8 + 2 * 8 + 8
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -199,6 +199,7 @@ def test_tile_partition(radii):
     from pointvs_b200.synthetic import synthetic_batch
     coords, bp, _, cptr = synthetic_batch(7, 5, ragged=True)
     g = radius_graph_batch(coords, bp, cptr, *radii)
+    g.c_struct()                      # tile partitions are built on first use
     t = int(g.n_tiles.item())
     assert 0 < t <= g.n_tiles_cap
     tp = g.tile_ptr.cpu().numpy()[:t + 1]
@@ -212,6 +213,15 @@ def test_tile_partition(radii):
     merged_e = edges[:-1] + edges[1:]
     merged_n = nodes[:-1] + nodes[1:]
     assert np.all(~same_chunk | (merged_e > 128) | (merged_n > 128))
+    # edge-packed tiles of the tcgen05 kernel: tile t owns edges
+    # [128 t, 128 t + 128); last[t] is the node of its last edge
+    e = int(rp[-1])
+    tpk = int(g.n_ptiles.item())
+    assert tpk == max(1, -(-e // 128)) and tpk <= g.n_ptiles_cap
+    last = g.ptile_last.cpu().numpy()[:tpk]
+    row_of = np.repeat(np.arange(g.n_nodes), np.diff(rp))
+    want = row_of[np.minimum(128 * (np.arange(tpk) + 1), e) - 1]
+    np.testing.assert_array_equal(last, want)
 
 
 def test_high_degree_node_gets_own_tile():
@@ -221,6 +231,7 @@ def test_high_degree_node_gets_own_tile():
     others = torch.arange(1, n)
     ei = torch.cat([torch.stack([hub, others]), torch.stack([others, hub])], 1)
     csr = csr_from_edge_index(ei.cuda(), None, n)
+    csr.c_struct()
     t = int(csr.n_tiles.item())
     tp = csr.tile_ptr.cpu().numpy()[:t + 1]
     assert tp[0] == 0 and tp[1] == 1 and tp[-1] == n
