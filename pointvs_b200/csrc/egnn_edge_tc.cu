@@ -368,30 +368,54 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                     issue_gemm<X3>(tmem_grp, 0, A_hi, A_lo, S.Wc1_hi, S.Wc1_lo, &Gm.mbar);
                 }
             }
-            // ---- M_i = sum_e alpha_e m_e over dst segments (warp per node) ----
+            // ---- M_i = sum_e alpha_e m_e over dst segments: a warp per node,
+            // four edges a step (8 lanes per edge row, one 16-byte chunk of the
+            // hi and of the lo tile each), partial sums folded by two shuffles.
+            // The order of the additions is fixed, so the sums are reproducible.
             if (!f_softmax) {
+                const int es = lane >> 3, cc = lane & 7;
                 for (int nl = warp; nl < nn; nl += TC_GROUP_THREADS / 32) {
-                    const int lo = max(Gm.rp[nl], c0) - c0;
-                    const int hi = min(Gm.rp[nl + 1], c0 + TE) - c0;
-                    float s0 = 0.0f, s1 = 0.0f;
-                    for (int el = lo; el < hi; ++el) {
-                        const uint32_t off = swz(el, lane >> 2) + ((lane & 3) << 2);
-                        const uint32_t h = *reinterpret_cast<const uint32_t *>(A_hi + off);
-                        float m0 = __uint_as_float(h << 16);
-                        float m1 = __uint_as_float(h & 0xffff0000u);
-                        if (X3) {
-                            const uint32_t l = *reinterpret_cast<const uint32_t *>(A_lo + off);
-                            m0 += __uint_as_float(l << 16);
-                            m1 += __uint_as_float(l & 0xffff0000u);
-                        }
+                    const int lo = Gm.rp[nl] - c0, hi = Gm.rp[nl + 1] - c0;
+                    float2 s[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) s[i] = make_float2(0.0f, 0.0f);
+                    for (int el = lo + es; el < hi; el += 4) {
+                        const uint32_t off = swz(el, cc);
+                        const uint4 h = *reinterpret_cast<const uint4 *>(A_hi + off);
                         const float al = Gm.e_z[el];
-                        s0 = fmaf(al, m0, s0);
-                        s1 = fmaf(al, m1, s1);
+                        const float2 al2 = make_float2(al, al);
+                        const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+                        float2 m[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            m[i] = make_float2(__uint_as_float(hw[i] << 16),
+                                               __uint_as_float(hw[i] & 0xffff0000u));
+                        if (X3) {
+                            const uint4 l = *reinterpret_cast<const uint4 *>(A_lo + off);
+                            const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                m[i] = fadd2(m[i], make_float2(__uint_as_float(lw[i] << 16),
+                                                               __uint_as_float(lw[i] & 0xffff0000u)));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) s[i] = ffma2(al2, m[i], s[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        s[i].x += __shfl_xor_sync(0xffffffffu, s[i].x, 8);
+                        s[i].y += __shfl_xor_sync(0xffffffffu, s[i].y, 8);
+                        s[i].x += __shfl_xor_sync(0xffffffffu, s[i].x, 16);
+                        s[i].y += __shfl_xor_sync(0xffffffffu, s[i].y, 16);
                     }
                     float *row = a.M + (size_t)(n0 + nl) * TC_K;
                     if (nl == 0 && Gm.split_lo) row = a.Mpart + ((size_t)t * 2) * TC_K;
                     else if (nl == nn - 1 && Gm.split_hi) row = a.Mpart + ((size_t)t * 2 + 1) * TC_K;
-                    *reinterpret_cast<float2 *>(row + 2 * lane) = make_float2(s0, s1);
+                    if (es == 0) {
+                        float4 *dst = reinterpret_cast<float4 *>(row + 8 * cc);
+                        dst[0] = make_float4(s[0].x, s[0].y, s[1].x, s[1].y);
+                        dst[1] = make_float4(s[2].x, s[2].y, s[3].x, s[3].y);
+                    }
                 }
             }
             // ---- messages out (edge residual of the next layer / softmax) ----
