@@ -39,7 +39,7 @@ FLOP_PER_EDGE_LAYER = 2 * (4 * 64 * 64 + 6 * 64)      # 33 536
 FLOP_PER_NODE_LAYER = 2 * (3 * 64 * 64 + 64)          # 24 704
 BYTES_PER_COMPLEX_FWD = 4.94e6
 EXTRA_WARMUP = 10           # untimed steps beyond --warmup (see run_ours)
-NCU_EDGE_TRAFFIC_BYTES = 77.57e6 + 15.06e6   # profiles/r01_d_edge_tc_ncu_full.csv
+NCU_EDGE_TRAFFIC_BYTES = 77.79e6 + 12.36e6   # profiles/r01_h_prof_edge_ncu_full.csv
 
 
 def parse_args():
@@ -471,7 +471,7 @@ def run_ours(args):
         'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf,
         'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf,
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel,
-        # ncu --set full, profiles/r01_d_edge_tc_ncu_full.csv (tcgen05 modes, the
+        # ncu --set full, profiles/r01_h_prof_edge_ncu_full.csv (tcgen05 modes, the
         # default batch); null for other configurations
         'traffic': NCU_EDGE_TRAFFIC_BYTES if (args.math != 'fp32' and args.batch == 128
                                               and args.atoms == 1000) else None,
