@@ -1,0 +1,94 @@
+"""Seeded differential sweep: random batch shapes (including one- and
+two-atom complexes and edgeless ones), radii and model options; every case is
+scored by the fp32 and the tcgen05 paths and compared with the CPU oracle on
+the edge list the device built (scores, final coordinates), and the edge list
+itself with the CPU oracle of `generate_edges`."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers
+from tests import gpu_helpers as gh
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(seed):
+    rng = np.random.default_rng(1000 + seed)
+    n_complexes = int(rng.integers(1, 7))
+    sizes = [int(rng.choice([1, 2, 3, 17, 60, 130, 260, 420]))
+             for _ in range(n_complexes)]
+    inter = float(rng.choice([2.5, 4.0, 5.5]))
+    intra = float(rng.choice([1.5, 2.0, inter]))
+    att = bool(rng.integers(0, 2))
+    kw = dict(dim_input=13, dim_output=int(rng.choice([1, 3])),
+              k=int(rng.choice([8, 16, 33, 48, 64])),
+              num_layers=int(rng.integers(1, 4)),
+              residual=bool(rng.integers(0, 2)),
+              edge_residual=bool(rng.integers(0, 2)),
+              edge_attention=att,
+              softmax_attention=att and bool(rng.integers(0, 2)),
+              node_attention=bool(rng.integers(0, 2)),
+              normalize=bool(rng.integers(0, 2)), tanh=bool(rng.integers(0, 2)),
+              graphnorm=bool(rng.integers(0, 2)),
+              update_coords=bool(rng.integers(0, 4) > 0),
+              permutation_invariance=bool(rng.integers(0, 4) == 0),
+              attention_activation_fn=str(rng.choice(['sigmoid', 'tanh', 'silu'])))
+    mode = int(rng.integers(0, 3))
+    kw['gated_residual'] = mode == 1
+    kw['rezero'] = mode == 2
+    return sizes, inter, intra, kw
+
+
+@pytest.mark.parametrize('seed', range(24))
+def test_random_configuration(seed):
+    import pointvs_b200 as pv
+    from oracle import radius_graph as rg
+    from pointvs_b200.synthetic import synthetic_complex
+    sizes, inter, intra, kw = _case(seed)
+    parts = [synthetic_complex(50 * seed + i, n, max(1, n // 10))
+             for i, n in enumerate(sizes)]
+    coords = np.concatenate([p[0] for p in parts])
+    bp = np.concatenate([p[1] for p in parts])
+    feats = np.concatenate([p[2] for p in parts])
+    cptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    graph = pv.PackedBatch.from_arrays(coords, bp, feats, cptr, inter, intra)
+    # edges against the CPU oracle, complex by complex, in CSR order
+    ei = graph.edge_index.cpu().numpy()
+    ea = graph.edge_attr.argmax(dim=1).cpu().numpy() if ei.shape[1] else \
+        np.zeros(0, dtype=np.int64)
+    off = 0
+    for b, n in enumerate(sizes):
+        s, e = cptr[b], cptr[b + 1]
+        _, row, col, attr = rg.radius_graph(coords[s:e], bp[s:e], inter, intra)
+        order = rg.csr_order(row, col, attr)
+        cnt = len(row)
+        np.testing.assert_array_equal(ei[0, off:off + cnt], row[order] + s)
+        np.testing.assert_array_equal(ei[1, off:off + cnt], col[order] + s)
+        np.testing.assert_array_equal(ea[off:off + cnt], attr[order])
+        off += cnt
+    assert off == ei.shape[1]
+    model = gh.build_model(kw, seed=seed, coord_gain=1.0)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if 'gate_parameter' in name:
+                p.fill_(0.37)
+            if 'node_mlp.1.' in name and kw['graphnorm']:
+                p.add_(0.2 * torch.randn_like(p))
+    pos0 = graph.pos.clone()
+    cpu = SimpleNamespace(x=graph.x, pos=pos0, edge_index=graph.edge_index,
+                          edge_attr=graph.edge_attr, batch=graph.batch)
+    want, x_want = gh.oracle_forward(model, kw, cpu)
+    want = want.numpy().reshape(-1)
+    scale = max(1e-3, float(np.abs(want).max()))
+    for math in ('fp32', 'bf16x3'):
+        model.set_math(math)
+        graph.pos = pos0.clone()
+        with torch.no_grad():
+            out = model(graph)
+        got = out.cpu().numpy().reshape(-1)
+        assert np.abs(got - want).max() <= 1e-4 * scale, (math, kw, sizes)
+        assert helpers.scaled_err(graph.pos.cpu().numpy(),
+                                  x_want.numpy()) < 1e-4, (math, kw, sizes)
