@@ -92,3 +92,58 @@ def test_random_configuration(seed):
         assert np.abs(got - want).max() <= 1e-4 * scale, (math, kw, sizes)
         assert helpers.scaled_err(graph.pos.cpu().numpy(),
                                   x_want.numpy()) < 1e-4, (math, kw, sizes)
+
+
+@pytest.mark.parametrize('seed', range(12))
+@pytest.mark.parametrize('math', ['fp32', 'bf16x3'])
+def test_random_configuration_gradients(seed, math):
+    """Same sweep for the backward: parameter and coordinate gradients of a
+    scalar loss against torch autograd through the CPU oracle.  Parameters the
+    oracle's autograd leaves untouched must have no gradient here either."""
+    import pointvs_b200 as pv
+    from oracle import egnn_oracle
+    from pointvs_b200.synthetic import synthetic_complex
+    from tests.test_gpu_backward import _close
+    sizes, inter, intra, kw = _case(100 + seed)
+    sizes = [min(s, 260) for s in sizes]
+    if kw['attention_activation_fn'] == 'relu':
+        kw['attention_activation_fn'] = 'sigmoid'
+    parts = [synthetic_complex(70 * seed + i, n, max(1, n // 10))
+             for i, n in enumerate(sizes)]
+    coords = np.concatenate([p[0] for p in parts])
+    bp = np.concatenate([p[1] for p in parts])
+    feats = np.concatenate([p[2] for p in parts])
+    cptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    graph = pv.PackedBatch.from_arrays(coords, bp, feats, cptr, inter, intra)
+    model = gh.build_model(kw, seed=seed, coord_gain=1.0).train()
+    model.set_math(math)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if 'gate_parameter' in name:
+                p.fill_(0.37)
+    w = torch.linspace(0.5, 1.5, len(sizes) * kw['dim_output'])
+    pos0 = graph.pos.clone()
+    graph.pos = pos0.clone().requires_grad_(True)
+    out = model(graph).reshape(-1)
+    (out * w.cuda()).sum().backward()
+
+    sd = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point())
+          for k, v in model.state_dict().items()}
+    pos_ref = pos0.cpu().clone().requires_grad_(True)
+    want, _ = egnn_oracle.model_forward(
+        sd, graph.x.cpu(), graph.edge_index.cpu(), pos_ref,
+        graph.edge_attr.cpu(), graph.batch.cpu(), num_layers=kw['num_layers'],
+        **helpers.oracle_kwargs(kw))
+    (want.reshape(-1) * w).sum().backward()
+    rtol = 2e-4 if math == 'fp32' else 5e-4
+    for pname, p in model.named_parameters():
+        ref = sd[pname].grad
+        if ref is None:
+            assert p.grad is None, (pname, kw)
+            continue
+        assert p.grad is not None, (pname, kw)
+        _close(p.grad.cpu().numpy(), ref.numpy(), f'{pname} {kw}', rtol=rtol,
+               atol=5e-6)
+    if pos_ref.grad is not None and graph.pos.grad is not None:
+        _close(graph.pos.grad.cpu().numpy(), pos_ref.grad.numpy(), f'pos {kw}',
+               rtol=rtol, atol=5e-6)
