@@ -486,6 +486,19 @@ class ComplexDataset:
     def __len__(self):
         return len(self.ligand_fnames)
 
+    # worker processes get a copy without locks, caches or device tensors
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state['_cache_lock'] = None
+        state['_cache'] = OrderedDict()
+        state['_rec_dev'] = OrderedDict()
+        state['sampler'] = None
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._cache_lock = threading.Lock()
+
     # edge radii exactly as PygPointCloudDataset.__getitem__ (:356-357)
     @property
     def inter_radius(self):
@@ -670,17 +683,87 @@ class ComplexDataset:
         return self.pack([item])
 
 
+_WORKER_DS = None
+
+
+def _worker_init(dataset):
+    global _WORKER_DS
+    _WORKER_DS = dataset
+
+
+def _worker_prepare(items):
+    """Runs in a loader process: host-side preparation of one mini-batch."""
+    return [_WORKER_DS.prepare(i) for i in items]
+
+
 class PackedLoader:
     """Iterates a ComplexDataset in mini-batches of PackedBatch (the role of
     `GeoDataLoader(ds, batch_size, False, sampler=..., drop_last=False)`,
-    data_loaders.py:514-519).  Parquet reading and cropping run on
-    `num_workers` host threads, `prefetch` batches ahead of the device."""
+    data_loaders.py:514-519).  Parquet reading (and the host crop, if that is
+    what the dataset uses) runs `prefetch` batches ahead of the device on
+    `num_workers` host threads, or -- `processes=True`, the counterpart of the
+    reference's DataLoader workers -- in that many spawned processes, which
+    do not share the interpreter lock."""
 
     def __init__(self, dataset, batch_size=32, sampler=None, num_workers=4,
-                 prefetch=2, edge_capacity=None):
+                 prefetch=2, edge_capacity=None, processes=False):
         self.dataset, self.batch_size, self.sampler = dataset, batch_size, sampler
         self.num_workers, self.prefetch = num_workers, max(1, prefetch)
         self.edge_capacity = edge_capacity
+        self.processes = bool(processes) and num_workers > 0
+        self._pool = None
+
+    def _process_pool(self):
+        if self._pool is None:
+            import multiprocessing as mp   # noqa: PLC0415
+            from concurrent.futures import ProcessPoolExecutor   # noqa: PLC0415
+            self._pool = ProcessPoolExecutor(
+                self.num_workers, mp_context=mp.get_context('spawn'),
+                initializer=_worker_init, initargs=(self.dataset,))
+        return self._pool
+
+    def close(self):
+        if self._pool is not None:
+            self._pool.shutdown(wait=False, cancel_futures=True)
+            self._pool = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # noqa: BLE001 - interpreter shutdown
+            pass
+
+    def prepared(self):
+        """(items, host-side prepared complexes) per mini-batch, in order --
+        everything that happens before the device is involved."""
+        batches = self._batches()
+        ds = self.dataset
+        if self.num_workers <= 0:
+            for items in batches:
+                yield items, [ds.prepare(i) for i in items]
+            return
+        if self.processes:
+            pool = self._process_pool()
+            depth = max(self.prefetch, self.num_workers)
+            pending, nxt = deque(), 0
+            while nxt < len(batches) or pending:
+                while nxt < len(batches) and len(pending) < depth:
+                    pending.append((batches[nxt],
+                                    pool.submit(_worker_prepare, batches[nxt])))
+                    nxt += 1
+                items, fut = pending.popleft()
+                yield items, fut.result()
+            return
+        with ThreadPoolExecutor(self.num_workers) as pool:
+            pending, nxt = deque(), 0
+            while nxt < len(batches) or pending:
+                while nxt < len(batches) and len(pending) < self.prefetch:
+                    items = batches[nxt]
+                    pending.append(
+                        (items, [pool.submit(ds.prepare, i) for i in items]))
+                    nxt += 1
+                items, futures = pending.popleft()
+                yield items, [f.result() for f in futures]
 
     def __len__(self):
         return math.ceil(len(self.dataset) / self.batch_size)
@@ -692,23 +775,9 @@ class PackedLoader:
                 for i in range(0, len(order), self.batch_size)]
 
     def __iter__(self):
-        batches = self._batches()
-        ds = self.dataset
-        if self.num_workers <= 0:
-            for items in batches:
-                yield ds.pack(items, edge_capacity=self.edge_capacity)
-            return
-        with ThreadPoolExecutor(self.num_workers) as pool:
-            pending, nxt = deque(), 0
-            while nxt < len(batches) or pending:
-                while nxt < len(batches) and len(pending) < self.prefetch:
-                    items = batches[nxt]
-                    pending.append(
-                        (items, [pool.submit(ds.prepare, i) for i in items]))
-                    nxt += 1
-                items, futures = pending.popleft()
-                yield ds.pack(items, [f.result() for f in futures],
-                              edge_capacity=self.edge_capacity)
+        for items, prepared in self.prepared():
+            yield self.dataset.pack(items, prepared,
+                                    edge_capacity=self.edge_capacity)
 
 
 def get_data_loader(data_root, dataset_class=None, receptors=None,
@@ -719,7 +788,8 @@ def get_data_loader(data_root, dataset_class=None, receptors=None,
                     fname_suffix='parquet', min_inactive_rms_distance=None,
                     types_fname=None, edge_radius=None, prune=False,
                     estimate_bonds=False, bp=None, p_noise=-1, num_workers=4,
-                    device=None, device_crop=False, **kwargs):
+                    device=None, device_crop=False, worker_processes=False,
+                    **kwargs):
     """Signature of the reference's `get_data_loader` (data_loaders.py:483-520).
     `dataset_class` is accepted for call compatibility and ignored: there is
     one dataset here.  As in the reference, classification training draws
@@ -740,7 +810,7 @@ def get_data_loader(data_root, dataset_class=None, receptors=None,
     sampler = ds.sampler if (ds.model_task == 'classification'
                              and mode == 'train') else None
     return PackedLoader(ds, batch_size, sampler=sampler,
-                        num_workers=num_workers)
+                        num_workers=num_workers, processes=worker_processes)
 
 
 __all__ = ['ComplexDataset', 'PackedLoader', 'get_data_loader',

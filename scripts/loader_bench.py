@@ -30,6 +30,8 @@ def main():
     ap.add_argument('--workers', type=int, default=8)
     ap.add_argument('--math', default='bf16x3')
     ap.add_argument('--host-crop', action='store_true')
+    ap.add_argument('--processes', action='store_true',
+                    help='loader workers are spawned processes, not threads')
     args = ap.parse_args()
     lines = [ln for ln in (COMPLEXES / 'pose.types').read_text().splitlines()
              if ln.strip()]
@@ -41,7 +43,8 @@ def main():
         dl = data.get_data_loader(
             COMPLEXES, types_fname=types, batch_size=args.batch_size,
             mode='val', rot=False, num_workers=args.workers, device='cuda',
-            device_crop=not args.host_crop, **cfg)
+            device_crop=not args.host_crop, worker_processes=args.processes,
+            **cfg)
         ds = dl.dataset
         torch.manual_seed(0)
         model = SartorrasEGNN(
@@ -69,13 +72,12 @@ def main():
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
 
-        # host-only: the loader threads without the device
+        # host-only: the loader workers without the device
         t0 = time.perf_counter()
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max(1, args.workers)) as pool:
-            list(pool.map(ds.prepare, range(len(ds))))
+        n_host = sum(len(items) for items, _ in dl.prepared())
         host = time.perf_counter() - t0
-
+        assert n_host == args.n
+        dl.close()
 
     print(json.dumps({
         'metric': 'complexes scored per second from types file + parquets',
@@ -83,6 +85,7 @@ def main():
         'n_complexes': args.n, 'atoms_per_complex': round(atoms / args.n, 1),
         'batch_size': args.batch_size, 'loader_threads': args.workers,
         'math': args.math, 'crop': 'host' if args.host_crop else 'device',
+        'workers': 'processes' if args.processes else 'threads',
         'host_loader_only_complexes_per_s': round(args.n / host, 1),
         'scores_finite': bool(torch.isfinite(scores).all())}))
 

@@ -145,3 +145,27 @@ def test_random_rotation_is_a_rotation():
     d0 = np.linalg.norm(x[:, None] - x[None], axis=-1)
     d1 = np.linalg.norm(y[:, None] - y[None], axis=-1)
     np.testing.assert_allclose(d0, d1, atol=1e-12)
+
+
+def test_loader_worker_processes_match_threads():
+    """processes=True (spawned loader workers, as the reference's DataLoader
+    workers) prepares exactly what the in-process path prepares, in order."""
+    for device_crop in (False, True):
+        ds = _dataset('atomic_h_r6_e3', device_crop=device_crop)
+        ref = list(data.PackedLoader(ds, batch_size=3, num_workers=0).prepared())
+        dl = data.PackedLoader(ds, batch_size=3, num_workers=2, processes=True)
+        try:
+            got = list(dl.prepared())
+        finally:
+            dl.close()
+        assert [i for i, _ in got] == [i for i, _ in ref]
+        for (_, a), (_, b) in zip(got, ref):
+            assert len(a) == len(b)
+            for x, y in zip(a, b):
+                np.testing.assert_array_equal(x.coords, y.coords)
+                if device_crop:
+                    np.testing.assert_array_equal(x.emit, y.emit)
+                    np.testing.assert_array_equal(x.code, y.code)
+                else:
+                    np.testing.assert_array_equal(x.feats, y.feats)
+                    np.testing.assert_array_equal(x.bp, y.bp)
