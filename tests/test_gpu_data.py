@@ -111,8 +111,10 @@ def test_inference_cli_scores_match_oracle_on_reference_graphs(
               graphnorm=True, edge_attention=True, node_attention=True,
               residual=True, normalize=True, tanh=True)
     run, model = _write_run(tmp_path, kw, cfg)
-    out = inference.main([str(run), str(ROOT / 'pose.types'), str(ROOT),
-                          '--math', math])
+    argv = [str(run), str(ROOT / 'pose.types'), str(ROOT), '--math', math]
+    if cfg == 'smina_wide_r7_bonds':      # spawned loader workers
+        argv += ['--workers', '2', '--worker_processes']
+    out = inference.main(argv)
     pose = out.parent / ('pose_' + out.name)
     lines = pose.read_text().splitlines()
     n = int(gold[f'{cfg}/n'])
