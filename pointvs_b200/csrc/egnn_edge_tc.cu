@@ -36,8 +36,14 @@ constexpr int TC_GROUP_THREADS = 128;
 #ifndef PVS_EXP_GROUPS
 #define PVS_EXP_GROUPS 5
 #endif
-constexpr int TC_GROUPS = PVS_EXP_GROUPS;
-constexpr int TC_THREADS = TC_GROUP_THREADS * TC_GROUPS;
+// The error-compensated mode needs a hi and a lo A tile per group (37.9 KB with
+// the per-group scalars): five groups fill the 227 KB of shared memory.  The
+// single-pass bf16 mode has no lo tiles, so eight groups (1024 threads, all 512
+// TMEM columns) fit.
+template <bool X3> struct TcCfg {
+    static constexpr int GROUPS = X3 ? PVS_EXP_GROUPS : 8;
+    static constexpr int THREADS = TC_GROUP_THREADS * GROUPS;
+};
 constexpr int TC_K = 64;          // padded hidden width of the tile
 constexpr uint32_t TC_TMEM_COLS = 512;   // whole TMEM: one CTA per SM
 constexpr uint32_t TC_GROUP_COLS = 64;   // D1 and D2 alias (never live together)
@@ -68,17 +74,19 @@ struct TcGroupMisc {
     uint64_t mbar;
 };
 
+template <bool X3>
 struct __align__(1024) TcSmem {
-    // swizzled bf16 tiles, each 1024-byte aligned
-    uint8_t A_hi[TC_GROUPS][TE * 128];
-    uint8_t A_lo[TC_GROUPS][TE * 128];
+    static constexpr int G = TcCfg<X3>::GROUPS;
+    // swizzled bf16 tiles, each 1024-byte aligned (lo tiles only where used)
+    uint8_t A_hi[G][TE * 128];
+    uint8_t A_lo[X3 ? G : 1][X3 ? TE * 128 : 1024];
     uint8_t W2_hi[TC_K * 128];
-    uint8_t W2_lo[TC_K * 128];
+    uint8_t W2_lo[X3 ? TC_K * 128 : 1024];
     uint8_t Wc1_hi[TC_K * 128];
-    uint8_t Wc1_lo[TC_K * 128];
+    uint8_t Wc1_lo[X3 ? TC_K * 128 : 1024];
     float b2[64], bc1[64], wc2[64], wa[64], wr[64];
     float T[PVS_MAX_EDGE_CLASSES][64];
-    TcGroupMisc grp[TC_GROUPS];
+    TcGroupMisc grp[G];
     uint32_t tmem_base;
 };
 
@@ -111,18 +119,19 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_base, uint32_t d_col,
 }
 
 template <bool X3>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TcCfg<X3>::THREADS, 1)
 egnn_edge_tc_kernel(const EdgeArgs a) {
     // SWIZZLE_128B tiles need 1024-byte alignment; the kernel has no static
     // shared memory, so the dynamic window starts at its (aligned) base.
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
-    TcSmem &S = *reinterpret_cast<TcSmem *>(smem_dyn);
+    constexpr int TC_GROUPS = TcCfg<X3>::GROUPS, TC_THREADS = TcCfg<X3>::THREADS;
+    TcSmem<X3> &S = *reinterpret_cast<TcSmem<X3> *>(smem_dyn);
     if ((smem_u32(smem_dyn) & 1023u) != 0u) __trap();
     const int g = threadIdx.x / TC_GROUP_THREADS;          // group
     const int tid = threadIdx.x % TC_GROUP_THREADS;        // thread in group
     const int lane = tid & 31, warp = tid >> 5;            // warp in group
     TcGroupMisc &Gm = S.grp[g];
-    uint8_t *A_hi = S.A_hi[g], *A_lo = S.A_lo[g];
+    uint8_t *A_hi = S.A_hi[g], *A_lo = S.A_lo[X3 ? g : 0];
     const int k = a.k;
     const bool f_att = a.flags & PVS_F_EDGE_ATTENTION;
     const bool f_softmax = f_att && (a.flags & PVS_F_SOFTMAX_ATTENTION);
@@ -564,20 +573,27 @@ int launch_edge_tc(const EdgeArgs &a, int n_ptiles_cap, int mode, cudaStream_t s
     if (a.ptile_last == nullptr || a.n_ptiles == nullptr || a.Mpart == nullptr ||
         a.xpart == nullptr)
         return PVS_ERR_INVALID_ARG;   // the tcgen05 kernel walks edge-packed tiles
-    const size_t smem = sizeof(TcSmem);
-    int grid = num_sms();   // one persistent CTA (5 groups) per SM
-    const int need = (n_ptiles_cap + TC_GROUPS - 1) / TC_GROUPS;
-    if (need < grid) grid = need;
-    if (grid < 1) grid = 1;
     int rc;
     if (mode == PVS_MATH_BF16X3) {
+        constexpr int G = TcCfg<true>::GROUPS;
+        const size_t smem = sizeof(TcSmem<true>);
+        int grid = num_sms();   // one persistent CTA per SM
+        const int need = (n_ptiles_cap + G - 1) / G;
+        if (need < grid) grid = need;
+        if (grid < 1) grid = 1;
         rc = ensure_smem(egnn_edge_tc_kernel<true>, smem);
         if (rc) return rc;
-        egnn_edge_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(a);
+        egnn_edge_tc_kernel<true><<<grid, TcCfg<true>::THREADS, smem, st>>>(a);
     } else {
+        constexpr int G = TcCfg<false>::GROUPS;
+        const size_t smem = sizeof(TcSmem<false>);
+        int grid = num_sms();
+        const int need = (n_ptiles_cap + G - 1) / G;
+        if (need < grid) grid = need;
+        if (grid < 1) grid = 1;
         rc = ensure_smem(egnn_edge_tc_kernel<false>, smem);
         if (rc) return rc;
-        egnn_edge_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(a);
+        egnn_edge_tc_kernel<false><<<grid, TcCfg<false>::THREADS, smem, st>>>(a);
     }
     const bool softmax = (a.flags & PVS_F_EDGE_ATTENTION) && (a.flags & PVS_F_SOFTMAX_ATTENTION);
     const int do_m = softmax ? 0 : 1, do_x = a.x_out != nullptr ? 1 : 0;
