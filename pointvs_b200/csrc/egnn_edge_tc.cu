@@ -4,7 +4,10 @@
 // 64x64 contractions (edge_mlp.2 and coord_mlp.0; reference
 // egnn_satorras.py:76-80, 88-96) run as tcgen05.mma tiles:
 //
-//   tile      : 128 dst-sorted edges (UMMA M = 128, cta_group::1), N = 64, K = 64
+//   tile      : 128 dst-sorted edges (UMMA M = 128, cta_group::1), N = 64, K = 64;
+//               edge-packed (pvs_build_packed_tiles): tile t = edges
+//               [128 t, 128 t + 128), nodes cut by a tile boundary go through
+//               per-tile partial slots and edge_tile_fixup_kernel
 //   A operand : activations written by the CTA's threads into shared memory in
 //               the canonical K-major SWIZZLE_128B layout (one 128-byte row per
 //               edge), as a bf16 hi tile and, for BF16X3, a bf16 lo tile
@@ -19,7 +22,8 @@
 //               shared memory; the coordinate GEMM overlaps the message
 //               segment-reduce.
 //
-// One persistent CTA per SM holds G = 5 independent 4-warp groups (640 threads).
+// One persistent CTA per SM holds G independent 4-warp groups (5 in the
+// error-compensated mode, 8 in the single-pass bf16 mode: see TcCfg).
 // The groups share the weight tiles and each own an A-tile pair, 64 TMEM columns,
 // an mbarrier and a named barrier; they walk different tiles and drift out of
 // phase, so one group's gather latency hides behind another's MUFU-heavy
