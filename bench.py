@@ -52,7 +52,7 @@ def parse_args():
                     help='complexes per GPU per step')
     ap.add_argument('--atoms', type=int, default=1000)
     ap.add_argument('--math', default=os.environ.get('PVS_MATH', 'bf16x3'),
-                    choices=['fp32', 'bf16x3', 'bf16'],
+                    choices=['fp32', 'bf16x3', 'bf16', 'fp16x2'],
                     help='arithmetic of the edge/node contractions: fp32 = FFMA; '
                          'bf16x3 = tcgen05 with error-compensated bf16 split '
                          '(fp32-class: score error ~4e-6 vs the 1e-4 bound, the '
@@ -491,7 +491,7 @@ def run_ours(args):
     modes = None
     if args.other_modes:
         modes = {}
-        for m in ('fp32', 'bf16x3', 'bf16'):
+        for m in ('fp32', 'bf16x3', 'bf16', 'fp16x2'):
             if m == args.math:
                 continue
             model.set_math(m)
@@ -540,7 +540,11 @@ def run_ours(args):
             'dtype': {'fp32': 'f32',
                       'bf16x3': 'f32 (tcgen05 bf16x3 error-compensated, '
                                 'fp32 accumulate; score error ~4e-6 rel)',
-                      'bf16': 'bf16 (single pass, score error ~3e-3 rel)'}[args.math],
+                      'bf16': 'bf16 (single pass, score error ~3e-3 rel)',
+                      'fp16x2': 'f32 (tcgen05: fp16 activations x fp16 hi+lo '
+                                'weights on the edge GEMMs, bf16x3 on the node '
+                                'GEMMs, fp32 accumulate; score error ~4e-6 rel)',
+                      }[args.math],
             'data': 'synthetic',
             'config': workload_config(args),
             'edges_per_s': total_edges / (ms_total * 1e-3),

@@ -78,7 +78,11 @@ typedef enum pvs_act {
 typedef enum pvs_math {
     PVS_MATH_FP32 = 0,   /* FFMA, fp32 throughout                            */
     PVS_MATH_BF16X3 = 1, /* tcgen05, error-compensated bf16 split (fp32-class) */
-    PVS_MATH_BF16 = 2    /* tcgen05, single bf16 pass (fast mode)            */
+    PVS_MATH_BF16 = 2,   /* tcgen05, single bf16 pass (fast mode)            */
+    PVS_MATH_FP16X2 = 3  /* tcgen05, fp32-class: the per-edge GEMMs take the
+                            activations as one fp16 tile and the weights as
+                            fp16 hi + lo (A.Bhi + A.Blo); the per-node GEMMs
+                            run as BF16X3.  Activations saturate at +-65504. */
 } pvs_math;
 
 /* Destination-sorted CSR of one packed batch plus its work-tile partition. */

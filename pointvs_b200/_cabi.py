@@ -28,7 +28,7 @@ F_REZERO = 0x400
 F_SOFTMAX_ATTENTION = 0x800
 
 ACT = {'none': 0, 'sigmoid': 1, 'tanh': 2, 'relu': 3, 'silu': 4, 'softplus': 5}
-MATH = {'fp32': 0, 'bf16x3': 1, 'bf16': 2}
+MATH = {'fp32': 0, 'bf16x3': 1, 'bf16': 2, 'fp16x2': 3}
 MAX_K = 64
 TILE_EDGES = 128
 

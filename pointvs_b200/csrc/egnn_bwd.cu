@@ -1190,7 +1190,7 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
                        int64_t workspace_bytes, void *stream) {
     if (!g || !cfg || !p || !grads) return PVS_ERR_INVALID_ARG;
     if (cfg->k < 1 || cfg->k > PVS_MAX_K) return PVS_ERR_UNSUPPORTED_K;
-    if (cfg->math < PVS_MATH_FP32 || cfg->math > PVS_MATH_BF16) return PVS_ERR_INVALID_ARG;
+    if (cfg->math < PVS_MATH_FP32 || cfg->math > PVS_MATH_FP16X2) return PVS_ERR_INVALID_ARG;
     const uint32_t f = cfg->flags;
     const bool graphnorm = f & PVS_F_GRAPHNORM;
     const bool softmax = (f & PVS_F_EDGE_ATTENTION) && (f & PVS_F_SOFTMAX_ATTENTION);

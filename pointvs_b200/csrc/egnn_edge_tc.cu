@@ -44,8 +44,20 @@ constexpr int TC_GROUP_THREADS = 128;
 // the per-group scalars): five groups fill the 227 KB of shared memory.  The
 // single-pass bf16 mode has no lo tiles, so eight groups (1024 threads, all 512
 // TMEM columns) fit.
-template <bool X3> struct TcCfg {
-    static constexpr int GROUPS = X3 ? PVS_EXP_GROUPS : 8;
+// Arithmetic of the two per-edge GEMMs (template parameter MODE):
+//   TCM_BF16   : A bf16, B bf16                 (fast mode, tanh.approx SiLU)
+//   TCM_BF16X3 : Ahi.Bhi + Alo.Bhi + Ahi.Blo    (bf16 hi/lo of both operands)
+//   TCM_FP16X2 : A16.Bhi + A16.Blo              (activations as ONE fp16 tile,
+//                weights as fp16 hi + lo).  Rounding the activations to 11 bits
+//                costs ~3e-6 on the scores (the fp32 path itself is at 1e-6;
+//                bf16 activations would cost 3e-5) and frees the lo tile.
+enum { TCM_BF16 = 0, TCM_BF16X3 = 1, TCM_FP16X2 = 2 };
+template <int MODE> struct TcCfg {
+    static constexpr bool A_LO = MODE == TCM_BF16X3;      // second activation tile
+    static constexpr bool B_LO = MODE != TCM_BF16;        // second weight tile
+    static constexpr bool F16 = MODE == TCM_FP16X2;
+    static constexpr bool EXACT_SILU = MODE != TCM_BF16;
+    static constexpr int GROUPS = A_LO ? PVS_EXP_GROUPS : 8;
     static constexpr int THREADS = TC_GROUP_THREADS * GROUPS;
 };
 constexpr int TC_K = 64;          // padded hidden width of the tile
@@ -78,16 +90,17 @@ struct TcGroupMisc {
     uint64_t mbar;
 };
 
-template <bool X3>
+template <int MODE>
 struct __align__(1024) TcSmem {
-    static constexpr int G = TcCfg<X3>::GROUPS;
+    static constexpr int G = TcCfg<MODE>::GROUPS;
+    static constexpr bool X3 = TcCfg<MODE>::A_LO, BLO = TcCfg<MODE>::B_LO;
     // swizzled bf16 tiles, each 1024-byte aligned (lo tiles only where used)
     uint8_t A_hi[G][TE * 128];
     uint8_t A_lo[X3 ? G : 1][X3 ? TE * 128 : 1024];
     uint8_t W2_hi[TC_K * 128];
-    uint8_t W2_lo[X3 ? TC_K * 128 : 1024];
+    uint8_t W2_lo[BLO ? TC_K * 128 : 1024];
     uint8_t Wc1_hi[TC_K * 128];
-    uint8_t Wc1_lo[X3 ? TC_K * 128 : 1024];
+    uint8_t Wc1_lo[BLO ? TC_K * 128 : 1024];
     float b2[64], bc1[64], wc2[64], wa[64], wr[64];
     float T[PVS_MAX_EDGE_CLASSES][64];
     TcGroupMisc grp[G];
@@ -100,7 +113,7 @@ __device__ __forceinline__ void group_sync(int g) {
 }
 
 // one 128 x 64 x 64 GEMM into TMEM columns [d_col, d_col + 64)
-template <bool X3>
+template <int MODE>
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_base, uint32_t d_col,
                                            const uint8_t *a_hi, const uint8_t *a_lo,
                                            const uint8_t *b_hi, const uint8_t *b_lo,
@@ -108,28 +121,30 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_base, uint32_t d_col,
     const uint64_t ah = make_desc(smem_u32(a_hi)), al = make_desc(smem_u32(a_lo));
     const uint64_t bh = make_desc(smem_u32(b_hi)), bl = make_desc(smem_u32(b_lo));
     const uint32_t d = tmem_base + d_col;
+    constexpr uint32_t idesc = TcCfg<MODE>::F16 ? TC_IDESC_F16 : TC_IDESC;
     uint32_t acc = 0;
 #pragma unroll
     for (int ks = 0; ks < TC_K / 16; ++ks) {
-        const uint64_t adv = (uint64_t)(ks * 2);   // 16 bf16 = 32 B = 2 x 16 B
-        umma_bf16(d, ah + adv, bh + adv, TC_IDESC, acc);
+        const uint64_t adv = (uint64_t)(ks * 2);   // 16 elements = 32 B = 2 x 16 B
+        umma_bf16(d, ah + adv, bh + adv, idesc, acc);
         acc = 1;
-        if (X3) {
-            umma_bf16(d, al + adv, bh + adv, TC_IDESC, 1);
-            umma_bf16(d, ah + adv, bl + adv, TC_IDESC, 1);
-        }
+        if (TcCfg<MODE>::A_LO) umma_bf16(d, al + adv, bh + adv, idesc, 1);
+        if (TcCfg<MODE>::B_LO) umma_bf16(d, ah + adv, bl + adv, idesc, 1);
     }
     umma_commit(bar);
 }
 
-template <bool X3>
-__global__ void __launch_bounds__(TcCfg<X3>::THREADS, 1)
+template <int MODE>
+__global__ void __launch_bounds__(TcCfg<MODE>::THREADS, 1)
 egnn_edge_tc_kernel(const EdgeArgs a) {
     // SWIZZLE_128B tiles need 1024-byte alignment; the kernel has no static
     // shared memory, so the dynamic window starts at its (aligned) base.
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
-    constexpr int TC_GROUPS = TcCfg<X3>::GROUPS, TC_THREADS = TcCfg<X3>::THREADS;
-    TcSmem<X3> &S = *reinterpret_cast<TcSmem<X3> *>(smem_dyn);
+    constexpr int TC_GROUPS = TcCfg<MODE>::GROUPS, TC_THREADS = TcCfg<MODE>::THREADS;
+    constexpr bool X3 = TcCfg<MODE>::A_LO;            // hi + lo activation tiles
+    constexpr bool F16 = TcCfg<MODE>::F16;            // fp16 operands
+    constexpr bool EXACT = TcCfg<MODE>::EXACT_SILU;
+    TcSmem<MODE> &S = *reinterpret_cast<TcSmem<MODE> *>(smem_dyn);
     if ((smem_u32(smem_dyn) & 1023u) != 0u) __trap();
     const int g = threadIdx.x / TC_GROUP_THREADS;          // group
     const int tid = threadIdx.x % TC_GROUP_THREADS;        // thread in group
@@ -143,8 +158,13 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
     const bool f_eres = (a.flags & PVS_F_EDGE_RESIDUAL) && a.m_prev != nullptr;
 
     // ---- one-time setup (whole CTA) ----
-    load_weight_tiles<X3>(S.W2_hi, S.W2_lo, a.edge_w2, k, k, k);
-    load_weight_tiles<X3>(S.Wc1_hi, S.Wc1_lo, a.coord_w1, k, k, k);
+    if (F16) {
+        load_weight_tiles_f16(S.W2_hi, S.W2_lo, a.edge_w2, k, k, k);
+        load_weight_tiles_f16(S.Wc1_hi, S.Wc1_lo, a.coord_w1, k, k, k);
+    } else {
+        load_weight_tiles<X3>(S.W2_hi, S.W2_lo, a.edge_w2, k, k, k);
+        load_weight_tiles<X3>(S.Wc1_hi, S.Wc1_lo, a.coord_w1, k, k, k);
+    }
     const int col_r = (a.flags & PVS_F_PERM_INVARIANT) ? k : 2 * k;
     for (int n = threadIdx.x; n < 64; n += TC_THREADS) {
         const bool ok = n < k;
@@ -275,12 +295,16 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             v[i] = ffma2(wr2[i], rad2, fadd2(fadd2(pv[i], qv[i]), tv[i]));
-                        silu4_mode<X3>(v[0], v[1]);
-                        silu4_mode<X3>(v[2], v[3]);
-                        uint4 hi, lo;
-                        split8p<X3>(v, hi, lo);
-                        *reinterpret_cast<uint4 *>(A_hi + swz(r, c)) = hi;
-                        if (X3) *reinterpret_cast<uint4 *>(A_lo + swz(r, c)) = lo;
+                        silu4_mode<EXACT>(v[0], v[1]);
+                        silu4_mode<EXACT>(v[2], v[3]);
+                        if (F16) {
+                            *reinterpret_cast<uint4 *>(A_hi + swz(r, c)) = pack8_f16(v);
+                        } else {
+                            uint4 hi, lo;
+                            split8p<X3>(v, hi, lo);
+                            *reinterpret_cast<uint4 *>(A_hi + swz(r, c)) = hi;
+                            if (X3) *reinterpret_cast<uint4 *>(A_lo + swz(r, c)) = lo;
+                        }
                     };
 #pragma unroll
                     for (int p = 0; p < DEPTH; ++p) issue(p, buf[p], radv[p], attv[p]);
@@ -298,7 +322,7 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                 // ---- GEMM 1: t2 = s1 . W2^T ----
                 if (tid == 0) {
                     tc_fence_after();
-                    issue_gemm<X3>(tmem_grp, 0, A_hi, A_lo, S.W2_hi, S.W2_lo, &Gm.mbar);
+                    issue_gemm<MODE>(tmem_grp, 0, A_hi, A_lo, S.W2_hi, S.W2_lo, &Gm.mbar);
                 }
                 mbar_wait(&Gm.mbar, phase);
                 phase ^= 1;
@@ -332,8 +356,8 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                                 mv[i] = fadd2(
                                     make_float2(acc[8 * hlf + 2 * i], acc[8 * hlf + 2 * i + 1]),
                                     bias[i]);
-                            silu4_mode<X3>(mv[0], mv[1]);
-                            silu4_mode<X3>(mv[2], mv[3]);
+                            silu4_mode<EXACT>(mv[0], mv[1]);
+                            silu4_mode<EXACT>(mv[2], mv[3]);
                             if (f_eres && r < ne) {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
@@ -351,11 +375,15 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                             }
 #pragma unroll
                             for (int i = 0; i < 4; ++i) dot2 = ffma2(wat[i], mv[i], dot2);
-                            uint4 hi, lo;
-                            split8p<X3>(mv, hi, lo);
                             const int c = 2 * q + hlf;
-                            *reinterpret_cast<uint4 *>(A_hi + swz(r, c)) = hi;
-                            if (X3) *reinterpret_cast<uint4 *>(A_lo + swz(r, c)) = lo;
+                            if (F16) {
+                                *reinterpret_cast<uint4 *>(A_hi + swz(r, c)) = pack8_f16(mv);
+                            } else {
+                                uint4 hi, lo;
+                                split8p<X3>(mv, hi, lo);
+                                *reinterpret_cast<uint4 *>(A_hi + swz(r, c)) = hi;
+                                if (X3) *reinterpret_cast<uint4 *>(A_lo + swz(r, c)) = lo;
+                            }
                         }
                     }
                     const float dot = dot2.x + dot2.y;
@@ -378,7 +406,7 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                 // reduced below ----
                 if (f_coords && tid == 0) {
                     tc_fence_after();
-                    issue_gemm<X3>(tmem_grp, 0, A_hi, A_lo, S.Wc1_hi, S.Wc1_lo, &Gm.mbar);
+                    issue_gemm<MODE>(tmem_grp, 0, A_hi, A_lo, S.Wc1_hi, S.Wc1_lo, &Gm.mbar);
                 }
             }
             // ---- M_i = sum_e alpha_e m_e over dst segments: a warp per node,
@@ -401,8 +429,9 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                         float2 m[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            m[i] = make_float2(__uint_as_float(hw[i] << 16),
-                                               __uint_as_float(hw[i] & 0xffff0000u));
+                            m[i] = F16 ? unpack_f16x2(hw[i])
+                                       : make_float2(__uint_as_float(hw[i] << 16),
+                                                     __uint_as_float(hw[i] & 0xffff0000u));
                         if (X3) {
                             const uint4 l = *reinterpret_cast<const uint4 *>(A_lo + off);
                             const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
@@ -439,6 +468,11 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                     const uint32_t h = *reinterpret_cast<const uint32_t *>(A_hi + off);
                     float m0 = __uint_as_float(h << 16);
                     float m1 = __uint_as_float(h & 0xffff0000u);
+                    if (F16) {
+                        const float2 mf = unpack_f16x2(h);
+                        m0 = mf.x;
+                        m1 = mf.y;
+                    }
                     if (X3) {
                         const uint32_t l = *reinterpret_cast<const uint32_t *>(A_lo + off);
                         m0 += __uint_as_float(l << 16);
@@ -469,7 +503,7 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
                                           make_float2(bb.x, bb.y));
                         float2 s1 = fadd2(make_float2(acc[4 * v4 + 2], acc[4 * v4 + 3]),
                                           make_float2(bb.z, bb.w));
-                        silu4_mode<X3>(s0, s1);
+                        silu4_mode<EXACT>(s0, s1);
                         d2 = ffma2(make_float2(ww.x, ww.y), s0, d2);
                         d2 = ffma2(make_float2(ww.z, ww.w), s1, d2);
                     }
@@ -573,32 +607,29 @@ extern "C" int pvs_debug_phase_cycles(unsigned long long *out, int reset) {
 }
 #endif
 
+template <int MODE>
+static int launch_mode(const EdgeArgs &a, int n_ptiles_cap, cudaStream_t st) {
+    constexpr int G = TcCfg<MODE>::GROUPS;
+    const size_t smem = sizeof(TcSmem<MODE>);
+    int grid = num_sms();   // one persistent CTA per SM
+    const int need = (n_ptiles_cap + G - 1) / G;
+    if (need < grid) grid = need;
+    if (grid < 1) grid = 1;
+    const int rc = ensure_smem(egnn_edge_tc_kernel<MODE>, smem);
+    if (rc) return rc;
+    egnn_edge_tc_kernel<MODE><<<grid, TcCfg<MODE>::THREADS, smem, st>>>(a);
+    return PVS_OK;
+}
+
 int launch_edge_tc(const EdgeArgs &a, int n_ptiles_cap, int mode, cudaStream_t st) {
     if (a.ptile_last == nullptr || a.n_ptiles == nullptr || a.Mpart == nullptr ||
         a.xpart == nullptr)
         return PVS_ERR_INVALID_ARG;   // the tcgen05 kernel walks edge-packed tiles
     int rc;
-    if (mode == PVS_MATH_BF16X3) {
-        constexpr int G = TcCfg<true>::GROUPS;
-        const size_t smem = sizeof(TcSmem<true>);
-        int grid = num_sms();   // one persistent CTA per SM
-        const int need = (n_ptiles_cap + G - 1) / G;
-        if (need < grid) grid = need;
-        if (grid < 1) grid = 1;
-        rc = ensure_smem(egnn_edge_tc_kernel<true>, smem);
-        if (rc) return rc;
-        egnn_edge_tc_kernel<true><<<grid, TcCfg<true>::THREADS, smem, st>>>(a);
-    } else {
-        constexpr int G = TcCfg<false>::GROUPS;
-        const size_t smem = sizeof(TcSmem<false>);
-        int grid = num_sms();
-        const int need = (n_ptiles_cap + G - 1) / G;
-        if (need < grid) grid = need;
-        if (grid < 1) grid = 1;
-        rc = ensure_smem(egnn_edge_tc_kernel<false>, smem);
-        if (rc) return rc;
-        egnn_edge_tc_kernel<false><<<grid, TcCfg<false>::THREADS, smem, st>>>(a);
-    }
+    if (mode == PVS_MATH_BF16X3) rc = launch_mode<TCM_BF16X3>(a, n_ptiles_cap, st);
+    else if (mode == PVS_MATH_FP16X2) rc = launch_mode<TCM_FP16X2>(a, n_ptiles_cap, st);
+    else rc = launch_mode<TCM_BF16>(a, n_ptiles_cap, st);
+    if (rc) return rc;
     const bool softmax = (a.flags & PVS_F_EDGE_ATTENTION) && (a.flags & PVS_F_SOFTMAX_ATTENTION);
     const int do_m = softmax ? 0 : 1, do_x = a.x_out != nullptr ? 1 : 0;
     if (do_m || do_x)

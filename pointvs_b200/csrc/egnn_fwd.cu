@@ -815,7 +815,7 @@ int pvs_mean_pool_fwd(const float *h, const int32_t *graph_ptr, int32_t n_graphs
 int64_t pvs_egnn_layer_workspace_bytes(int32_t n_nodes, int32_t n_edges,
                                        const pvs_layer_config *cfg) {
     if (!cfg || cfg->k < 1 || cfg->k > PVS_MAX_K) return -1;
-    if (cfg->math < PVS_MATH_FP32 || cfg->math > PVS_MATH_BF16) return -1;
+    if (cfg->math < PVS_MATH_FP32 || cfg->math > PVS_MATH_FP16X2) return -1;
     const int kp = (cfg->k <= 32 && cfg->math == PVS_MATH_FP32) ? 32 : 64;
     return carve_workspace(nullptr, n_nodes, n_edges, kp, cfg->flags).bytes + 256;
 }
@@ -828,7 +828,7 @@ int pvs_egnn_layer_fwd(const pvs_graph *g, const pvs_layer_config *cfg,
                        void *stream) {
     if (!g || !cfg || !p) return PVS_ERR_INVALID_ARG;
     if (cfg->k < 1 || cfg->k > PVS_MAX_K) return PVS_ERR_UNSUPPORTED_K;
-    if (cfg->math < PVS_MATH_FP32 || cfg->math > PVS_MATH_BF16) return PVS_ERR_INVALID_ARG;
+    if (cfg->math < PVS_MATH_FP32 || cfg->math > PVS_MATH_FP16X2) return PVS_ERR_INVALID_ARG;
     if (cfg->n_edge_classes < 0 || cfg->n_edge_classes > PVS_MAX_EDGE_CLASSES)
         return PVS_ERR_INVALID_ARG;
     if (g->n_nodes < 0 || g->n_edges < 0) return PVS_ERR_INVALID_ARG;

@@ -467,7 +467,7 @@ int launch_node_pre_tc(const float *h, const float *edge_w1, const float *edge_b
     if (need < grid) grid = need;
     if (grid < 1) grid = 1;
     int rc;
-    if (mode == PVS_MATH_BF16X3) {
+    if (mode != PVS_MATH_BF16) {   // BF16X3, and the node stages of FP16X2
         rc = ensure_smem(node_pre_tc_kernel<true>, smem);
         if (rc) return rc;
         node_pre_tc_kernel<true><<<grid, NP_THREADS, smem, st>>>(a);
@@ -497,7 +497,7 @@ int launch_node_tc(const float *h_in, const float *M, float *h_out, float *natt_
     if (need < grid) grid = need;
     if (grid < 1) grid = 1;
     int rc;
-    if (mode == PVS_MATH_BF16X3) {
+    if (mode != PVS_MATH_BF16) {   // BF16X3, and the node stages of FP16X2
         rc = ensure_smem(node_tc_kernel<true>, smem);
         if (rc) return rc;
         node_tc_kernel<true><<<grid, NM_THREADS, smem, st>>>(a);

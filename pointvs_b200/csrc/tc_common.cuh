@@ -2,6 +2,7 @@
 // helpers shared by the tensor-core kernels (egnn_edge_tc.cu, egnn_node_tc.cu).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "pvs_common.cuh"
 
@@ -87,10 +88,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 // Instruction descriptor (kind::f16): D fp32 [4,6)=1, A bf16 [7,10)=1,
 // B bf16 [10,13)=1, both K-major, N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t tc_idesc(uint32_t n) {   // M = 128, N = n
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+// f16 = true: A and B are IEEE half (format code 0) instead of bf16 (1).
+__host__ __device__ constexpr uint32_t tc_idesc(uint32_t n, bool f16 = false) {   // M = 128, N = n
+    return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((n >> 3) << 17) |
+           ((128u >> 4) << 24);
 }
 constexpr uint32_t TC_IDESC = tc_idesc(64);
+constexpr uint32_t TC_IDESC_F16 = tc_idesc(64, true);
 
 // byte offset of 16-byte chunk `c` (8 bf16 = channels 8c..8c+7) of row `r`
 __device__ __forceinline__ uint32_t swz(int r, int c) {
@@ -180,6 +184,47 @@ __device__ __forceinline__ void split8p(const float2 (&v)[4], uint4 &hi, uint4 &
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ---- fp16 operand helpers (PVS_MATH_FP16X2: activations as ONE fp16 tile) ----
+// two fp32 -> packed half2, round to nearest, saturating at +-65504
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t w) {
+    return __half22float2(*reinterpret_cast<const __half2 *>(&w));
+}
+__device__ __forceinline__ uint4 pack8_f16(const float2 (&v)[4]) {
+    return make_uint4(pack_f16x2(v[0].x, v[0].y), pack_f16x2(v[1].x, v[1].y),
+                      pack_f16x2(v[2].x, v[2].y), pack_f16x2(v[3].x, v[3].y));
+}
+// W block -> fp16 hi / lo B tiles (w = hi + lo to 2^-22), same layout as
+// load_weight_tiles
+__device__ __forceinline__ void load_weight_tiles_f16(uint8_t *hi_tile, uint8_t *lo_tile,
+                                                      const float *__restrict__ W, int ld,
+                                                      int n_valid, int k_valid,
+                                                      int n_rows = 64) {
+    for (int idx = threadIdx.x; idx < n_rows * 8; idx += blockDim.x) {
+        const int n = idx >> 3, c = idx & 7;
+        float2 v[4], r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int kk = 8 * c + 2 * i;
+            v[i].x = (n < n_valid && kk < k_valid) ? W[(size_t)n * ld + kk] : 0.0f;
+            v[i].y = (n < n_valid && kk + 1 < k_valid) ? W[(size_t)n * ld + kk + 1] : 0.0f;
+        }
+        const uint4 hi = pack8_f16(v);
+        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 h = unpack_f16x2(hw[i]);
+            r[i] = make_float2(v[i].x - h.x, v[i].y - h.y);
+        }
+        *reinterpret_cast<uint4 *>(hi_tile + swz(n, c)) = hi;
+        *reinterpret_cast<uint4 *>(lo_tile + swz(n, c)) = pack8_f16(r);
+    }
 }
 
 // MMAs of one 64-wide K block: D[128 x N] (+)= A[128 x 64] . B[N x 64]^T with the

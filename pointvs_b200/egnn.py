@@ -596,7 +596,8 @@ class SartorrasEGNN(PNNGeometricBase):
         return nn.Sequential(*layers)
 
     def set_math(self, math):
-        """'fp32' (FFMA), 'bf16x3' (tcgen05, fp32-class) or 'bf16' (fast)."""
+        """'fp32' (FFMA), 'bf16x3' or 'fp16x2' (tcgen05, fp32-class) or 'bf16'
+        (tcgen05, fast)."""
         if math not in _cabi.MATH:
             raise ValueError(f'math must be one of {sorted(_cabi.MATH)}')
         for layer in self.layers:

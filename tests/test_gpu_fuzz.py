@@ -83,7 +83,7 @@ def test_random_configuration(seed):
     want, x_want = gh.oracle_forward(model, kw, cpu)
     want = want.numpy().reshape(-1)
     scale = max(1e-3, float(np.abs(want).max()))
-    for math in ('fp32', 'bf16x3'):
+    for math in ('fp32', 'bf16x3', 'fp16x2'):
         model.set_math(math)
         graph.pos = pos0.clone()
         with torch.no_grad():
@@ -95,7 +95,7 @@ def test_random_configuration(seed):
 
 
 @pytest.mark.parametrize('seed', range(12))
-@pytest.mark.parametrize('math', ['fp32', 'bf16x3'])
+@pytest.mark.parametrize('math', ['fp32', 'bf16x3', 'fp16x2'])
 def test_random_configuration_gradients(seed, math):
     """Same sweep for the backward: parameter and coordinate gradients of a
     scalar loss against torch autograd through the CPU oracle.  Parameters the

@@ -23,7 +23,8 @@ def _batches():
     return out
 
 
-@pytest.mark.parametrize('math,capacity', [('fp32', 'auto'), ('bf16x3', None)])
+@pytest.mark.parametrize('math,capacity', [('fp32', 'auto'), ('bf16x3', None),
+                                           ('fp16x2', 'auto')])
 def test_stream_equals_one_at_a_time(math, capacity):
     import pointvs_b200 as pv
     from pointvs_b200.pipeline import ScoreStream

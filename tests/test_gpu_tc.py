@@ -49,7 +49,8 @@ def test_tc_layer_matches_fp32_layer(k):
         assert helpers.scaled_err(a.cpu().numpy(), b.cpu().numpy()) < 3e-2, name
 
 
-@pytest.mark.parametrize('math,tol', [('bf16x3', 1e-4), ('bf16', 3e-2)])
+@pytest.mark.parametrize('math,tol', [('bf16x3', 1e-4), ('fp16x2', 1e-4),
+                                      ('bf16', 3e-2)])
 def test_tc_config3_vs_oracle(math, tol):
     model = gh.build_model(CFG3, seed=0, coord_gain=1.0)
     model.set_math(math)
@@ -67,11 +68,12 @@ def test_tc_config3_vs_oracle(math, tol):
     assert err < tol
 
 
+@pytest.mark.parametrize('math', ['bf16x3', 'fp16x2'])
 @pytest.mark.parametrize('name', sorted(helpers.MODEL_GOLDENS))
-def test_tc_bf16x3_vs_reference_golden(name):
+def test_tc_bf16x3_vs_reference_golden(name, math):
     _, _, tasks = helpers.MODEL_GOLDENS[name]
     for task in tasks:
-        model, g = gh.cuda_model(name, task, math='bf16x3')
+        model, g = gh.cuda_model(name, task, math=math)
         with torch.no_grad():
             out = model(gh.cuda_graph(g))
         assert helpers.rel_err(out.cpu().numpy().reshape(-1),
@@ -135,7 +137,8 @@ def test_tc_graphnorm_node_stage_vs_oracle(k, ragged):
                                    edge_index=graph.edge_index,
                                    edge_attr=graph.edge_attr,
                                    batch=graph.batch))
-    for math, tol in (('fp32', 1e-4), ('bf16x3', 1e-4), ('bf16', 3e-2)):
+    for math, tol in (('fp32', 1e-4), ('bf16x3', 1e-4), ('fp16x2', 1e-4),
+                      ('bf16', 3e-2)):
         model.set_math(math)
         graph.pos = pos0.clone()
         with torch.no_grad():
@@ -152,8 +155,9 @@ def test_tc_graphnorm_node_stage_vs_oracle(k, ragged):
     assert g is not None and torch.isfinite(g).all() and g.abs().max() > 0
 
 
+@pytest.mark.parametrize('math', ['bf16x3', 'fp16x2'])
 @pytest.mark.parametrize('softmax', [False, True])
-def test_tc_packed_tiles_split_nodes_and_edgeless_runs(softmax):
+def test_tc_packed_tiles_split_nodes_and_edgeless_runs(softmax, math):
     """The tcgen05 edge kernel walks edge-packed tiles: nodes cut by a tile
     boundary (every 128 edges), hubs spanning several tiles, and runs of more
     than 128 edgeless nodes inside a tile's node range."""
@@ -185,7 +189,7 @@ def test_tc_packed_tiles_split_nodes_and_edgeless_runs(softmax):
     x = torch.randn(n, 3, generator=gen) * 4
     layer = EGNNLayer(48, 48, 48, edges_in_d=3, edge_attention=True,
                       normalize=True, tanh=True, softmax_attention=softmax,
-                      math='bf16x3').cuda()
+                      math=math).cuda()
     with torch.no_grad():
         layer.coord_mlp[2].weight.mul_(300.0)
         h2, x2, _, m2 = layer(h.cuda(), ei.cuda(), x.clone().cuda(), ea.cuda())
