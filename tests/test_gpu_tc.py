@@ -199,9 +199,12 @@ def test_tc_packed_tiles_split_nodes_and_edgeless_runs(softmax, math):
                                   softmax_attention=softmax)
     ho, xo, mo, _ = egnn_oracle.layer_forward(sd, 'l.', cfg, h, ei[0], ei[1],
                                               x, ea)
-    assert helpers.scaled_err(h2.cpu().numpy(), ho.numpy()) < 1e-4
-    assert helpers.scaled_err(x2.cpu().numpy(), xo.numpy()) < 1e-4
-    assert helpers.scaled_err(m2.cpu().numpy(), mo.numpy()) < 1e-4
+    # per-node / per-edge outputs: fp16x2 carries the 2^-12 rounding of its
+    # activation tile (stated separately from the fp32-class modes)
+    tol = 5e-4 if math == 'fp16x2' else 1e-4
+    assert helpers.scaled_err(h2.cpu().numpy(), ho.numpy()) < tol
+    assert helpers.scaled_err(x2.cpu().numpy(), xo.numpy()) < tol
+    assert helpers.scaled_err(m2.cpu().numpy(), mo.numpy()) < tol
     # edgeless nodes keep their coordinates exactly
     assert torch.equal(x2[201:561].cpu(), x[201:561])
     assert torch.equal(x2[861:].cpu(), x[861:])
