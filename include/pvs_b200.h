@@ -49,6 +49,8 @@ typedef enum pvs_status {
 #define PVS_CAP_FWD_FP32 1u      /* FFMA forward                              */
 #define PVS_CAP_FWD_TCGEN05 2u   /* tcgen05 edge-MLP tiles (bf16x3 / bf16)    */
 #define PVS_CAP_BWD_FP32 4u      /* backward kernels                          */
+#define PVS_CAP_FWD_FP16X2 8u    /* PVS_MATH_FP16X2 edge kernel               */
+#define PVS_CAP_CROP 16u         /* K0: pvs_crop_count / pvs_crop_fill        */
 
 /* pvs_layer_config.flags -- EGNNLayer.__init__ (egnn_satorras.py:26-46) */
 #define PVS_F_RESIDUAL 0x001u

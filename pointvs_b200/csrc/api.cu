@@ -52,7 +52,8 @@ extern "C" {
 int pvs_version(void) { return PVS_VERSION; }
 
 uint32_t pvs_capabilities(void) {
-    return PVS_CAP_FWD_FP32 | PVS_CAP_FWD_TCGEN05 | PVS_CAP_BWD_FP32;
+    return PVS_CAP_FWD_FP32 | PVS_CAP_FWD_TCGEN05 | PVS_CAP_BWD_FP32 | PVS_CAP_FWD_FP16X2 |
+           PVS_CAP_CROP;
 }
 
 const char *pvs_status_string(int status) {
