@@ -471,9 +471,9 @@ def run_ours(args):
         'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf,
         'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf,
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel,
-        # ncu --set full, profiles/r01_h_prof_edge_ncu_full.csv (tcgen05 modes, the
+        # ncu --set full, profiles/r01_h_prof_edge_ncu_full.csv (bf16x3, the
         # default batch); null for other configurations
-        'traffic': NCU_EDGE_TRAFFIC_BYTES if (args.math != 'fp32' and args.batch == 128
+        'traffic': NCU_EDGE_TRAFFIC_BYTES if (args.math == 'bf16x3' and args.batch == 128
                                               and args.atoms == 1000) else None,
         'peak_source': peak_src,
         'algorithmic_flop_per_launch': flop_per_launch,
