@@ -17,7 +17,7 @@ from torch import nn
 from . import _cabi
 from ._cabi import check, lib, ptr, stream
 from .base import PointNeuralNetworkBase, DEVICE
-from .graph import CSRGraph, csr_from_edge_index
+from .graph import CSRGraph, csr_from_edge_index, dropout_adj
 
 
 class GraphNorm(nn.Module):
@@ -404,6 +404,8 @@ class PNNGeometricBase(PointNeuralNetworkBase):
         if torch.is_grad_enabled() and any(
                 p.requires_grad for p in self.parameters()):
             return False
+        if self.training and getattr(self, 'dropout_p', 0) > 0:
+            return False        # edge dropout rebuilds the graph per call
         if STAGE_TIMER is not None and getattr(STAGE_TIMER, 'split_stages', True):
             return False
         egnn = [l for l in self.layers if isinstance(l, EGNNLayer)]
@@ -617,13 +619,12 @@ class SartorrasEGNN(PNNGeometricBase):
         """Reference signature (egnn_satorras.py:319-329) -> (h [N,k],
         m [E,k] in the caller's edge order).  `coords` is updated in place
         when it is an fp32 CUDA tensor, as in the reference."""
-        if self.dropout_p > 0 and self.training:
-            raise NotImplementedError(
-                'dropout_adj (edge dropout during training) is not part of '
-                'the B200 hot path; use dropout=0')
         _cabi.require_cuda(feats, coords)
         csr = _csr if isinstance(_csr, CSRGraph) else \
             _csr_for(edges, edge_attributes, feats.shape[0])
+        if self.dropout_p > 0 and self.training:
+            # the messages returned below are those of the thinned edge list
+            csr = dropout_adj(csr, self.dropout_p, force_undirected=True)
         embed = self.layers[0]
         if embed.feats_appended_to_coords:
             raise NotImplementedError('feats_appended_to_coords')

@@ -353,6 +353,37 @@ def csr_from_edge_index(edge_index, edge_attr, n_nodes):
     return g
 
 
+def dropout_adj(csr, p, force_undirected=True, generator=None):
+    """Edge dropout of the reference's training path: `dropout_adj(edges,
+    edge_attributes, p, force_undirected=True, training=True)`
+    (egnn_satorras.py:320-323; torch_geometric 2.0.4 `utils.dropout_adj`,
+    third-party, restated from its published source): keep the edges with
+    row < col, drop each with probability p, then add the mirror image of
+    every survivor.  -> a new CSRGraph (`perm` = order [kept | mirrored]).
+    The random stream is this device's, so results match the reference in
+    distribution, not draw for draw."""
+    if p < 0.0 or p > 1.0:
+        raise ValueError(f'Dropout probability has to be between 0 and 1 (got {p})')
+    csr._exact()
+    row, col, attr = csr.rows(), csr.col.long(), csr.attr.long()
+    if force_undirected:
+        keep = row < col
+        row, col, attr = row[keep], col[keep], attr[keep]
+    prob = torch.full((row.numel(),), 1.0 - p, dtype=torch.float32,
+                      device=csr.device)
+    mask = torch.bernoulli(prob, generator=generator).to(torch.bool)
+    row, col, attr = row[mask], col[mask], attr[mask]
+    if force_undirected:
+        ei = torch.stack([torch.cat([row, col]), torch.cat([col, row])])
+        attr = torch.cat([attr, attr])
+    else:
+        ei = torch.stack([row, col])
+    onehot = torch.nn.functional.one_hot(attr, csr.n_classes)
+    out = csr_from_edge_index(ei, onehot, csr.n_nodes)
+    out._key_refs = (ei, onehot)
+    return out
+
+
 class PackedBatch:
     """Variable-size complexes packed for the EGNN kernels; duck-types the PyG
     `Batch` consumed by `forward(graph)` (x, pos, edge_index, edge_attr,

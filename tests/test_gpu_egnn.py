@@ -446,3 +446,65 @@ def test_val_writes_reference_prediction_file(tmp_path):
         assert y_true == ('1.000' if i % 2 == 0 else '0.000')
         assert 0.0 <= float(y_pred) <= 1.0 and len(y_pred.split('.')[1]) == 3
         assert rec == f'rec_{i // 2}.parquet' and lig == f'lig_{i // 2}_{i % 2}.parquet'
+
+
+def test_edge_dropout_matches_published_dropout_adj_semantics():
+    """Training-time edge dropout (egnn_satorras.py:320-323, PyG 2.0.4
+    dropout_adj with force_undirected=True): survivors are a symmetric subset
+    of the original edges, about (1 - p) of the undirected pairs; p = 0 and
+    eval mode leave the graph alone; a forward on the thinned graph equals the
+    oracle on that edge list."""
+    from pointvs_b200.graph import dropout_adj
+    kw = dict(dim_input=13, dim_output=1, k=32, num_layers=2, graphnorm=False,
+              edge_attention=True, node_attention=True, residual=True,
+              normalize=True, tanh=True, dropout=0.4)
+    model = gh.build_model(kw, seed=3, coord_gain=1.0)
+    graph = gh.synthetic_graph(400, 3, 300, 15)
+    csr = graph.pvs_csr
+    base = set(zip(*[t.tolist() for t in csr.edge_index('csr').cpu()],
+                   csr.attr.cpu().tolist()))
+    gen = torch.Generator(device='cuda').manual_seed(7)
+    thin = dropout_adj(csr, 0.4, generator=gen)
+    ei = thin.edge_index('csr').cpu()
+    got = set(zip(ei[0].tolist(), ei[1].tolist(), thin.attr.cpu().tolist()))
+    assert got <= base
+    assert all((c, r, a) in got for r, c, a in got)          # mirrored
+    und = sum(1 for r, c, _ in base if r < c)
+    frac = (thin.n_edges / 2) / und
+    assert abs(frac - 0.6) < 0.03
+    same = dropout_adj(csr, 0.0)
+    assert same.n_edges == 2 * und          # every undirected pair, mirrored
+    # eval mode: dropout is off, scores equal the dropout-free model's
+    pos0 = graph.pos.clone()
+    with torch.no_grad():
+        a = model(graph)
+    model.dropout_p = 0.0
+    graph.pos = pos0.clone()
+    with torch.no_grad():
+        b = model(graph)
+    assert torch.equal(a, b)
+    # training mode: the layers run on the thinned graph
+    model.dropout_p = 0.4
+    model.train()
+    torch.manual_seed(11)
+    graph.pos = pos0.clone()
+    with torch.no_grad():
+        h_got, _ = model.get_embeddings(graph.x, None, graph.pos, None,
+                                        graph.batch, _csr=csr,
+                                        _want_messages=False)
+    torch.manual_seed(11)
+    thin = dropout_adj(csr, 0.4)
+    model.eval()
+    graph.pos = pos0.clone()
+    with torch.no_grad():
+        h_want, _ = model.get_embeddings(graph.x, None, graph.pos, None,
+                                         graph.batch, _csr=thin,
+                                         _want_messages=False)
+    assert torch.equal(h_got, h_want)
+    from oracle import egnn_oracle
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    cfgs = egnn_oracle.layer_configs(2, **helpers.oracle_kwargs(kw))
+    h_ref, _, _ = egnn_oracle.embeddings(
+        sd, cfgs, graph.x.cpu(), thin.edge_index('csr').cpu(), pos0.cpu(),
+        thin.edge_attr_onehot('csr').cpu())
+    assert helpers.scaled_err(h_want.cpu().numpy(), h_ref.numpy()) < 1e-4
