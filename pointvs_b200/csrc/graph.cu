@@ -138,7 +138,7 @@ static size_t rg_smem_bytes(int max_n, bool with_prefix, bool stage) {
     size_t words = (size_t)(max_n + 31) / 32;
     size_t b = sizeof(RgSmem);
     b += (size_t)max_n * sizeof(int);                 // sorted_idx
-    b += (size_t)RG_WARPS * 2 * words * sizeof(int);  // per-warp bit masks
+    b += (size_t)RG_WARPS * 4 * words * sizeof(int);  // bit masks: 2 lists x 2 half-warps
     b += (size_t)max_n * sizeof(int);                 // prefix_inter (fill + ref_pos)
     (void)with_prefix;
     b = (b + 7) & ~(size_t)7;
@@ -176,7 +176,7 @@ radius_graph_kernel(const double *__restrict__ coords,
     const int words = (max_n + 31) / 32;
     int *sorted_idx = reinterpret_cast<int *>(smem_raw + sizeof(RgSmem));
     unsigned *masks = reinterpret_cast<unsigned *>(sorted_idx + max_n);
-    int *prefix_inter = reinterpret_cast<int *>(masks + (size_t)RG_WARPS * 2 * words);
+    int *prefix_inter = reinterpret_cast<int *>(masks + (size_t)RG_WARPS * 4 * words);
     // cell-sorted copy of the coordinates / bp: the neighbour loop then reads
     // contiguous shared-memory ranges instead of chasing sorted_idx into global
     double *scoord = reinterpret_cast<double *>(
@@ -284,15 +284,11 @@ radius_graph_kernel(const double *__restrict__ coords,
     const double intra_lo = r_intra * r_intra * (1.0 - 1e-15);
     const double intra_hi = r_intra * r_intra * (1.0 + 1e-15);
     const double pos_hi = 1e-14 * (1.0 + 1e-15);
-    unsigned *m_inter = masks + (size_t)warp * 2 * words;
-    unsigned *m_intra = m_inter + words;
     const int nw = (n + 31) / 32;
-    for (int i = warp + RG_WARPS * part; i < n; i += RG_WARPS * RG_SPLIT) {
-        for (int w = lane; w < nw; w += 32) {
-            m_inter[w] = 0u;
-            m_intra[w] = 0u;
-        }
-        __syncwarp();
+    // neighbour search of destination atom i by W lanes (lane index l):
+    // sets the bits of its inter / intra neighbours in m_inter / m_intra
+    auto search = [&](const int i, const int l, const int W, unsigned *m_inter,
+                      unsigned *m_intra) {
         const double xi = cx[3 * i], yi = cx[3 * i + 1], zi = cx[3 * i + 2];
         const int bi = cbp[i];
         const int ci0 = cell_coord(xi, blo[0], cs[0], dim[0]);
@@ -307,7 +303,7 @@ radius_graph_kernel(const double *__restrict__ coords,
                 if (c1 < 0 || c1 >= dim[1]) continue;
                 int cb = dim[0] * (c1 + dim[1] * c2);
                 int p_end = S.cell_start[cb + x_hi + 1];
-                for (int p = S.cell_start[cb + x_lo] + lane; p < p_end; p += 32) {
+                for (int p = S.cell_start[cb + x_lo] + l; p < p_end; p += W) {
                     const int j = sorted_idx[p];
                     double xj, yj, zj;
                     int bj;
@@ -350,6 +346,61 @@ radius_graph_kernel(const double *__restrict__ coords,
                 }
             }
         }
+    };
+    if (!FILL) {
+        // count pass: a HALF-warp per destination atom (a run of three cells
+        // holds ~10 candidates, so 16 lanes are two-thirds busy where 32 were
+        // one-third), two atoms per warp
+        const int half = lane >> 4, hl = lane & 15;
+        unsigned *m_inter = masks + (size_t)(warp * 2 + half) * 2 * words;
+        unsigned *m_intra = m_inter + words;
+        for (int i0 = 2 * warp + 2 * RG_WARPS * part; i0 < n; i0 += 2 * RG_WARPS * RG_SPLIT) {
+            const int i = i0 + half;
+            const bool active = i < n;
+            for (int w = hl; w < nw; w += 16) {
+                m_inter[w] = 0u;
+                m_intra[w] = 0u;
+            }
+            __syncwarp();
+            if (active) search(i, hl, 16, m_inter, m_intra);
+            __syncwarp();
+            int ci = 0, ca = 0;
+            for (int w = hl; w < nw; w += 16) {
+                ci += __popc(m_inter[w]);
+                ca += __popc(m_intra[w]);
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {     // within the half-warp
+                ci += __shfl_xor_sync(0xffffffffu, ci, o);
+                ca += __shfl_xor_sync(0xffffffffu, ca, o);
+            }
+            if (active) {
+                if (hl == 0) {
+                    deg[n0 + i] = ci + ca;
+                    n_inter_out[n0 + i] = ci;
+                }
+                if (mask_out != nullptr) {   // keep the masks: fill only expands them
+                    uint32_t *mo = mask_out + (size_t)(n0 + i) * 2 * words;
+                    for (int w = hl; w < nw; w += 16) {
+                        mo[w] = m_inter[w];
+                        mo[words + w] = m_intra[w];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        return;
+    }
+    unsigned *m_inter = masks + (size_t)warp * 2 * words;
+    unsigned *m_intra = m_inter + words;
+    for (int i = warp + RG_WARPS * part; i < n; i += RG_WARPS * RG_SPLIT) {
+        for (int w = lane; w < nw; w += 32) {
+            m_inter[w] = 0u;
+            m_intra[w] = 0u;
+        }
+        __syncwarp();
+        search(i, lane, 32, m_inter, m_intra);
+        const int bi = cbp[i];
         __syncwarp();
         if (!FILL) {
             int ci = 0, ca = 0;
