@@ -188,6 +188,7 @@ struct __align__(1024) NmSmem {
     uint8_t W1m_hi[64 * 128], W1m_lo[64 * 128];   // node_w1[:, k:2k]  (M part)
     uint8_t W2_hi[64 * 128], W2_lo[64 * 128];
     float b1[64], b2[64], wn[64], ga[64], gb[64];
+    float srow[NM_GROUPS][NT_ROWS];   // node attention value of each row of the tile
     uint64_t mbar[NM_GROUPS];
     uint32_t tmem_base;
 };
@@ -371,32 +372,18 @@ node_tc_kernel(const NodeTcArgs a) {
         mbar_wait(&S.mbar[g], phase);
         phase ^= 1;
         tc_fence_after();
-        // ---- o = D + b2, node attention, residual -> staging -> h_out ----
+        // ---- o = D + b2 and the node-attention logit in ONE pass over TMEM
+        // (thread per row); o goes to the fp32 staging tile unscaled.  The
+        // attention factor and the residual are applied in the store pass, where
+        // a row of h is read as full 256-byte lines instead of per-thread rows.
         {
             const int r = tid;
             const bool ok = row0 + r < a.n_nodes;
-            float s = 1.0f;
-            if (f_natt) {
-                float dot = 0.0f;
-#pragma unroll 1
-                for (int q = 0; q < 4; ++q) {
-                    float acc[16];
-                    tmem_ld16(tmem_lane + 16 * q, acc);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        dot = fmaf(S.wn[16 * q + i], acc[i] + S.b2[16 * q + i], dot);
-                }
-                const float zn = dot + natt_b;
-                s = (a.flags & PVS_F_SOFTMAX_ATTENTION) ? zn : apply_act(zn, a.att_act);
-                if (a.natt_out && ok) a.natt_out[row0 + r] = s;
-            }
             // A tiles are free (GEMM 2 has completed): 64 rows of fp32 staging in
             // each 16 KB tile
             float *st = reinterpret_cast<float *>(r < 64 ? A_hi : A_lo);
             const int rr = r & 63;
-            const float *hrow = a.h_in + (size_t)(row0 + r) * k;
-            const bool hvec = (k & 3) == 0;
-            const float G = fmaxf(gate, 0.0f);
+            float dot = 0.0f;
 #pragma unroll 1
             for (int q = 0; q < 4; ++q) {
                 float acc[16];
@@ -404,49 +391,63 @@ node_tc_kernel(const NodeTcArgs a) {
 #pragma unroll
                 for (int v4 = 0; v4 < 4; ++v4) {
                     const int n = 16 * q + 4 * v4;
-                    float o[4], hv[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (f_res && ok) {
-                        if (hvec && n + 3 < k) {
-                            const float4 h4 = __ldg(reinterpret_cast<const float4 *>(hrow + n));
-                            hv[0] = h4.x; hv[1] = h4.y; hv[2] = h4.z; hv[3] = h4.w;
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) hv[i] = (n + i < k) ? __ldg(hrow + n + i) : 0.0f;
-                        }
-                    }
+                    float o[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        float out = (acc[4 * v4 + i] + S.b2[n + i]) * s;
-                        if (f_res) {
-                            if (a.flags & PVS_F_REZERO) out = hv[i] + gate * out;
-                            else if (a.flags & PVS_F_GATED_RESIDUAL) out = G * out + (1.0f - G) * hv[i];
-                            else out = hv[i] + out;
-                        }
-                        o[i] = out;
+                        o[i] = acc[4 * v4 + i] + S.b2[n + i];
+                        dot = fmaf(S.wn[n + i], o[i], dot);
                     }
                     *stage_ptr(st, rr, 4 * q + v4) = make_float4(o[0], o[1], o[2], o[3]);
                 }
             }
+            float s = 1.0f;
+            if (f_natt) {
+                const float zn = dot + natt_b;
+                s = (a.flags & PVS_F_SOFTMAX_ATTENTION) ? zn : apply_act(zn, a.att_act);
+                if (a.natt_out && ok) a.natt_out[row0 + r] = s;
+            }
+            S.srow[g][r] = s;
         }
         tc_fence_before();
         nt_group_sync(g);
         {
             const int c4 = tid & 15, slot = tid >> 4;
             const bool vec = (k & 3) == 0;
+            const float G = fmaxf(gate, 0.0f);
 #pragma unroll 4
             for (int p = 0; p < NT_ROWS / 8; ++p) {
                 const int row = p * 8 + slot;
                 if (row0 + row >= a.n_nodes) continue;
                 const float *sp = reinterpret_cast<const float *>(row < 64 ? A_hi : A_lo);
-                const float4 v = *stage_ptr(const_cast<float *>(sp), row & 63, c4);
+                float4 v = *stage_ptr(const_cast<float *>(sp), row & 63, c4);
+                const float s = S.srow[g][row];
+                const float *hrow = a.h_in + (size_t)(row0 + row) * k + 4 * c4;
+                float o[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
+                if (f_res) {
+                    float hv[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (vec && 4 * c4 + 3 < k) {
+                        const float4 h4 = __ldg(reinterpret_cast<const float4 *>(hrow));
+                        hv[0] = h4.x; hv[1] = h4.y; hv[2] = h4.z; hv[3] = h4.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            hv[i] = (4 * c4 + i < k) ? __ldg(hrow + i) : 0.0f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (a.flags & PVS_F_REZERO) o[i] = hv[i] + gate * o[i];
+                        else if (a.flags & PVS_F_GATED_RESIDUAL) o[i] = G * o[i] + (1.0f - G) * hv[i];
+                        else o[i] = hv[i] + o[i];
+                    }
+                }
                 float *d = a.h_out + (size_t)(row0 + row) * k + 4 * c4;
                 if (vec && 4 * c4 + 3 < k) {
-                    *reinterpret_cast<float4 *>(d) = v;
+                    *reinterpret_cast<float4 *>(d) = make_float4(o[0], o[1], o[2], o[3]);
                 } else {
-                    if (4 * c4 < k) d[0] = v.x;
-                    if (4 * c4 + 1 < k) d[1] = v.y;
-                    if (4 * c4 + 2 < k) d[2] = v.z;
-                    if (4 * c4 + 3 < k) d[3] = v.w;
+                    if (4 * c4 < k) d[0] = o[0];
+                    if (4 * c4 + 1 < k) d[1] = o[1];
+                    if (4 * c4 + 2 < k) d[2] = o[2];
+                    if (4 * c4 + 3 < k) d[3] = o[3];
                 }
             }
         }
