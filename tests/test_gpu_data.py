@@ -260,3 +260,47 @@ def test_training_on_packed_loader_matches_oracle_autograd(tmp_path, gold):
         if v.is_floating_point():
             ref = sd[k].detach()
             assert helpers.scaled_err(v.cpu().numpy(), ref.numpy()) < 5e-3, k
+
+
+def test_train_cli_pose_then_affinity_then_inference(tmp_path):
+    """`python -m pointvs_b200.train multitask ...` (mirror of point_vs.py):
+    pose epochs -> pose validation -> affinity epochs -> affinity validation
+    on the sample complexes, the reference's output files, and the run
+    directory loads back through load_model / inference."""
+    from pointvs_b200 import inference, train
+    from pointvs_b200.load_model import load_model
+    run = tmp_path / 'run'
+    model = train.main([
+        'multitask', str(run), '--model_task', 'both',
+        '--train_data_root_pose', str(ROOT),
+        '--train_types_pose', str(ROOT / 'pose.types'), '-ep', '2',
+        '--train_data_root_affinity', str(ROOT),
+        '--train_types_affinity', str(ROOT / 'affinity.types'), '-ea', '1',
+        '--test_data_root_pose', str(ROOT),
+        '--test_types_pose', str(ROOT / 'pose.types'),
+        '--test_data_root_affinity', str(ROOT),
+        '--test_types_affinity', str(ROOT / 'affinity.types'),
+        '--layers', '2', '-k', '32', '-b', '4', '--egnn_attention',
+        '--node_attention', '--egnn_residual', '--egnn_normalise',
+        '--egnn_tanh', '--multi_target_affinity', '--math', 'bf16x3',
+        '--end_flag'])
+    for name in ('cmd_args.yaml', 'model_kwargs.yaml', '_FINISHED',
+                 'checkpoints/pose_ckpt_epoch_2.pt',
+                 'checkpoints/affinity_ckpt_epoch_1.pt',
+                 'pose_predictions.txt', 'affinity_predictions.txt'):
+        assert (run / name).is_file(), name
+    pose = (run / 'pose_predictions.txt').read_text().splitlines()
+    assert len(pose) == 7 and all(' | ' in ln for ln in pose)
+    aff = (run / 'affinity_predictions.txt').read_text().splitlines()
+    assert len(aff) >= 7 and aff[0].rsplit(' | ', 1)[1] in ('pki', 'pkd', 'ic50')
+    kwargs = yaml.safe_load((run / 'model_kwargs.yaml').read_text())
+    assert kwargs['dim_input'] == 22 and kwargs['dim_output'] == 3
+    # the run directory is a reference-format checkpoint
+    path, loaded, _, cmd = load_model(run, model_task='affinity')
+    assert path.name == 'affinity_ckpt_epoch_1.pt' and cmd['model'] == 'multitask'
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), loaded.state_dict()[k].cpu()), k
+    out = inference.main([str(run), str(ROOT / 'pose.types'), str(ROOT),
+                          '--model_task', 'pose', '--math', 'bf16x3'])
+    lines = (out.parent / ('pose_' + out.name)).read_text().splitlines()
+    assert len(lines) == 7

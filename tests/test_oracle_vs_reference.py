@@ -59,3 +59,22 @@ def test_generate_edges_against_live_reference():
     np.testing.assert_array_equal(row, r2)
     np.testing.assert_array_equal(col, c2)
     np.testing.assert_array_equal(attr, a2)
+
+
+def test_train_cli_flags_match_reference_parse_args(monkeypatch):
+    """pointvs_b200.train.parse_args defines every flag of the reference's
+    point_vs/parse_args.py with the same default."""
+    import sys
+    from pointvs_b200 import train
+    ref_shim.install()
+    from point_vs.parse_args import parse_args as ref_parse
+    argv = ['multitask', '/tmp/run', '--train_data_root_pose', 'a',
+            '--train_types_pose', 'b', '-ep', '2', '-k', '48', '--egnn_tanh']
+    monkeypatch.setattr(sys, 'argv', ['point_vs.py'] + argv)
+    want = vars(ref_parse())
+    got = vars(train.parse_args(argv))
+    for key, value in want.items():
+        assert key in got, key
+        assert got[key] == value, (key, got[key], value)
+    extra = set(got) - set(want)
+    assert extra == {'math', 'workers', 'worker_processes', 'host_crop'}
