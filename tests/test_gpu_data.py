@@ -304,3 +304,23 @@ def test_train_cli_pose_then_affinity_then_inference(tmp_path):
                           '--model_task', 'pose', '--math', 'bf16x3'])
     lines = (out.parent / ('pose_' + out.name)).read_text().splitlines()
     assert len(lines) == 7
+
+
+def test_resume_training_continues_from_the_checkpoint_epoch(tmp_path):
+    """resume_training.py: the recorded flags rebuild the loaders and
+    train_model starts at the checkpoint's epoch."""
+    from pointvs_b200 import resume_training, train
+    run = tmp_path / 'run'
+    train.main(['egnn', str(run), '--train_data_root_pose', str(ROOT),
+                '--train_types_pose', str(ROOT / 'pose.types'), '-ep', '1',
+                '--test_data_root_pose', str(ROOT),
+                '--test_types_pose', str(ROOT / 'pose.types'),
+                '--layers', '2', '-k', '16', '-b', '4', '--egnn_attention',
+                '--compact', '--use_atomic_numbers', '--hydrogens',
+                '--radius', '6', '--edge_radius', '3'])
+    assert (run / 'checkpoints' / 'pose_ckpt_epoch_1.pt').is_file()
+    model = resume_training.main([str(run), '-ep', '3'])
+    assert model.p_epoch == 3
+    for epoch in (2, 3):
+        assert (run / 'checkpoints' / f'pose_ckpt_epoch_{epoch}.pt').is_file()
+    assert len((run / 'pose_predictions.txt').read_text().splitlines()) == 7
