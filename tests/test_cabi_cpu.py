@@ -119,3 +119,26 @@ def test_cli_flag_semantics_multitask_attention_placement():
     assert [l.node_attention for l in layers] == [False, False, False, True]
     with pytest.raises(ValueError):
         m.set_task('ranking')
+
+
+def test_entry_points_fail_loudly_without_a_gpu_path(tmp_path):
+    """Training / streaming entry points refuse what is outside the path
+    before any kernel is involved, and never fall back to the CPU."""
+    import pytest
+    import torch
+    from pointvs_b200 import train
+    from pointvs_b200._cabi import PvsError
+    with pytest.raises(NotImplementedError):
+        train.main(['lucid', str(tmp_path / 'a')])
+    with pytest.raises(RuntimeError):
+        train.main(['egnn', str(tmp_path / 'b'), '--model_task', 'both'])
+    with pytest.raises(NotImplementedError):
+        train.main(['egnn', str(tmp_path / 'c'), '--double'])
+    if not torch.cuda.is_available():
+        import pointvs_b200 as pv
+        from pointvs_b200.pipeline import ScoreStream
+        model = pv.SartorrasEGNN(tmp_path, 0, 0, None, None, silent=True,
+                                 dim_input=13, dim_output=1, k=16,
+                                 num_layers=1)
+        with pytest.raises(PvsError):
+            ScoreStream(model)
