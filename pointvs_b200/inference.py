@@ -80,7 +80,7 @@ def main(argv=None):
     parser.add_argument('test_data_root', type=str)
     parser.add_argument('--model_task', type=str,
                         help='(multitask models only) pose or affinity')
-    parser.add_argument('--math', default='fp32',
+    parser.add_argument('--math', default='bf16x3',
                         choices=['fp32', 'bf16x3', 'bf16', 'fp16x2'],
                         help='arithmetic of the per-edge contractions')
     parser.add_argument('--reference_loader', action='store_true',

@@ -107,7 +107,7 @@ def parse_args(argv=None):
     p.add_argument('--regression_loss', type=str, default='mse')
     p.add_argument('--softmax_attention', action='store_true')
     # additions of this implementation
-    p.add_argument('--math', default='fp32',
+    p.add_argument('--math', default='bf16x3',
                    choices=['fp32', 'bf16x3', 'fp16x2', 'bf16'],
                    help='arithmetic of the dense contractions (forward and '
                         'the recompute inside the backward)')
