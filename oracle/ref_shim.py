@@ -9,7 +9,10 @@ egnn_pytorch, plip, openbabel) are absent.  It is used for exactly two things:
     fixtures that pin ``oracle/egnn_oracle.py`` and ``oracle/radius_graph.py``
     to the reference's own outputs;
   * ``tests/test_oracle_vs_reference.py`` -- a live cross-check that is
-    skipped when ``/root/reference`` does not exist (i.e. on the GPU box).
+    skipped when ``/root/reference`` does not exist (i.e. on the GPU box);
+  * ``bench.py``'s CPU legs (``--impl reference`` and ``cpu_baseline``), which
+    time the reference's own classes on the host cores; on the GPU box they
+    import the untracked copy under ``oracle/_ref`` (``oracle/make_ref.py``).
 
 Nothing in ``pointvs_b200/`` may import this file.  The four third-party
 functions the EGNN path actually executes are restated from their published
@@ -24,7 +27,13 @@ import sys
 import types
 from unittest import mock
 
+# The reference's own tree when present (build container); otherwise the
+# untracked copy of its package made by oracle/make_ref.py (travels to the GPU
+# box with the gpurun snapshot: oracle/_ref is git-ignored, not gpurun-ignored).
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = '/root/reference'
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, 'point_vs')):
+    REFERENCE_ROOT = os.path.join(_HERE, '_ref')
 _MISSING_ROOTS = ('torch_scatter', 'torch_geometric', 'matplotlib', 'pymol',
                   'rdkit', 'egnn_pytorch', 'plip', 'openbabel', 'wandb')
 
