@@ -221,9 +221,24 @@ def install():
 
 
 def import_reference():
-    """Return a namespace holding the reference symbols on the hot path."""
+    """Return a namespace holding the reference symbols on the hot path.
+
+    The reference chooses its DEVICE once, at import (global_objects.py:14-22:
+    CUDA when available).  The oracle and bench.py's CPU legs want its CPU path
+    -- also on the GPU box -- so CUDA is reported unavailable while its modules
+    are imported; nothing else about the reference is changed."""
     install()
     import warnings
+    import torch
+    real_avail = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False
+    try:
+        return _import_reference(warnings)
+    finally:
+        torch.cuda.is_available = real_avail
+
+
+def _import_reference(warnings):
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         from point_vs.models.geometric.egnn_satorras import (

@@ -14,6 +14,30 @@ from . import _cabi
 from ._cabi import check, lib, ptr, stream
 
 
+# Gradient arena of the model whose `backprop()` is running (parallel.GradArena)
+# or None: the backward passes below then allocate their own zero-filled
+# gradient tensors.
+ARENA = None
+
+
+class use_arena:
+    """Context manager: parameter gradients of the backward passes inside go
+    straight into `arena`'s slots."""
+
+    def __init__(self, arena):
+        self.arena = arena
+
+    def __enter__(self):
+        global ARENA
+        self.prev, ARENA = ARENA, self.arena
+        return self.arena
+
+    def __exit__(self, *exc):
+        global ARENA
+        ARENA = self.prev
+        return False
+
+
 def _zeros_like_or_none(p):
     return None if p is None else torch.zeros_like(p, dtype=torch.float32)
 
@@ -32,18 +56,27 @@ def egnn_layer_backward(ctx, d_h, d_x, d_m):
 
     pstruct = _cabi.LayerParams(*[
         ptr(None if p is None else p.detach().contiguous()) for p in params])
-    # one zero-filled flat buffer for every parameter gradient of the layer
     by_name = dict(zip(_cabi.PARAM_FIELDS, params))
-    sizes = {name: (0 if by_name[name] is None else by_name[name].numel())
-             for name in _cabi.GRAD_FIELDS}
-    flat = torch.zeros(sum(sizes.values()), dtype=torch.float32, device=dev)
-    grads, off = {}, 0
-    for name in _cabi.GRAD_FIELDS:
-        if sizes[name]:
+    arena = ARENA
+    grads, in_arena = {}, []
+    if arena is not None:
+        # the model's gradient arena: slots are already zero
+        for name in _cabi.GRAD_FIELDS:
+            grads[name] = arena.grad_view(by_name[name])
+            if grads[name] is not None:
+                in_arena.append(by_name[name])
+    rest = [name for name in _cabi.GRAD_FIELDS
+            if by_name[name] is not None and grads.get(name) is None]
+    if rest:
+        # one zero-filled flat buffer for the remaining gradients of the layer
+        sizes = {name: by_name[name].numel() for name in rest}
+        flat = torch.zeros(sum(sizes.values()), dtype=torch.float32, device=dev)
+        off = 0
+        for name in rest:
             grads[name] = flat[off:off + sizes[name]]
             off += sizes[name]
-        else:
-            grads[name] = None
+    for name in _cabi.GRAD_FIELDS:
+        grads.setdefault(name, None)
     gstruct = _cabi.LayerGrads(*[ptr(grads[name]) for name in _cabi.GRAD_FIELDS])
 
     d_h_in = torch.empty_like(h)
@@ -59,6 +92,10 @@ def egnn_layer_backward(ctx, d_h, d_x, d_m):
             ptr(d_m), ptr(d_h_in), ptr(d_x_in), ptr(d_m_prev),
             C.byref(gstruct), ptr(ws), C.c_int64(ws.numel()), stream()),
             'pvs_egnn_layer_bwd')
+    if arena is not None and arena.reduce_in_backward and in_arena:
+        # data-parallel: this layer's slice of the arena is complete -- average
+        # it over the ranks while the next layer's backward runs
+        arena.reduce_async(*arena.span(in_arena))
     # inputs of _EGNNLayerFn.forward: layer, csr, want_m, want_side, h, x,
     # m_prev, *params
     # Parameters that cannot influence the loss get no gradient at all (None),
@@ -92,9 +129,15 @@ def linear_backward(ctx, d_out):
                                   'output features')
     need_in = ctx.needs_input_grad[0]
     d_in = torch.empty_like(inp) if need_in else None
-    d_w = torch.zeros_like(w)
-    d_b = torch.zeros(ko, dtype=torch.float32, device=inp.device) \
-        if ctx.has_bias else None
+    arena = ARENA
+    d_w = arena.grad_view(w) if arena is not None else None
+    if d_w is None:
+        d_w = torch.zeros_like(w)
+    d_b = None
+    if ctx.has_bias:
+        d_b = arena.grad_view(bias) if arena is not None else None
+        if d_b is None:
+            d_b = torch.zeros(ko, dtype=torch.float32, device=inp.device)
     nbytes = int(lib().pvs_linear_bwd_workspace_bytes(rows, ki, ko))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=inp.device)
     with torch.cuda.device(inp.device):

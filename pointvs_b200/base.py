@@ -130,6 +130,22 @@ class PointNeuralNetworkBase(nn.Module):
     def sync_gradients(self):
         """Hook for data-parallel training (pointvs_b200.parallel)."""
 
+    _grad_arena = None
+
+    def _arena_for_step(self, loss):
+        """The flat gradient arena (parallel.GradArena) the backward kernels
+        write into: one memset per step instead of a zero-filled tensor per
+        layer, and no pack / unpack copies around the data-parallel
+        all-reduce.  CUDA models only."""
+        if not loss.is_cuda:
+            return None
+        arena = self._grad_arena
+        if arena is None or not arena.matches(self):
+            from .parallel import GradArena
+            arena = GradArena(self)
+            self._grad_arena = arena
+        return arena
+
     def backprop(self, y_true, y_pred, sync=True):
         """loss -> backward -> (all-reduce) -> clip -> optimiser step
         (point_neural_network_base.py:417-429).  sync=True returns the loss as
@@ -138,7 +154,14 @@ class PointNeuralNetworkBase(nn.Module):
         caller, so the host can run ahead of the device (N1)."""
         loss = self.get_loss(y_true, y_pred)
         self.optimiser.zero_grad()
-        loss.backward()
+        arena = self._arena_for_step(loss)
+        if arena is None:
+            loss.backward()
+        else:
+            from . import backward as _bw
+            arena.begin_step()
+            with _bw.use_arena(arena):
+                loss.backward()
         self.sync_gradients()
         torch.nn.utils.clip_grad_value_(self.parameters(), 1.0)
         self.optimiser.step()

@@ -7,13 +7,15 @@ this is the multi-GPU layer the north star adds around the same model API.
   one shard per rank and every rank scores its shard locally -- no collective
   on the data path.  Only the final per-complex scores are gathered (a few
   bytes per complex) so rank 0 can write the reference's predictions file.
-* Training: replicas hold identical parameters; after backward the gradients
-  are flattened into one fp32 buffer (236 497 floats = 0.95 MB for the 8x64
-  model), summed with ONE all-reduce over NCCL/NVLink and divided by the world
-  size, *before* `clip_grad_value_` and the optimiser step, so the clip sees
-  the averaged gradient exactly as a single process with the whole batch would
-  (reference order of operations: point_neural_network_base.py:417-429).
-  The message is latency-bound on NVSwitch, so it is a single bucket.
+* Training: replicas hold identical parameters.  Every parameter gradient
+  lives in one flat fp32 arena (236 497 floats = 0.95 MB for the 8x64 model)
+  that the backward kernels write directly; each EGNN layer's slice is
+  averaged over NCCL/NVLink as soon as that layer's backward has been issued
+  (overlapping the next layer's backward), the rest right after, all *before*
+  `clip_grad_value_` and the optimiser step, so the clip sees the averaged
+  gradient exactly as a single process with the whole batch would (reference
+  order of operations: point_neural_network_base.py:417-429).  No pack / unpack
+  copies: `p.grad` is a view of the arena.
 """
 import numpy as np
 import torch
@@ -61,48 +63,175 @@ def gather_scores(local_indices, local_scores, n_total, group=None):
     return out
 
 
+class GradArena:
+    """One flat fp32 buffer with a slot per parameter of `module`.
+
+    The backward passes (pointvs_b200.backward) write their parameter
+    gradients straight into the slots, so a training step needs one memset
+    instead of a zero-filled tensor per layer, and a data-parallel step
+    all-reduces slices of the buffer with no pack / unpack copies: after the
+    reduction every `p.grad` is simply re-pointed at its slot.  Slots follow
+    `module.parameters()` order, so the parameters of one EGNN layer are
+    contiguous and a layer's gradients can be reduced as soon as its backward
+    has been issued, while the next layer's backward runs (K5 in SURVEY.md).
+    """
+
+    ALIGN = 4          # floats: every slot starts on a 16-byte boundary
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        self.slots, off = {}, 0
+        for p in self.params:
+            self.slots[p.data_ptr()] = (off, p.numel(), tuple(p.shape))
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = off
+        dev = self.params[0].device if self.params else torch.device('cpu')
+        self.flat = torch.zeros(max(1, off), dtype=torch.float32, device=dev)
+        self.group = None
+        self.reduce_in_backward = False   # set by GradAllReducer
+        self._handed, self._works, self._reduced = set(), [], []
+
+    def matches(self, module):
+        ps = [p for p in module.parameters() if p.requires_grad]
+        return len(ps) == len(self.params) and all(
+            p.data_ptr() in self.slots and p.device == self.flat.device
+            for p in ps)
+
+    def begin_step(self):
+        """Zero every slot (one kernel) and forget the previous step."""
+        self.flat.zero_()
+        self._handed.clear()
+        self._works.clear()
+        self._reduced.clear()
+
+    def view(self, param):
+        off, n, shape = self.slots[param.data_ptr()]
+        return self.flat[off:off + n].view(shape)
+
+    def grad_view(self, param):
+        """A fresh view of `param`'s (zeroed) slot for a backward pass to
+        accumulate into, or None when the parameter has no slot or has
+        already handed its slot out in this step (a parameter used twice:
+        autograd must add the second contribution itself)."""
+        if param is None:
+            return None
+        key = param.data_ptr()
+        if key not in self.slots or key in self._handed:
+            return None
+        self._handed.add(key)
+        return self.view(param)
+
+    def span(self, params):
+        """[lo, hi) of the slots of `params` (None entries are skipped)."""
+        lo, hi = None, None
+        for p in params:
+            if p is None or p.data_ptr() not in self.slots:
+                continue
+            off, n, _ = self.slots[p.data_ptr()]
+            lo = off if lo is None else min(lo, off)
+            hi = off + n if hi is None else max(hi, off + n)
+        return lo, hi
+
+    # -- data-parallel reduction -------------------------------------------------
+    def _world(self):
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def _all_reduce(self, lo, hi):
+        t = self.flat[lo:hi]
+        if dist.get_backend(self.group) == 'nccl':
+            self._works.append((dist.all_reduce(
+                t, op=dist.ReduceOp.AVG, group=self.group, async_op=True), None))
+        else:       # gloo (CPU tests) has no AVG
+            self._works.append((dist.all_reduce(
+                t, op=dist.ReduceOp.SUM, group=self.group, async_op=True), t))
+        self._reduced.append((lo, hi))
+
+    def reduce_async(self, lo, hi):
+        """Average flat[lo:hi) over the ranks on the collective's own stream;
+        called from inside backward right after the kernels that fill the
+        range have been issued."""
+        if lo is None or hi is None or hi <= lo or self._world() == 1:
+            return
+        self._all_reduce(lo, hi)
+
+    def finish_reduce(self):
+        """Reduce whatever reduce_async has not covered, then wait."""
+        world = self._world()
+        if world > 1:
+            covered = sorted(self._reduced)
+            pos, gaps = 0, []
+            for lo, hi in covered:
+                if lo > pos:
+                    gaps.append((pos, lo))
+                pos = max(pos, hi)
+            if pos < self.numel:
+                gaps.append((pos, self.numel))
+            for lo, hi in gaps:
+                self._all_reduce(lo, hi)
+            for work, t in self._works:
+                work.wait()
+                if t is not None:
+                    t.div_(world)
+        self._works.clear()
+        self._reduced.clear()
+
+    def in_reduced_span(self, param):
+        off, n, _ = self.slots[param.data_ptr()]
+        return any(lo < off + n and off < hi for lo, hi in self._reduced)
+
+
 class GradAllReducer:
-    """Averages the gradients of `module` across ranks with one flat
-    all-reduce.  Install with `attach(model)`: the training loop's
-    `backprop()` then calls it between backward and clip/step."""
+    """Averages the gradients of `module` across ranks through a GradArena.
+    Install with `attach(model)`: the training loop's `backprop()` then calls
+    `sync()` between backward and clip/step.
+
+    Arena-aware backward passes (the EGNN model on CUDA) have already written
+    into the arena and started per-layer reductions; gradients produced by
+    plain autograd (any other module) are copied into their slots first.
+    Either way every `p.grad` ends up as a view of the reduced arena, and a
+    parameter whose gradient is None stays None (an optimiser with weight
+    decay must skip it, exactly as a single process would)."""
 
     def __init__(self, module, group=None):
         self.module = module
         self.group = group
-        self.params = [p for p in module.parameters() if p.requires_grad]
-        self.numel = sum(p.numel() for p in self.params)
-        self._flat = None
+        self.arena = None
+        self.numel = sum(p.numel() for p in module.parameters()
+                         if p.requires_grad)
 
-    def _buffer(self, device):
-        if self._flat is None or self._flat.device != device:
-            self._flat = torch.zeros(self.numel, dtype=torch.float32,
-                                     device=device)
-        return self._flat
+    def _arena(self):
+        if self.arena is None or not self.arena.matches(self.module):
+            arena = getattr(self.module, '_grad_arena', None)
+            if arena is None or not arena.matches(self.module):
+                arena = GradArena(self.module)
+                if hasattr(self.module, '_grad_arena'):
+                    self.module._grad_arena = arena
+            arena.group = self.group
+            arena.reduce_in_backward = True
+            self.arena = arena
+        return self.arena
 
     def sync(self):
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return
-        device = self.params[0].device
-        flat = self._buffer(device)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                flat[off:off + n].zero_()
-            else:
-                flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-        flat.div_(dist.get_world_size(self.group))
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            # a parameter unused on this rank is unused on every rank (same
-            # model, same task): leave its grad None so the optimiser skips
-            # it exactly as a single process would
-            if p.grad is not None:
-                p.grad.copy_(flat[off:off + n].view_as(p))
-            off += n
+        arena = self._arena()
+        with torch.no_grad():
+            for p in arena.params:
+                # a slot handed to an arena-aware backward already holds this
+                # step's gradient (and may be mid-reduction): never write it
+                if p.grad is None or p.data_ptr() in arena._handed:
+                    continue
+                v = arena.view(p)
+                if p.grad.data_ptr() != v.data_ptr():
+                    if arena.in_reduced_span(p):
+                        raise RuntimeError(
+                            'a plain-autograd gradient lies inside a span that '
+                            'was reduced during backward')
+                    v.copy_(p.grad)
+            arena.finish_reduce()
+            for p in arena.params:
+                if p.grad is not None:
+                    p.grad = arena.view(p)
 
     def attach(self, model=None):
         (model or self.module).sync_gradients = self.sync

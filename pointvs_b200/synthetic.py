@@ -89,3 +89,50 @@ def synthetic_pocket_poses(first_pose, n_poses, n_pocket=800, n_lig=30,
         ptr.append(ptr[-1] + n_all)
     return (np.concatenate(coords), np.concatenate(bps), np.concatenate(feats),
             np.asarray(ptr, dtype=np.int32))
+
+
+POSE_BLOCK = 4096
+
+
+def synthetic_pocket(n_pocket=800, n_lig=30, density=DENSITY):
+    """The fixed pocket of `synthetic_pocket_poses` (seed 0): coords f64
+    [n_pocket, 3], atom types int64 [n_pocket], and the cavity radius."""
+    rng = np.random.default_rng(0)
+    n_all = n_pocket + n_lig
+    ball_r = (3.0 * n_all / (4.0 * np.pi * density)) ** (1.0 / 3.0)
+    cavity_r = (3.0 * n_lig / (4.0 * np.pi * density)) ** (1.0 / 3.0)
+    direction = rng.normal(size=(n_pocket, 3))
+    direction /= np.linalg.norm(direction, axis=1, keepdims=True)
+    u = rng.random(n_pocket)
+    radius = (cavity_r ** 3 + u * (ball_r ** 3 - cavity_r ** 3)) ** (1.0 / 3.0)
+    pocket = (direction * radius[:, None]).astype(np.float32).astype(np.float64)
+    return pocket, rng.integers(0, N_TYPES, n_pocket), cavity_r
+
+
+def synthetic_ligand_poses(first_pose, n_poses, n_lig=30, density=DENSITY):
+    """Ligand poses for a screening sweep over millions of poses: pose p is a
+    pure function of p (block p // 4096 seeds one generator, the pose is row
+    p % 4096 of its draw), generated a block at a time so that 1 M poses cost
+    seconds, not a generator construction per pose.  Same distribution as the
+    ligands of `synthetic_pocket_poses` (uniform in the pocket's cavity).
+    Returns coords f64 [n_poses, n_lig, 3] (float32-representable) and atom
+    types int16 [n_poses, n_lig]."""
+    cavity_r = (3.0 * n_lig / (4.0 * np.pi * density)) ** (1.0 / 3.0)
+    coords = np.empty((n_poses, n_lig, 3), dtype=np.float64)
+    types = np.empty((n_poses, n_lig), dtype=np.int16)
+    done = 0
+    while done < n_poses:
+        p = first_pose + done
+        blk, row = divmod(p, POSE_BLOCK)
+        take = min(POSE_BLOCK - row, n_poses - done)
+        rng = np.random.default_rng(2_000_003 + blk)
+        d = rng.normal(size=(POSE_BLOCK, n_lig, 3))
+        rad = cavity_r * rng.random((POSE_BLOCK, n_lig)) ** (1.0 / 3.0)
+        ty = rng.integers(0, N_TYPES, (POSE_BLOCK, n_lig))
+        d = d[row:row + take]
+        d /= np.linalg.norm(d, axis=2, keepdims=True)
+        c = d * rad[row:row + take, :, None]
+        coords[done:done + take] = c.astype(np.float32).astype(np.float64)
+        types[done:done + take] = ty[row:row + take]
+        done += take
+    return coords, types
