@@ -24,22 +24,54 @@ DEVICE = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
 
 
 def find_latest_checkpoint(root, model_task=None):
-    """Latest `*ckpt_epoch_N.pt` under root/checkpoints (utils.py:33-45)."""
+    """Most recently created checkpoint under root/checkpoints, as the
+    reference picks it (utils.py:33-45: glob `<model_task>*.pt`, newest by
+    st_ctime).  In a multitask pose -> affinity run that is the affinity
+    checkpoint written last, not the file with the largest epoch number."""
+    if model_task is not None and model_task not in ('pose', 'affinity'):
+        raise RuntimeError(
+            'model_task must be either pose or affinity if specified.')
     root = Path(root).expanduser()
     ckpt_dir = root / 'checkpoints' if (root / 'checkpoints').is_dir() else root
-    pattern = '*ckpt_epoch_*.pt' if model_task is None else \
-        f'{model_task}_ckpt_epoch_*.pt'
-    best, best_epoch = None, -1
-    for f in ckpt_dir.glob(pattern):
-        try:
-            epoch = int(f.stem.split('_')[-1])
-        except ValueError:
-            continue
-        if epoch > best_epoch:
-            best, best_epoch = f, epoch
-    if best is None:
-        raise FileNotFoundError(f'no checkpoint under {ckpt_dir}')
-    return best
+    found = list(ckpt_dir.glob((model_task or '') + '*.pt'))
+    if not found:
+        raise FileNotFoundError(f'No checkpoints found in {root}.')
+    # ties (same ctime tick) go to the later file name, deterministically
+    return max(found, key=lambda f: (f.stat().st_ctime_ns, f.name))
+
+
+def top_n(predictions_file, n=1):
+    """Fraction of receptors whose n best-scored poses contain an active
+    (analysis/top_n.py:41-49 of the reference: predictions grouped by the
+    receptor column, sorted by y_pred descending)."""
+    scores = {}
+    with open(Path(predictions_file).expanduser(), encoding='utf-8') as f:
+        for line in f:
+            parts = line.split()
+            if len(parts) < 5:
+                continue
+            scores.setdefault(parts[3], []).append(
+                (float(parts[2]), int(float(parts[0]))))
+    if not scores:
+        return 0.0
+    hits = 0
+    for vals in scores.values():
+        vals.sort(key=lambda v: v[0], reverse=True)
+        hits += 1 if sum(v[1] for v in vals[:n]) else 0
+    return hits / len(scores)
+
+
+def get_regression_pearson(predictions_file):
+    """(r, p) of y_true vs y_pred in a predictions file (utils.py:189-198)."""
+    from scipy.stats import pearsonr
+    true, pred = [], []
+    with open(Path(predictions_file).expanduser(), encoding='utf-8') as f:
+        for line in f:
+            parts = line.split()
+            if len(parts) >= 5:
+                true.append(float(parts[0]))
+                pred.append(float(parts[2]))
+    return pearsonr(true, pred)
 
 
 class PointNeuralNetworkBase(nn.Module):
@@ -228,8 +260,13 @@ class PointNeuralNetworkBase(nn.Module):
         if not self.only_save_best_models:
             self.save()
         if epoch_end_validation_set is not None and epoch < epochs:
-            self.val(epoch_end_validation_set, predictions_file=Path(
-                self.predictions_file.parent, f'predictions_epoch_{epoch}.txt'))
+            best = self.val(
+                epoch_end_validation_set, predictions_file=Path(
+                    self.predictions_file.parent,
+                    f'predictions_epoch_{epoch}.txt'),
+                top1_on_end=top1_on_end)
+            if self.only_save_best_models and best:
+                self.save()
 
     # -- scoring -------------------------------------------------------------------
     def val(self, data_loader, predictions_file=None, top1_on_end=False,
@@ -263,6 +300,19 @@ class PointNeuralNetworkBase(nn.Module):
                     pending = []
                     with open(predictions_file, 'a', encoding='utf-8') as f:
                         f.write(text)
+        if top1_on_end:
+            # best-model tracking (point_neural_network_base.py:330-360): top-1
+            # for pose classification, Pearson r (p < 0.05) for regression
+            if self.model_task == 'classification':
+                metric = top_n(predictions_file)
+                best = metric > self.test_metric
+            else:
+                metric, p_value = get_regression_pearson(predictions_file)
+                best = p_value < 0.05 and metric > self.test_metric
+            if best:
+                self.test_metric = metric
+            if self.only_save_best_models and not best:
+                return False
         return True
 
     def _format_predictions(self, y_pred, y_true, ligands, receptors):
@@ -314,10 +364,12 @@ class PointNeuralNetworkBase(nn.Module):
     @staticmethod
     def _transform_names(d):
         """Key renames of old reference checkpoints (:520-526)."""
+        import re
         return OrderedDict(
-            (k.replace('edge_attention_mlp', 'att_mlp')
-              .replace('node_attention_mlp', 'node_att_mlp')
-              .replace('att_mlp.2.', 'att_mlp.0.'), v) for k, v in d.items())
+            (re.sub(r'(?<![A-Za-z_])att_mlp\.2\.', 'att_mlp.0.',
+                    k.replace('edge_attention_mlp', 'att_mlp')
+                     .replace('node_attention_mlp', 'node_att_mlp')), v)
+            for k, v in d.items())
 
     def load_weights(self, checkpoint_file, silent=False):
         checkpoint_file = Path(checkpoint_file).expanduser()
@@ -335,13 +387,21 @@ class PointNeuralNetworkBase(nn.Module):
         if self.model_task == saved_task:
             try:
                 self.load_state_dict(state)
-            except RuntimeError:
+            except RuntimeError as exc:
+                # old reference checkpoints use other key names (:520-526);
+                # a genuine shape mismatch must surface as it is
+                msg = str(exc)
+                if 'Missing key' not in msg and 'Unexpected key' not in msg:
+                    raise
                 self.load_state_dict(self._transform_names(state))
             try:
                 self.optimiser.load_state_dict(
                     checkpoint['optimiser_state_dict'])
-            except (ValueError, KeyError):
-                pass
+            except (ValueError, KeyError) as exc:
+                import warnings
+                warnings.warn(
+                    f'optimiser state of {checkpoint_file} not restored '
+                    f'({exc!r}): training resumes with fresh optimiser moments')
             self.p_epoch = checkpoint.get('p_epoch', checkpoint.get('epoch', 0))
             self.a_epoch = checkpoint.get('a_epoch', 0)
         else:

@@ -73,7 +73,13 @@ class ScoreStream:
         """src (host) -> slot's device buffer on the copy stream.  A tensor
         that already lives on the device is used where it is."""
         if isinstance(src, torch.Tensor) and src.is_cuda:
-            return src if src.dtype == dtype else src.to(dtype)
+            if src.dtype != dtype:
+                # a conversion here would run on the copy stream, unordered
+                # with the stream that produced `src`: make the caller do it
+                raise TypeError(
+                    f'ScoreStream: device-resident {name} must already be '
+                    f'{dtype} (got {src.dtype}); convert it on your stream')
+            return src
         src = self._as_cpu_tensor(src, dtype)
         n = src.shape[0]
         dev = slot.dev.get(name)

@@ -123,6 +123,13 @@ def parse_args(argv=None):
 
 def main(argv=None):
     args = parse_args(argv)
+    # the --load_args overlay comes first (point_vs.py:54-58), so that values
+    # it sets (double, synthpharm, model ...) meet the same checks as flags
+    if args.load_args is not None:
+        with open(Path(args.load_args).expanduser(), encoding='utf-8') as f:
+            for key, value in (yaml.safe_load(f) or {}).items():
+                if hasattr(args, key):
+                    setattr(args, key, value)
     if args.model not in ('egnn', 'multitask'):
         raise NotImplementedError(
             f"model '{args.model}' is outside the B200 hot path "
@@ -135,12 +142,6 @@ def main(argv=None):
         raise NotImplementedError('--double: the CUDA path computes in fp32')
     if args.synth_pharm or args.synthpharm:
         raise NotImplementedError('synthpharm datasets are outside this path')
-    if args.load_args is not None:
-        with open(Path(args.load_args).expanduser(), encoding='utf-8') as f:
-            for key, value in (yaml.safe_load(f) or {}).items():
-                if hasattr(args, key):
-                    setattr(args, key, value)
-
     if args.wandb_project is None:
         save_path = Path(args.save_path).expanduser()
     elif args.wandb_run is None:
