@@ -20,6 +20,7 @@
 //   wgrad / finalize: dW = A^T B for the node-level weights, reduce per-CTA
 //              partials, dh += dP.W1a + dQ.W1b
 #include "egnn_common.cuh"
+#include "egnn_bwd_common.cuh"
 #include "tile_gemm.cuh"
 
 namespace pvs {
@@ -494,32 +495,6 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
 // ---------------------------------------------------------------------------
 // edge backward
 // ---------------------------------------------------------------------------
-constexpr int EP_W2 = 0, EP_WC1 = 4096, EP_B2 = 8192, EP_BC1 = 8256, EP_WC2 = 8320,
-              EP_WA = 8384, EP_WR = 8448, EP_T = 8512, EP_BA = 9024, EP_GATE = 9025,
-              EP_STRIDE = 9088;
-
-struct EdgeBwdArgs {
-    const int32_t *row_ptr, *col, *tile_ptr, *n_tiles;
-    const uint8_t *attr;
-    const float *P, *Q, *x_in, *m_prev;
-    const float *dM;        // [N][64]
-    const float *d_x_out;   // [N][3] or null
-    const float *d_m_out;   // [E][k] or null
-    float *dP;              // [N][64]
-    float *DT1;             // [E][64]
-    float *DD;              // [E][3]
-    float *d_x_in;          // [N][3]
-    float *d_m_prev;        // [E][k] or null
-    float *partial;         // [grid][EP_STRIDE]
-    const float *alpha_in;  // [E] softmax attention values (softmax mode) or null
-    const float *seg_s;     // [N] sum over the dst segment of alpha * d(alpha)
-    const float *edge_w1, *edge_w2, *edge_b2, *coord_w1, *coord_b1, *coord_w2;
-    const float *att_w, *att_b, *edge_gate;
-    int k, in_e, n_classes;
-    uint32_t flags;
-    int att_act;
-};
-
 struct EdgeBwdSmem {
     float W2t[64 * 64], W2n[64 * 64], Wc1t[64 * 64], Wc1n[64 * 64];
     float B1[TE * LDT];   // s1
@@ -1308,10 +1283,17 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
     eb.k = k; eb.in_e = in_e; eb.n_classes = cfg->n_edge_classes; eb.flags = f;
     eb.att_act = cfg->att_act;
     {
-        size_t smem = sizeof(EdgeBwdSmem);
-        rc = ensure_smem(egnn_edge_bwd_kernel, smem);
-        if (rc) return rc;
-        egnn_edge_bwd_kernel<<<w.edge_grid, BT, smem, st>>>(eb);
+        // tcgen05 kernel (egnn_edge_bwd_tc.cu) in the tensor-core modes, for
+        // the configurations it covers; fp32 FFMA kernel otherwise
+        if (cfg->math != PVS_MATH_FP32 && edge_bwd_tc_supported(eb)) {
+            rc = launch_edge_bwd_tc(eb, w.edge_grid, st);
+            if (rc) return rc;
+        } else {
+            size_t smem = sizeof(EdgeBwdSmem);
+            rc = ensure_smem(egnn_edge_bwd_kernel, smem);
+            if (rc) return rc;
+            egnn_edge_bwd_kernel<<<w.edge_grid, BT, smem, st>>>(eb);
+        }
         edge_bwd_reduce_kernel<<<(EP_STRIDE + 255) / 256, 256, 0, st>>>(
             w.edge_partial, w.edge_grid, *grads, k, in_e, col_r, cfg->n_edge_classes);
         csc_gather_kernel<<<(n + 7) / 8, 256, 0, st>>>(csc_ptr, csc_eid, n, w.DT1, w.DD, w.dQ, d_x_in);

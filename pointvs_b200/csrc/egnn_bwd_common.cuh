@@ -1,0 +1,40 @@
+// Argument block and per-CTA partial layout shared by the two edge-backward
+// kernels (egnn_bwd.cu: fp32 FFMA; egnn_edge_bwd_tc.cu: tcgen05).
+#pragma once
+#include "egnn_common.cuh"
+
+namespace pvs {
+
+constexpr int EP_W2 = 0, EP_WC1 = 4096, EP_B2 = 8192, EP_BC1 = 8256, EP_WC2 = 8320,
+              EP_WA = 8384, EP_WR = 8448, EP_T = 8512, EP_BA = 9024, EP_GATE = 9025,
+              EP_STRIDE = 9088;
+
+struct EdgeBwdArgs {
+    const int32_t *row_ptr, *col, *tile_ptr, *n_tiles;
+    const uint8_t *attr;
+    const float *P, *Q, *x_in, *m_prev;
+    const float *dM;        // [N][64]
+    const float *d_x_out;   // [N][3] or null
+    const float *d_m_out;   // [E][k] or null
+    float *dP;              // [N][64]
+    float *DT1;             // [E][64]
+    float *DD;              // [E][3]
+    float *d_x_in;          // [N][3]
+    float *d_m_prev;        // [E][k] or null
+    float *partial;         // [grid][EP_STRIDE]
+    const float *alpha_in;  // [E] softmax attention values (softmax mode) or null
+    const float *seg_s;     // [N] sum over the dst segment of alpha * d(alpha)
+    const float *edge_w1, *edge_w2, *edge_b2, *coord_w1, *coord_b1, *coord_w2;
+    const float *att_w, *att_b, *edge_gate;
+    int k, in_e, n_classes;
+    uint32_t flags;
+    int att_act;
+};
+
+// tcgen05 edge backward (egnn_edge_bwd_tc.cu).  Supports the configurations
+// without edge residual / softmax attention / incoming message gradients; the
+// caller falls back to the FFMA kernel otherwise.
+bool edge_bwd_tc_supported(const EdgeBwdArgs &a);
+int launch_edge_bwd_tc(const EdgeBwdArgs &a, int grid, cudaStream_t st);
+
+}  // namespace pvs
