@@ -46,14 +46,15 @@ wgrad_kernel(const float *__restrict__ A, int lda, int ko,
     const int r_lo = blockIdx.x * rows_per, r_hi = min(rows, r_lo + rows_per);
     float acc[2][4][4] = {};
     float bsum[4] = {};
+    const int nj = ki > 64 ? 2 : 1;      // column halves of B actually present
     for (int r0 = r_lo; r0 < r_hi; r0 += WR) {
         __syncthreads();
         for (int idx = tid; idx < WR * 64; idx += BT) {
             int r = idx >> 6, c = idx & 63;
             As[r * 68 + c] = (r0 + r < r_hi && c < ko) ? A[(size_t)(r0 + r) * lda + c] : 0.0f;
         }
-        for (int idx = tid; idx < WR * 128; idx += BT) {
-            int r = idx >> 7, c = idx & 127;
+        for (int idx = tid; idx < WR * 64 * nj; idx += BT) {
+            int r = idx / (64 * nj), c = idx - r * 64 * nj;
             Bs[r * 132 + c] = (r0 + r < r_hi && c < ki) ? B[(size_t)(r0 + r) * ldb + c] : 0.0f;
         }
         __syncthreads();
@@ -63,6 +64,7 @@ wgrad_kernel(const float *__restrict__ A, int lda, int ko,
             const float av[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
+                if (j >= nj) break;
                 const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[r * 132 + 4 * tk + 64 * j]);
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
@@ -112,9 +114,10 @@ __global__ void wgrad_reduce_kernel(const float *__restrict__ partial, int n_cta
 }
 
 static int wgrad_ctas(int rows) {
-    // >= 256 rows per CTA: the partials (one [64 x 128] block per CTA) are what
-    // the reduce kernel has to read back
-    int g = (rows + 255) / 256;
+    // >= 128 rows per CTA: the partials (one [64 x 128] block per CTA) are what
+    // the reduce kernel has to read back.  (256 rows per CTA left a 16-complex
+    // training batch on 63 of the 148 SMs.)
+    int g = (rows + 127) / 128;
     int cap = num_sms() * 2;
     if (g > cap) g = cap;
     return g < 1 ? 1 : g;
