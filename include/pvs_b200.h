@@ -122,6 +122,13 @@ typedef struct pvs_layer_config {
     void *ev_edge_end;      /* around the edge stage (NULL = none): lets a     */
                             /* caller time the dominant kernel with no extra   */
                             /* host work inside a step                          */
+    const void *saved_fwd_workspace; /* pvs_egnn_layer_bwd only (NULL = recompute):
+                               the workspace pvs_egnn_layer_fwd was given for this
+                               layer, same inputs, parameters and math, contents
+                               untouched since.  The backward then reads P, Q and
+                               M from it instead of re-running the node_pre and
+                               edge stages (tensor-core modes without softmax
+                               attention / GraphNorm; ignored otherwise).       */
 } pvs_layer_config;
 
 #define PVS_STAGE_NODE_PRE 1 /* P = h W1a^T + b1, Q = h W1b^T                 */

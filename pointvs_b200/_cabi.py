@@ -51,7 +51,8 @@ class LayerConfig(C.Structure):
     _fields_ = [('k', C.c_int32), ('n_edge_classes', C.c_int32),
                 ('flags', C.c_uint32), ('att_act', C.c_int32),
                 ('math', C.c_int32), ('stages', C.c_int32),
-                ('ev_edge_begin', C.c_void_p), ('ev_edge_end', C.c_void_p)]
+                ('ev_edge_begin', C.c_void_p), ('ev_edge_end', C.c_void_p),
+                ('saved_fwd_workspace', C.c_void_p)]
 
 
 PARAM_FIELDS = ('edge_w1', 'edge_b1', 'edge_w2', 'edge_b2', 'coord_w1',

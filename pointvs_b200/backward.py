@@ -46,6 +46,9 @@ def egnn_layer_backward(ctx, d_h, d_x, d_m):
     layer, csr = ctx.layer, ctx.csr
     h, x, m_prev, *params = ctx.saved_tensors
     cfg = layer.c_config()
+    fwd_ws = getattr(ctx, 'fwd_ws', None)
+    if fwd_ws is not None and getattr(ctx, 'fwd_math', None) == layer.math:
+        cfg.saved_fwd_workspace = ptr(fwd_ws)
     n, e, k = csr.n_nodes, csr.n_edges, layer.hidden_nf
     dev = h.device
     d_h = torch.zeros_like(h) if d_h is None else d_h.contiguous().float()
@@ -108,10 +111,17 @@ def egnn_layer_backward(ctx, d_h, d_x, d_m):
         unused.update(('coord_w1', 'coord_b1', 'coord_w2'))
     if m_prev is None:          # first layer: no incoming messages to gate
         unused.add('edge_gate')
+    arena_ptrs = {p.data_ptr() for p in in_arena}
     param_grads = []
     for name, p in zip(_cabi.PARAM_FIELDS, params):
         if p is None or name not in grads or grads[name] is None \
                 or name in unused:
+            param_grads.append(None)
+        elif p.data_ptr() in arena_ptrs:
+            # the gradient already sits in the parameter's arena slot, which
+            # becomes `p.grad` (GradArena.attach_grads): nothing for autograd
+            # to accumulate
+            arena.grant(p)
             param_grads.append(None)
         else:
             param_grads.append(grads[name].reshape(p.shape))
@@ -131,11 +141,13 @@ def linear_backward(ctx, d_out):
     d_in = torch.empty_like(inp) if need_in else None
     arena = ARENA
     d_w = arena.grad_view(w) if arena is not None else None
+    w_in_arena = d_w is not None
     if d_w is None:
         d_w = torch.zeros_like(w)
-    d_b = None
+    d_b, b_in_arena = None, False
     if ctx.has_bias:
         d_b = arena.grad_view(bias) if arena is not None else None
+        b_in_arena = d_b is not None
         if d_b is None:
             d_b = torch.zeros(ko, dtype=torch.float32, device=inp.device)
     nbytes = int(lib().pvs_linear_bwd_workspace_bytes(rows, ki, ko))
@@ -146,6 +158,12 @@ def linear_backward(ctx, d_out):
             _cabi.ACT[ctx.act], ptr(d_out), ko, ptr(d_in), ki, ptr(d_w), ki,
             ptr(d_b), ptr(ws), C.c_int64(ws.numel()), stream()),
             'pvs_linear_bwd')
+    if w_in_arena:
+        arena.grant(w)
+        d_w = None
+    if b_in_arena:
+        arena.grant(bias)
+        d_b = None
     return d_in, d_w, d_b, None
 
 

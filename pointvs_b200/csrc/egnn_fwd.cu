@@ -717,6 +717,12 @@ int64_t fwd_recompute_bytes(int n, int e, uint32_t flags) {
 // Forward recompute for the backward pass (64-wide pitch): P, Q, M (and the
 // softmax attention values + messages, and the GraphNorm pre-activation V with
 // its batch statistics).  No h_out / x_out is produced.
+FwdWorkspace fwd_saved(const void *saved_workspace, int n, int e, uint32_t flags) {
+    // same carve as pvs_egnn_layer_fwd in the tensor-core modes (pitch 64)
+    return carve_workspace((void *)align_up((int64_t)(uintptr_t)saved_workspace, 256), n, e, 64,
+                           flags);
+}
+
 int fwd_recompute(const pvs_graph *g, const pvs_layer_config *cfg, const pvs_layer_params *p,
                   const float *h_in, const float *x_in, const float *m_prev, void *ws_base,
                   FwdWorkspace *out, cudaStream_t st) {

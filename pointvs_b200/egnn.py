@@ -125,6 +125,10 @@ class _EGNNLayerFn(torch.autograd.Function):
                 if split:
                     timer.end(stages)
         ctx.layer, ctx.csr = layer, csr
+        # training: keep this layer's workspace (P, Q, M: 768 B per node) so
+        # the backward need not re-run the node_pre and edge stages
+        ctx.fwd_ws = ws if (any(ctx.needs_input_grad) and not split) else None
+        ctx.fwd_math = layer.math
         ctx.save_for_backward(h, x, m_prev, *params)
         ctx.mark_non_differentiable(*[t for t in (att, natt) if t is not None])
         if x_out is None:
@@ -233,7 +237,7 @@ class EGNNLayer(nn.Module):
         act = 'none' if self.softmax_attention else self.attention_activation_fn
         return _cabi.LayerConfig(self.hidden_nf, self.edges_in_d,
                                  self.c_flags(), _cabi.ACT[act],
-                                 _cabi.MATH[self.math], 0, None, None)
+                                 _cabi.MATH[self.math], 0, None, None, None)
 
     def param_list(self):
         """Parameters in _cabi.PARAM_FIELDS order (None where absent)."""

@@ -90,6 +90,12 @@ class GradArena:
         self.group = None
         self.reduce_in_backward = False   # set by GradAllReducer
         self._handed, self._works, self._reduced = set(), [], []
+        # one long-lived view per slot: `p.grad` of a parameter whose gradient
+        # the arena-aware backward passes produce IS this view, step after step
+        self.views = {p.data_ptr(): self.flat[o:o + n].view(shape)
+                      for p, (o, n, shape) in ((p, self.slots[p.data_ptr()])
+                                               for p in self.params)}
+        self._granted, self._assigned = set(), set()
 
     def matches(self, module):
         ps = [p for p in module.parameters() if p.requires_grad]
@@ -98,28 +104,59 @@ class GradArena:
             for p in ps)
 
     def begin_step(self):
-        """Zero every slot (one kernel) and forget the previous step."""
+        """Zero every slot (one kernel) and forget the previous step.  Gradients
+        that plain autograd left on a parameter in the previous step are
+        dropped here (what `optimiser.zero_grad()` would do); gradients that
+        are views of the arena stay attached and are simply zeroed."""
+        for p in self.params:
+            if p.grad is not None and p.data_ptr() not in self._assigned:
+                p.grad = None
         self.flat.zero_()
         self._handed.clear()
+        self._granted.clear()
         self._works.clear()
         self._reduced.clear()
 
     def view(self, param):
-        off, n, shape = self.slots[param.data_ptr()]
-        return self.flat[off:off + n].view(shape)
+        return self.views[param.data_ptr()]
 
     def grad_view(self, param):
-        """A fresh view of `param`'s (zeroed) slot for a backward pass to
-        accumulate into, or None when the parameter has no slot or has
-        already handed its slot out in this step (a parameter used twice:
-        autograd must add the second contribution itself)."""
+        """`param`'s (zeroed) slot for a backward pass to accumulate into, or
+        None when the parameter has no slot or has already handed its slot out
+        in this step (a parameter used twice: autograd must add the second
+        contribution itself)."""
         if param is None:
             return None
         key = param.data_ptr()
         if key not in self.slots or key in self._handed:
             return None
         self._handed.add(key)
-        return self.view(param)
+        return self.views[key]
+
+    def grant(self, param):
+        """The backward pass that was handed `param`'s slot reports that the
+        slot now holds a real gradient (parameters that cannot influence the
+        loss are handed out but never granted: their `.grad` stays None, as
+        under the reference's autograd)."""
+        self._granted.add(param.data_ptr())
+
+    def attach_grads(self):
+        """After backward: `p.grad` = its arena view for every granted
+        parameter, None for a parameter that was granted in an earlier step but
+        not in this one (e.g. the other head after a task switch).  No tensor is
+        created and no kernel runs; in steady state this is two set compares."""
+        if self._granted == self._assigned and all(
+                p.grad is not None for p in self.params
+                if p.data_ptr() in self._assigned):
+            return
+        for p in self.params:
+            key = p.data_ptr()
+            if key in self._granted:
+                if p.grad is None or p.grad.data_ptr() != self.views[key].data_ptr():
+                    p.grad = self.views[key]
+            elif key in self._assigned:
+                p.grad = None
+        self._assigned = set(self._granted)
 
     def span(self, params):
         """[lo, hi) of the slots of `params` (None entries are skipped)."""
@@ -220,6 +257,8 @@ class GradAllReducer:
                 # a slot handed to an arena-aware backward already holds this
                 # step's gradient (and may be mid-reduction): never write it
                 if p.grad is None or p.data_ptr() in arena._handed:
+                    continue
+                if p.data_ptr() in arena._assigned:
                     continue
                 v = arena.view(p)
                 if p.grad.data_ptr() != v.data_ptr():

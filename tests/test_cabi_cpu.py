@@ -64,7 +64,7 @@ def test_argument_validation_happens_before_any_launch():
 
 def test_structs_match_header_layout():
     from pointvs_b200 import _cabi
-    assert C.sizeof(_cabi.LayerConfig) == 6 * 4 + 2 * 8
+    assert C.sizeof(_cabi.LayerConfig) == 6 * 4 + 3 * 8
     assert C.sizeof(_cabi.LayerParams) == 20 * 8
     assert C.sizeof(_cabi.LayerGrads) == 20 * 8
     assert C.sizeof(_cabi.Graph) == 8 + 5 * 8 + 8 + 2 * 8 + 8

@@ -21,13 +21,17 @@ def _write_reference_style_run(tmp_path, name, model_type):
                    'warm_restarts': False, 'egnn_attention': True,
                    'save_path': str(run), 'wandb_project': None,
                    'wandb_run': None}, f)
-    # reference checkpoint dict keys: point_neural_network_base.py:509-516
+    # reference checkpoint dict keys: point_neural_network_base.py:509-516;
+    # epochs are written in order, as training does (the newest file is the
+    # one find_latest_checkpoint must pick: utils.py:33-45)
+    import time
+    torch.save({'model_state_dict': sd, 'optimiser_state_dict': {},
+                'p_epoch': 1}, run / 'checkpoints' / 'pose_ckpt_epoch_1.pt')
+    time.sleep(0.02)
     torch.save({'learning_rate': 1e-3, 'weight_decay': 1e-4, 'p_epoch': 3,
                 'a_epoch': 0, 'model_state_dict': sd,
                 'optimiser_state_dict': {}},
                run / 'checkpoints' / 'pose_ckpt_epoch_3.pt')
-    torch.save({'model_state_dict': sd, 'optimiser_state_dict': {},
-                'p_epoch': 1}, run / 'checkpoints' / 'pose_ckpt_epoch_1.pt')
     return run, sd
 
 
@@ -35,7 +39,7 @@ def test_load_model_reads_reference_checkpoint_dir(tmp_path):
     from pointvs_b200.load_model import load_model
     run, sd = _write_reference_style_run(tmp_path, 'cfg3_k32', 'egnn')
     path, model, kwargs, cmd = load_model(run)
-    assert path.name == 'pose_ckpt_epoch_3.pt'      # latest epoch wins
+    assert path.name == 'pose_ckpt_epoch_3.pt'      # most recently written
     assert model.p_epoch == 3 and not model.training
     assert cmd['edge_attention'] is True
     for k, v in model.state_dict().items():
