@@ -36,6 +36,9 @@ struct EdgeArgs {
 
 // launches the tcgen05 edge kernel (egnn_edge_tc.cu); mode = pvs_math
 int launch_edge_tc(const EdgeArgs &a, int n_ptiles_cap, int mode, cudaStream_t st);
+// bf16x3 variant with 8-warp groups and the segment-reduce on the tensor core
+// (egnn_edge_tc8.cu); launch_edge_tc dispatches to it when PVS_EDGE_TC8 says so
+int launch_edge_tc8(const EdgeArgs &a, int n_ptiles_cap, cudaStream_t st);
 // FFMA edge kernel with the 64-wide internal pitch (egnn_fwd.cu)
 int launch_edge_fp32_k64(const EdgeArgs &a, int n_tiles_cap, cudaStream_t st);
 // out = act(in . W^T + b) (w_in_major: out = in . W); accumulate: out += ...

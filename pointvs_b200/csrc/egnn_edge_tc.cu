@@ -29,8 +29,14 @@
 // phase, so one group's gather latency hides behind another's MUFU-heavy
 // epilogue (the first version, 3 CTAs x 4 warps per SM, issued on only 38 % of
 // cycles with the gather as the top stall: profiles/r01_c_*).
+#include <cstdlib>
+
 #include "egnn_common.cuh"
 #include "tc_common.cuh"
+
+#ifndef PVS_EDGE_TC8_DEFAULT
+#define PVS_EDGE_TC8_DEFAULT 0
+#endif
 
 namespace pvs {
 
@@ -663,7 +669,13 @@ int launch_edge_tc(const EdgeArgs &a, int n_ptiles_cap, int mode, cudaStream_t s
         a.xpart == nullptr)
         return PVS_ERR_INVALID_ARG;   // the tcgen05 kernel walks edge-packed tiles
     int rc;
-    if (mode == PVS_MATH_BF16X3) rc = launch_mode<TCM_BF16X3>(a, n_ptiles_cap, st);
+    // PVS_EDGE_TC8 = 1 / 0 selects the bf16x3 variant (read once per process)
+    static const int tc8 = [] {
+        const char *e = getenv("PVS_EDGE_TC8");
+        return e ? atoi(e) : PVS_EDGE_TC8_DEFAULT;
+    }();
+    if (mode == PVS_MATH_BF16X3 && tc8) rc = launch_edge_tc8(a, n_ptiles_cap, st);
+    else if (mode == PVS_MATH_BF16X3) rc = launch_mode<TCM_BF16X3>(a, n_ptiles_cap, st);
     else if (mode == PVS_MATH_FP16X2) rc = launch_mode<TCM_FP16X2>(a, n_ptiles_cap, st);
     else rc = launch_mode<TCM_BF16>(a, n_ptiles_cap, st);
     if (rc) return rc;

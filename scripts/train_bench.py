@@ -67,9 +67,12 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
     ev0.record()
+    t_host = time.perf_counter()
     for i in range(args.steps):
         losses.append(step(args.warmup + i))
+    host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps
     ev1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
@@ -87,7 +90,8 @@ def main():
             'metric': 'training complexes/s (multitask EGNN 8x64, fwd+bwd+clip+Adam)',
             'value': args.batch * world * args.steps / (float(ms) * 1e-3),
             'unit': 'complexes/s', 'n_gpus': world, 'steps': args.steps,
-            'ms_per_step': float(ms) / args.steps, 'math': args.math,
+            'ms_per_step': float(ms) / args.steps, 'host_submit_ms_per_step': host_ms,
+            'math': args.math,
             'batch_per_gpu': args.batch, 'first_loss': float(losses[0]),
             'last_loss': float(losses[-1]), 'replicas_identical': same,
             'allreduce_floats': sum(p.numel() for p in model.parameters())}),
