@@ -408,6 +408,42 @@ int pvs_egnn_layer_bwd(const pvs_graph *graph, const int32_t *csc_ptr,
                        float *d_m_prev, const pvs_layer_grads *grads,
                        void *workspace, int64_t workspace_bytes, void *stream);
 
+/* ---- Training through the whole stack of EGNN layers: one call each way ----
+ * The layer loop of get_embeddings (egnn_satorras.py:319-329) and its autograd,
+ * issued from C so that a training step costs two library calls instead of two
+ * per layer (for hosts slower than the ~350 kernel launches of a step; on the
+ * B200 box the per-layer calls are as fast).  Layers without edge residual
+ * only; no side channels.
+ *   H [L+1][N][k]: H[0] = input features (caller), H[l+1] = output of layer l.
+ *   X [L+1][N][3]: likewise for the coordinates (copied through a layer that
+ *   does not update them).
+ *   layer_ws: L slices of pvs_egnn_stack_layer_ws_stride() bytes, one forward
+ *   workspace per layer, KEPT until the backward (its P, Q, M are reused).
+ * pvs_egnn_stack_bwd walks the layers in reverse through pvs_egnn_layer_bwd:
+ * d_h_out / d_x_out are the gradients of H[L] / X[L] (d_x_out NULL = the final
+ * coordinates are not consumed), d_h_in / d_x_in those of H[0] / X[0];
+ * parameter gradients are accumulated into grads[l]. */
+int64_t pvs_egnn_stack_layer_ws_stride(int32_t n_nodes, int32_t n_edges,
+                                       int32_t n_layers,
+                                       const pvs_layer_config *cfgs);
+int pvs_egnn_stack_fwd(const pvs_graph *graph, int32_t n_layers,
+                       const pvs_layer_config *cfgs,
+                       const pvs_layer_params *params, float *H, float *X,
+                       void *layer_ws, int64_t layer_ws_stride, void *stream);
+int64_t pvs_egnn_stack_bwd_workspace_bytes(int32_t n_nodes, int32_t n_edges,
+                                           int32_t n_layers,
+                                           const pvs_layer_config *cfgs);
+int pvs_egnn_stack_bwd(const pvs_graph *graph, const int32_t *csc_ptr,
+                       const int32_t *csc_eid, int32_t n_layers,
+                       const pvs_layer_config *cfgs,
+                       const pvs_layer_params *params,
+                       const pvs_layer_grads *grads, const float *H,
+                       const float *X, const void *layer_ws,
+                       int64_t layer_ws_stride, const float *d_h_out,
+                       const float *d_x_out, float *d_h_in, float *d_x_in,
+                       void *workspace, int64_t workspace_bytes, void *stream);
+
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,7 +109,9 @@ def lib():
                      'pvs_egnn_model_workspace_bytes',
                      'pvs_radius_graph_mask_bytes',
                      'pvs_linear_bwd_workspace_bytes',
-                     'pvs_egnn_layer_bwd_workspace_bytes'):
+                     'pvs_egnn_layer_bwd_workspace_bytes',
+                     'pvs_egnn_stack_layer_ws_stride',
+                     'pvs_egnn_stack_bwd_workspace_bytes'):
             if hasattr(handle, name):
                 getattr(handle, name).restype = C.c_int64
         _lib = handle

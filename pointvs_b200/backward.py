@@ -128,6 +128,84 @@ def egnn_layer_backward(ctx, d_h, d_x, d_m):
     return (None, None, None, None, d_h_in, d_x_in, d_m_prev, *param_grads)
 
 
+def egnn_stack_backward(ctx, d_h, d_x):
+    """Backward of _EGNNStackFn: every layer's K3 in one library call."""
+    layers, csr = ctx.layers, ctx.csr
+    L = len(layers)
+    per = len(_cabi.PARAM_FIELDS)
+    saved = list(ctx.saved_tensors)
+    params = [saved.pop(0) if present else None for present in ctx.param_mask]
+    H, X, ws = ctx.H, ctx.X, ctx.ws
+    n, e = csr.n_nodes, csr.n_edges
+    dev = H.device
+    d_h = torch.zeros_like(H[L]) if d_h is None else d_h.contiguous().float()
+    no_dx = d_x is None
+    d_x = None if no_dx else d_x.contiguous().float()
+    csc_ptr, csc_eid = csr.csc()
+    arena = ARENA
+    cfgs = (_cabi.LayerConfig * L)()
+    pstructs = (_cabi.LayerParams * L)()
+    gstructs = (_cabi.LayerGrads * L)()
+    keep, plans = [], []
+    span_params = []
+    for i, layer in enumerate(layers):
+        cfgs[i] = layer.c_config()
+        ps = params[i * per:(i + 1) * per]
+        det = [None if p is None else p.detach().contiguous() for p in ps]
+        keep.append(det)
+        pstructs[i] = _cabi.LayerParams(*[ptr(p) for p in det])
+        by_name = dict(zip(_cabi.PARAM_FIELDS, ps))
+        grads, in_arena = {}, set()
+        for name in _cabi.GRAD_FIELDS:
+            p = by_name[name]
+            view = arena.grad_view(p) if (arena is not None and p is not None) \
+                else None
+            if view is not None:
+                in_arena.add(name)
+                span_params.append(p)
+            elif p is not None:
+                view = torch.zeros_like(p, dtype=torch.float32)
+            grads[name] = view
+        keep.append(grads)
+        gstructs[i] = _cabi.LayerGrads(*[ptr(grads[name])
+                                         for name in _cabi.GRAD_FIELDS])
+        plans.append((by_name, grads, in_arena))
+    d_h_in = torch.empty_like(H[0])
+    d_x_in = torch.empty_like(X[0])
+    nbytes = int(lib().pvs_egnn_stack_bwd_workspace_bytes(n, e, L, cfgs))
+    bws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    use_saved = ctx.math == layers[0].math
+    g = csr.c_struct()
+    with torch.cuda.device(dev):
+        check(lib().pvs_egnn_stack_bwd(
+            C.byref(g), ptr(csc_ptr), ptr(csc_eid), L, cfgs, pstructs, gstructs,
+            ptr(H), ptr(X), ptr(ws) if use_saved else None,
+            C.c_int64(ctx.stride), ptr(d_h), ptr(d_x), ptr(d_h_in), ptr(d_x_in),
+            ptr(bws), C.c_int64(bws.numel()), stream()), 'pvs_egnn_stack_bwd')
+    if arena is not None and arena.reduce_in_backward and span_params:
+        arena.reduce_async(*arena.span(span_params))
+    # same rules as egnn_layer_backward for parameters that cannot influence the
+    # loss: the coordinate MLP of a layer whose output coordinates nobody
+    # consumes (the last layer when d_x is None) or which does not update
+    # coordinates, and the edge gate (no incoming messages in a stack)
+    out = []
+    for i, layer in enumerate(layers):
+        by_name, grads, in_arena = plans[i]
+        unused = {'edge_gate'}
+        if not layer.use_coords or (no_dx and i == L - 1):
+            unused.update(('coord_w1', 'coord_b1', 'coord_w2'))
+        for name in _cabi.PARAM_FIELDS:
+            p = by_name[name]
+            if p is None or grads[name] is None or name in unused:
+                out.append(None)
+            elif name in in_arena:
+                arena.grant(p)
+                out.append(None)
+            else:
+                out.append(grads[name].reshape(p.shape))
+    return (None, None, d_h_in, d_x_in, *out)
+
+
 def linear_backward(ctx, d_out):
     inp, w, out = ctx.saved_tensors
     bias = ctx.bias_ref

@@ -136,4 +136,109 @@ int pvs_egnn_model_fwd(const pvs_graph *g, const pvs_model_desc *md, const float
     return PVS_OK;
 }
 
+
+/* ---- training through the whole stack of EGNN layers, one call each way ---- */
+
+static int64_t stack_layer_ws_stride(int32_t n_nodes, int32_t n_edges, int32_t n_layers,
+                                     const pvs_layer_config *cfgs) {
+    int64_t lw = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        const int64_t v = pvs_egnn_layer_workspace_bytes(n_nodes, n_edges, &cfgs[l]);
+        if (v < 0) return -1;
+        if (v > lw) lw = v;
+    }
+    return align_up(lw, 256);
+}
+
+int64_t pvs_egnn_stack_layer_ws_stride(int32_t n_nodes, int32_t n_edges, int32_t n_layers,
+                                       const pvs_layer_config *cfgs) {
+    if (!cfgs || n_layers < 1 || n_nodes < 0 || n_edges < 0) return -1;
+    return stack_layer_ws_stride(n_nodes, n_edges, n_layers, cfgs);
+}
+
+int pvs_egnn_stack_fwd(const pvs_graph *g, int32_t n_layers, const pvs_layer_config *cfgs,
+                       const pvs_layer_params *params, float *H, float *X, void *layer_ws,
+                       int64_t layer_ws_stride, void *stream) {
+    if (!g || !cfgs || !params || !H || !X || !layer_ws || n_layers < 1)
+        return PVS_ERR_INVALID_ARG;
+    const int n = g->n_nodes;
+    if (n <= 0) return PVS_OK;
+    const int k = cfgs[0].k;
+    if (layer_ws_stride < stack_layer_ws_stride(n, g->n_edges, n_layers, cfgs))
+        return PVS_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int l = 0; l < n_layers; ++l) {
+        if (cfgs[l].k != k) return PVS_ERR_INVALID_ARG;
+        if (cfgs[l].flags & PVS_F_EDGE_RESIDUAL) return PVS_ERR_INVALID_ARG;   // per-layer path
+        const bool coords = cfgs[l].flags & PVS_F_UPDATE_COORDS;
+        const float *h_in = H + (size_t)l * n * k;
+        float *h_out = H + (size_t)(l + 1) * n * k;
+        const float *x_in = X + (size_t)l * n * 3;
+        float *x_out = X + (size_t)(l + 1) * n * 3;
+        int rc = pvs_egnn_layer_fwd(g, &cfgs[l], &params[l], h_in, x_in, nullptr, h_out,
+                                    coords ? x_out : nullptr, nullptr, nullptr, nullptr,
+                                    (char *)layer_ws + (size_t)l * layer_ws_stride,
+                                    layer_ws_stride, stream);
+        if (rc) return rc;
+        if (!coords) {
+            rc = cuda_call(cudaMemcpyAsync(x_out, x_in, (size_t)n * 3 * 4,
+                                           cudaMemcpyDeviceToDevice, st));
+            if (rc) return rc;
+        }
+    }
+    return PVS_OK;
+}
+
+int64_t pvs_egnn_stack_bwd_workspace_bytes(int32_t n_nodes, int32_t n_edges, int32_t n_layers,
+                                           const pvs_layer_config *cfgs) {
+    if (!cfgs || n_layers < 1 || n_nodes < 0 || n_edges < 0) return -1;
+    int64_t lw = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        const int64_t v = pvs_egnn_layer_bwd_workspace_bytes(n_nodes, n_edges, &cfgs[l]);
+        if (v > lw) lw = v;
+    }
+    const int k = cfgs[0].k;
+    return align_up(lw, 256) + 2 * align_up((int64_t)n_nodes * k * 4, 256) +
+           2 * align_up((int64_t)n_nodes * 3 * 4, 256) + 256;
+}
+
+int pvs_egnn_stack_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t *csc_eid,
+                       int32_t n_layers, const pvs_layer_config *cfgs,
+                       const pvs_layer_params *params, const pvs_layer_grads *grads,
+                       const float *H, const float *X, const void *layer_ws,
+                       int64_t layer_ws_stride, const float *d_h_out, const float *d_x_out,
+                       float *d_h_in, float *d_x_in, void *workspace, int64_t workspace_bytes,
+                       void *stream) {
+    if (!g || !cfgs || !params || !grads || !H || !X || !d_h_out || !d_h_in || !d_x_in ||
+        !workspace || n_layers < 1)
+        return PVS_ERR_INVALID_ARG;
+    const int n = g->n_nodes;
+    if (n <= 0) return PVS_OK;
+    if (workspace_bytes < pvs_egnn_stack_bwd_workspace_bytes(n, g->n_edges, n_layers, cfgs))
+        return PVS_ERR_WORKSPACE;
+    const int k = cfgs[0].k;
+    char *p = (char *)align_up((int64_t)(uintptr_t)workspace, 256);
+    float *dh[2], *dx[2];
+    for (int i = 0; i < 2; ++i) { dh[i] = (float *)p; p += align_up((int64_t)n * k * 4, 256); }
+    for (int i = 0; i < 2; ++i) { dx[i] = (float *)p; p += align_up((int64_t)n * 3 * 4, 256); }
+    void *lws = p;
+    const int64_t lws_bytes = workspace_bytes - (p - (char *)workspace);
+    const float *dh_cur = d_h_out, *dx_cur = d_x_out;
+    for (int l = n_layers - 1; l >= 0; --l) {
+        pvs_layer_config cfg = cfgs[l];
+        if (layer_ws != nullptr)
+            cfg.saved_fwd_workspace = (const char *)layer_ws + (size_t)l * layer_ws_stride;
+        float *dh_next = l == 0 ? d_h_in : dh[l & 1];
+        float *dx_next = l == 0 ? d_x_in : dx[l & 1];
+        int rc = pvs_egnn_layer_bwd(g, csc_ptr, csc_eid, &cfg, &params[l],
+                                    H + (size_t)l * n * k, X + (size_t)l * n * 3, nullptr,
+                                    dh_cur, dx_cur, nullptr, dh_next, dx_next, nullptr,
+                                    &grads[l], lws, lws_bytes, stream);
+        if (rc) return rc;
+        dh_cur = dh_next;
+        dx_cur = dx_next;
+    }
+    return PVS_OK;
+}
+
 }  // extern "C"

@@ -10,6 +10,7 @@ order); all arithmetic happens in the kernels.  There is no PyTorch fallback:
 without the built library, or on CPU tensors, forward raises.
 """
 import ctypes as C
+import os
 
 import torch
 from torch import nn
@@ -139,6 +140,56 @@ class _EGNNLayerFn(torch.autograd.Function):
     def backward(ctx, d_h, d_x, d_m, _d_att, _d_natt):
         from .backward import egnn_layer_backward
         return egnn_layer_backward(ctx, d_h, d_x, d_m)
+
+
+class _EGNNStackFn(torch.autograd.Function):
+    """All EGNN layers of a model in ONE library call each way
+    (pvs_egnn_stack_fwd / pvs_egnn_stack_bwd): the training counterpart of the
+    fused scoring pass.  Used by get_embeddings when gradients are wanted and
+    no layer needs edge messages or side channels, and PVS_STACK_TRAIN=1."""
+
+    @staticmethod
+    def forward(ctx, layers, csr, h, x, *params):
+        ctx.set_materialize_grads(False)
+        L = len(layers)
+        n, e, k = csr.n_nodes, csr.n_edges, layers[0].hidden_nf
+        dev = h.device
+        cfgs = (_cabi.LayerConfig * L)()
+        pstructs = (_cabi.LayerParams * L)()
+        per = len(_cabi.PARAM_FIELDS)
+        keep = []
+        for i, layer in enumerate(layers):
+            cfgs[i] = layer.c_config()
+            ps = params[i * per:(i + 1) * per]
+            det = [None if p is None else p.detach().contiguous() for p in ps]
+            keep.append(det)
+            pstructs[i] = _cabi.LayerParams(*[ptr(p) for p in det])
+        H = torch.empty((L + 1, n, k), dtype=torch.float32, device=dev)
+        X = torch.empty((L + 1, n, 3), dtype=torch.float32, device=dev)
+        H[0].copy_(h)
+        X[0].copy_(x)
+        stride = int(lib().pvs_egnn_stack_layer_ws_stride(n, e, L, cfgs))
+        if stride < 0:
+            raise _cabi.PvsError('unsupported layer configuration for the '
+                                 'stacked training pass')
+        ws = torch.empty(max(1, L * stride), dtype=torch.uint8, device=dev)
+        tc = layers[0].math != 'fp32'
+        g = csr.c_struct(node_tiles=True, packed_tiles=tc)
+        with torch.cuda.device(dev):
+            check(lib().pvs_egnn_stack_fwd(
+                C.byref(g), L, cfgs, pstructs, ptr(H), ptr(X), ptr(ws),
+                C.c_int64(stride), stream()), 'pvs_egnn_stack_fwd')
+        ctx.layers, ctx.csr, ctx.stride = layers, csr, stride
+        ctx.H, ctx.X, ctx.ws = H, X, ws
+        ctx.math = layers[0].math
+        ctx.save_for_backward(*[p for p in params if p is not None])
+        ctx.param_mask = [p is not None for p in params]
+        return H[L], X[L]
+
+    @staticmethod
+    def backward(ctx, d_h, d_x):
+        from . import backward as _bw
+        return _bw.egnn_stack_backward(ctx, d_h, d_x)
 
 
 class EGNNLayer(nn.Module):
@@ -618,6 +669,28 @@ class SartorrasEGNN(PNNGeometricBase):
                 layer.record_side_channels = bool(on)
         return self
 
+    def _stack_ok(self, egnn_layers, h, want_messages):
+        """Training pass through all layers in one call each way: gradients
+        wanted, nobody needs edge messages / side channels / stage timing, one
+        arithmetic mode."""
+        if not egnn_layers or want_messages or STAGE_TIMER is not None:
+            return False
+        if not torch.is_grad_enabled() or not (
+                h.requires_grad or any(p.requires_grad
+                                       for p in egnn_layers[0].parameters())):
+            return False
+        # Opt-in (PVS_STACK_TRAIN=1): measured on B200 the step is bound by the
+        # GPU side of its ~350 small launches, not by the sixteen Python calls
+        # (8.1 ms per 16-complex step this way, 7.7 ms per layer), so the
+        # per-layer path -- which also overlaps the gradient all-reduce layer
+        # by layer -- stays the default.
+        if os.environ.get('PVS_STACK_TRAIN', '0') in ('', '0'):
+            return False
+        return all(not l.edge_residual and not l.record_side_channels and
+                   l.math == egnn_layers[0].math and
+                   l.hidden_nf == egnn_layers[0].hidden_nf
+                   for l in egnn_layers)
+
     def get_embeddings(self, feats, edges, coords, edge_attributes, batch,
                        _csr=None, _want_messages=True):
         """Reference signature (egnn_satorras.py:319-329) -> (h [N,k],
@@ -638,6 +711,11 @@ class SartorrasEGNN(PNNGeometricBase):
         x = coords.float()
         m = None
         egnn_layers = list(self.layers)[1:]
+        if self._stack_ok(egnn_layers, h, _want_messages):
+            flat = [p for layer in egnn_layers for p in layer.param_list()]
+            h, x = _EGNNStackFn.apply(tuple(egnn_layers), csr, h.contiguous(),
+                                      x.contiguous(), *flat)
+            egnn_layers = []
         for i, layer in enumerate(egnn_layers):
             last = i == len(egnn_layers) - 1
             want_m = layer_needs = (

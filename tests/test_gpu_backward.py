@@ -209,3 +209,28 @@ def test_hub_node_softmax_backward():
     _close(hc.grad.cpu().numpy(), hr.grad.numpy(), 'h')
     for pname, p in layer.named_parameters():
         _close(p.grad.cpu().numpy(), sd['l.' + pname].grad.numpy(), pname)
+
+
+def test_stacked_training_pass_equals_per_layer_pass(monkeypatch):
+    """pvs_egnn_stack_fwd / pvs_egnn_stack_bwd (all layers in one call each
+    way, PVS_STACK_TRAIN=1) give bit-identical outputs and gradients to the
+    per-layer calls."""
+    kw = dict(dim_input=13, dim_output=1, graphnorm=False, **VARIANTS['cfg3_k64'])
+    results = []
+    for stack in ('0', '1'):
+        monkeypatch.setenv('PVS_STACK_TRAIN', stack)
+        model = gh.build_model(kw, seed=7, coord_gain=1.0).train()
+        model.set_math('bf16x3')
+        graph = gh.synthetic_graph(900, 2, 400, 15)
+        graph.pos = graph.pos.clone().requires_grad_(True)
+        out = model(graph)
+        out.sum().backward()
+        grads = {n: (None if p.grad is None else p.grad.clone())
+                 for n, p in model.named_parameters()}
+        results.append((out.detach().clone(), graph.pos.grad.clone(), grads))
+    (o0, x0, g0), (o1, x1, g1) = results
+    assert torch.equal(o0, o1) and torch.equal(x0, x1)
+    for name in g0:
+        assert (g0[name] is None) == (g1[name] is None), name
+        if g0[name] is not None:
+            assert torch.equal(g0[name], g1[name]), name
