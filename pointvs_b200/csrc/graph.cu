@@ -168,10 +168,12 @@ radius_graph_kernel(const double *__restrict__ coords,
                     int32_t *__restrict__ col, uint8_t *__restrict__ attr,
                     int32_t *__restrict__ ref_pos, int max_n, int stage,
                     uint32_t *__restrict__ mask_out, int edge_capacity,
-                    int32_t *__restrict__ overflow) {
+                    int32_t *__restrict__ overflow, int split = RG_SPLIT) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RgSmem &S = *reinterpret_cast<RgSmem *>(smem_raw);
-    const int cplx = blockIdx.x / RG_SPLIT, part = blockIdx.x % RG_SPLIT;
+    // `split` CTAs per complex: RG_SPLIT for the warp-per-atom passes, fewer for
+    // the thread-per-atom count pass (one thread per atom: 512 atoms a CTA)
+    const int cplx = blockIdx.x / split, part = blockIdx.x % split;
     const int n0 = complex_ptr[cplx];
     const int n = complex_ptr[cplx + 1] - n0;
     if (n <= 0 || n > max_n) return;   // host sizes smem from max_n
@@ -349,10 +351,105 @@ radius_graph_kernel(const double *__restrict__ coords,
             }
         }
     };
+    if (!FILL && mask_out != nullptr) {
+        // Round 2 count pass: ONE THREAD per destination atom, atoms taken in
+        // cell-sorted order (the 32 atoms of a warp sit in the same or adjacent
+        // cells, so they walk nearly the same candidate runs and the shared-
+        // memory reads broadcast).  The half-warp version below issued ~4x the
+        // warp instructions for the same pair tests (16 lanes share ~12
+        // candidates of a run, nine runs per atom, plus mask bookkeeping in
+        // shared memory): 186 us per 128 x 1000 atoms, issue-bound.  Each
+        // thread sets bits in its atom's PRIVATE mask row in global memory (no
+        // atomics; the row lives in L1 while it is written), which the fill
+        // pass then only expands -- sorted output without a sort, as before.
+        // The CTAs of a complex each run their own counting sort, and the order
+        // of the atoms INSIDE a cell depends on the order of their atomics; the
+        // cell boundaries do not.  So the sorted positions are split between
+        // the CTAs at cell boundaries: part k takes the cells that start in
+        // [k n / split, (k + 1) n / split).
+        auto part_begin = [&](int k) {
+            if (k <= 0) return 0;
+            if (k >= split) return n;
+            const int target = (int)(((long long)n * k) / split);
+            int lo = 0, hi = ncell;          // first cell with cell_start >= target
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (S.cell_start[mid] < target) lo = mid + 1; else hi = mid;
+            }
+            return S.cell_start[lo];
+        };
+        const int p_begin = part_begin(part), p_end = part_begin(part + 1);
+        for (int p = p_begin + tid; p < p_end; p += RG_THREADS) {
+            const int i = sorted_idx[p];
+            uint32_t *m_inter = mask_out + (size_t)(n0 + i) * 2 * words;
+            uint32_t *m_intra = m_inter + words;   // rows zeroed by the caller
+            const double xi = cx[3 * i], yi = cx[3 * i + 1], zi = cx[3 * i + 2];
+            const int bi = cbp[i];
+            const int ci0 = cell_coord(xi, blo[0], cs[0], dim[0]);
+            const int ci1 = cell_coord(yi, blo[1], cs[1], dim[1]);
+            const int ci2 = cell_coord(zi, blo[2], cs[2], dim[2]);
+            const int x_lo = max(ci0 - 1, 0), x_hi = min(ci0 + 1, dim[0] - 1);
+            int n_i = 0, n_a = 0;
+            for (int dz = -1; dz <= 1; ++dz) {
+                const int c2 = ci2 + dz;
+                if (c2 < 0 || c2 >= dim[2]) continue;
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int c1 = ci1 + dy;
+                    if (c1 < 0 || c1 >= dim[1]) continue;
+                    const int cb = dim[0] * (c1 + dim[1] * c2);
+                    const int q_end = S.cell_start[cb + x_hi + 1];
+                    for (int q = S.cell_start[cb + x_lo]; q < q_end; ++q) {
+                        const int j = sorted_idx[q];
+                        double xj, yj, zj;
+                        int bj;
+                        if (stage) {
+                            xj = scoord[3 * q]; yj = scoord[3 * q + 1]; zj = scoord[3 * q + 2];
+                            bj = sbp[q];
+                        } else {
+                            xj = cx[3 * j]; yj = cx[3 * j + 1]; zj = cx[3 * j + 2];
+                            bj = cbp[j];
+                        }
+                        // same arithmetic as `search` above (scipy cdist order,
+                        // no FMA contraction, sqrt only inside the 1e-15 band)
+                        const double ddx = __dsub_rn(xi, xj);
+                        const double ddy = __dsub_rn(yi, yj);
+                        const double ddz = __dsub_rn(zi, zj);
+                        const double d2 = __dadd_rn(
+                            __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)),
+                            __dmul_rn(ddz, ddz));
+                        bool pos, in_inter, in_intra;
+                        if (d2 > pos_hi && (d2 < inter_lo || d2 > inter_hi) &&
+                            (d2 < intra_lo || d2 > intra_hi)) {
+                            pos = true;
+                            in_inter = d2 < inter_lo;
+                            in_intra = d2 < intra_lo;
+                        } else {
+                            const double d = __dsqrt_rn(d2);
+                            pos = d > 1e-7;
+                            in_inter = d < r_inter;
+                            in_intra = d < r_intra;
+                        }
+                        const unsigned bit = 1u << (j & 31);
+                        if (pos && in_inter && bj != bi) {       // :110-117
+                            m_inter[j >> 5] |= bit;
+                            ++n_i;
+                        }
+                        if (pos && in_intra) {                   // :119-121
+                            m_intra[j >> 5] |= bit;
+                            ++n_a;
+                        }
+                    }
+                }
+            }
+            deg[n0 + i] = n_i + n_a;
+            n_inter_out[n0 + i] = n_i;
+        }
+        return;
+    }
     if (!FILL) {
-        // count pass: a HALF-warp per destination atom (a run of three cells
-        // holds ~10 candidates, so 16 lanes are two-thirds busy where 32 were
-        // one-third), two atoms per warp
+        // count pass without kept masks: a HALF-warp per destination atom (a
+        // run of three cells holds ~10 candidates, so 16 lanes are two-thirds
+        // busy where 32 were one-third), two atoms per warp
         const int half = lane >> 4, hl = lane & 15;
         unsigned *m_inter = masks + (size_t)(warp * 2 + half) * 2 * words;
         unsigned *m_intra = m_inter + words;
@@ -472,7 +569,77 @@ radius_graph_kernel(const double *__restrict__ coords,
     }
 }
 
-// fill from the masks stored by the count pass: one warp per node, flat grid
+// fill from the masks stored by the count pass: EIGHT LANES per node (four
+// nodes per warp), flat grid.  A lane owns 32 bytes of each 256-byte mask row
+// (so a row is one coalesced 256-byte read), counts its bits, takes its offset
+// from a 3-step scan inside the 8-lane group and writes its entries.  (One
+// warp per node spent 55 us per 128 x 1000 atoms scanning empty words; one
+// thread per node 40 us on uncoalesced row reads.)
+__global__ void __launch_bounds__(256)
+radius_graph_emit1_kernel(const uint32_t *__restrict__ masks, int words,
+                          const int32_t *__restrict__ bp,
+                          const int32_t *__restrict__ complex_ptr, int n_complexes,
+                          int n_nodes, const int32_t *__restrict__ row_ptr,
+                          int32_t *__restrict__ col, uint8_t *__restrict__ attr,
+                          int edge_capacity, int32_t *__restrict__ overflow) {
+    const int lane = threadIdx.x & 31, sub = lane & 7;
+    const unsigned gmask = 0xffu << (lane & 24);          // this node's 8 lanes
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    if (i >= n_nodes) return;      // whole 8-lane groups leave together
+    int lo = 0, hi = n_complexes;     // complex of node i
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (complex_ptr[mid] <= i) lo = mid; else hi = mid;
+    }
+    const int n0 = complex_ptr[lo];
+    const int nw = (complex_ptr[lo + 1] - n0 + 31) / 32;
+    const int bi = bp[i];
+    int run = row_ptr[i];
+    const uint32_t *mk0 = masks + (size_t)i * 2 * words;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const uint32_t *mk = mk0 + pass * words;
+        for (int w0 = 0; w0 < nw; w0 += 64) {             // 8 lanes x 8 words
+            uint32_t b8[8];
+            int cnt = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int w = w0 + 8 * sub + q;
+                b8[q] = w < nw ? mk[w] : 0u;
+                cnt += __popc(b8[q]);
+            }
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const int up = __shfl_up_sync(gmask, incl, o, 8);
+                if (sub >= o) incl += up;
+            }
+            int off = run + incl - cnt;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                unsigned bits = b8[q];
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const int j = n0 + (w0 + 8 * sub + q) * 32 + b;
+                    if (off < edge_capacity) {
+                        const int bj = bp[j];
+                        col[off] = j;
+                        attr[off] = pass == 0
+                            ? (((bi == 0 && bj == 1) || (bi == 1 && bj == 0)) ? 1 : 0)
+                            : ((bi == 1 && bj == 1) ? 2 : 0);
+                    } else if (overflow) {
+                        *overflow = 1;
+                    }
+                    ++off;
+                }
+            }
+            run += __shfl_sync(gmask, incl, 7, 8);
+        }
+    }
+}
+
+// the same with one warp per node (kept for reference / A-B timing)
 __global__ void __launch_bounds__(256)
 radius_graph_emit_kernel(const uint32_t *__restrict__ masks, int words,
                          const int32_t *__restrict__ bp,
@@ -751,10 +918,24 @@ int pvs_radius_graph_count(const double *coords, const int32_t *bp,
         if (smem > (size_t)max_optin_smem()) return PVS_ERR_TOO_LARGE;
         rc = ensure_smem(radius_graph_kernel<false>, smem);
         if (rc) return rc;
-        radius_graph_kernel<false><<<n_complexes * RG_SPLIT, RG_THREADS, smem, st>>>(
+        if (mask_scratch != nullptr) {
+            // the thread-per-atom count pass ORs bits into zeroed private rows
+            rc = cuda_call(cudaMemsetAsync(
+                mask_scratch, 0,
+                (size_t)pvs_radius_graph_mask_bytes(n_nodes, max_complex_nodes), st));
+            if (rc) return rc;
+        }
+        // thread-per-atom count pass (masks kept): one CTA per 512 atoms of the
+        // largest complex; warp-per-atom pass: RG_SPLIT CTAs per complex
+        int split = RG_SPLIT;
+        if (mask_scratch != nullptr) {
+            split = (max_complex_nodes + RG_THREADS - 1) / RG_THREADS;
+            split = split < 1 ? 1 : (split > 8 ? 8 : split);
+        }
+        radius_graph_kernel<false><<<n_complexes * split, RG_THREADS, smem, st>>>(
             coords, bp, complex_ptr, inter_radius, intra_radius, deg, n_inter,
             nullptr, nullptr, nullptr, nullptr, nullptr, max_complex_nodes, stage,
-            mask_scratch, 0, nullptr);
+            mask_scratch, 0, nullptr, split);
         rc = check_launch();
         if (rc) return rc;
     }
@@ -811,7 +992,7 @@ int pvs_radius_graph_fill(const double *coords, const int32_t *bp,
     if (!n_inter || !row_ptr || !col || !attr || edge_capacity < 0) return PVS_ERR_INVALID_ARG;
     if (mask_scratch != nullptr && ref_pos == nullptr) {
         const int words = (max_complex_nodes + 31) / 32;
-        radius_graph_emit_kernel<<<(n_nodes + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        radius_graph_emit1_kernel<<<(n_nodes + 31) / 32, 256, 0, (cudaStream_t)stream>>>(
             mask_scratch, words, bp, complex_ptr, n_complexes, n_nodes, row_ptr, col, attr,
             edge_capacity, overflow);
         rc = check_launch();
