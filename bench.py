@@ -754,7 +754,9 @@ def train_block(args, torch, dist, dev, rank, world, barrier, max_over_ranks,
         'value': b * world * steps / (ms * 1e-3), 'unit': 'complexes/s',
         'ms_per_step': ms / steps, 'steps': steps, 'warmup': warmup,
         'batch_per_gpu': b, 'n_gpus': world,
-        'forward_math': args.math, 'backward_math': 'fp32',
+        'forward_math': args.math,
+        'backward_math': 'fp32 FFMA' if args.math == 'fp32' else
+                         'edge stage on tcgen05 (bf16x3), node stage / weight grads fp32 FFMA',
         'parallelism': f'data-parallel x{world}: per-layer gradient-arena '
                        'all-reduce (NCCL, AVG) overlapped with backward'
                        if world > 1 else 'single GPU',
