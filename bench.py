@@ -723,15 +723,17 @@ def train_block(args, torch, dist, dev, rank, world, barrier, max_over_ranks,
                          dtype=torch.float32, device=dev)
         sets.append((torch.from_numpy(coords).to(dev), torch.from_numpy(bp).to(dev),
                      torch.from_numpy(feats).to(dev), cptr, y))
-    losses = []
+    losses, overflow = [], []
 
     def step(i):
         coords, bp, feats, cptr, y = sets[i % 3]
         batch = pv.PackedBatch.from_arrays(coords, bp, feats, cptr, EDGE_RADIUS,
-                                           EDGE_RADIUS, y=y, device=dev)
+                                           EDGE_RADIUS, y=y, device=dev,
+                                           edge_capacity='auto')
         batch.lig_fname = batch.rec_fname = [''] * b
         y_pred, y_true, _, _ = model.unpack_input_data_and_predict(batch)
         losses.append(model.backprop(y_true, y_pred, sync=False))
+        overflow.append(batch.pvs_csr._overflow)
 
     for i in range(warmup):
         step(i)
@@ -748,6 +750,8 @@ def train_block(args, torch, dist, dev, rank, world, barrier, max_over_ranks,
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         same = bool(ok.item())
     vals = torch.stack(losses).float().cpu()
+    if int(torch.stack(overflow).sum().item()):
+        raise RuntimeError('train block: edge capacity exceeded')
     return {
         'metric': 'training complexes/s (BASELINE configs[3]: multitask EGNN '
                   '8 x 64; step = graph build + fwd + bwd + all-reduce + clip + Adam)',

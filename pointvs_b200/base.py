@@ -218,14 +218,25 @@ class PointNeuralNetworkBase(nn.Module):
         return loss_
 
     @staticmethod
-    def _drain_losses(pending, losses):
-        """One device->host transfer for the losses of the last few steps."""
+    def _drain_losses(pending, losses, overflow=None):
+        """One device->host transfer for the losses of the last few steps (and
+        for the edge-capacity overflow flags of their graphs, if the loader
+        builds capacity-bounded graphs)."""
         if pending:
             vals = torch.stack(pending).cpu().tolist()
             pending.clear()
             if any(math.isnan(v) for v in vals):
                 raise FloatingPointError('We have hit a NaN loss value.')
             losses.extend(vals)
+        if overflow:
+            dropped = int(torch.stack(overflow).sum().item())
+            overflow.clear()
+            if dropped:
+                raise RuntimeError(
+                    'edge capacity exceeded while training: a batch had more '
+                    'edges than its capacity-bounded edge list holds; build '
+                    'the loader with edge_capacity=None (exact edge lists) '
+                    'or a larger bound')
 
     def training_setup(self, data_loader, epochs, model_task=None):
         if self.use_1cycle:
@@ -245,20 +256,23 @@ class PointNeuralNetworkBase(nn.Module):
     def train_model(self, data_loader, epochs=1, epoch_end_validation_set=None,
                     top1_on_end=False):
         init_epoch, _ = self.training_setup(data_loader, epochs)
-        losses, pending = [], []
+        losses, pending, overflow = [], [], []
         for _ in range(init_epoch, epochs):
             self.train()
             for self.batch, graph in enumerate(data_loader):
                 y_pred, y_true, _, _ = self.unpack_input_data_and_predict(graph)
                 pending.append(self.backprop(y_true, y_pred, sync=False))
-                # losses (and the NaN check) come back once per log interval,
-                # not once per step
+                csr = getattr(graph, 'pvs_csr', None)
+                if csr is not None and not csr.exact_edge_count:
+                    overflow.append(csr._overflow)
+                # losses (and the NaN / overflow checks) come back once per
+                # log interval, not once per step
                 if len(pending) >= self.log_interval:
-                    self._drain_losses(pending, losses)
+                    self._drain_losses(pending, losses, overflow)
                 if self.scheduler is not None:
                     self.scheduler.step()
                 self.global_iter += 1
-            self._drain_losses(pending, losses)
+            self._drain_losses(pending, losses, overflow)
             self.eval()
             self.on_epoch_end(epoch_end_validation_set, epochs, top1_on_end)
         return losses

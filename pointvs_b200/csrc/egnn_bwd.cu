@@ -139,6 +139,148 @@ static int launch_wgrad(const float *A, int lda, int ko, const float *B, int ldb
 }
 
 // ---------------------------------------------------------------------------
+// grouped wgrad: every node-level weight gradient of one layer (up to WG_MAX_JOBS
+// products A_j^T B_j over the same rows) in ONE launch + ONE reduce.  A 16-complex
+// training batch has 16 k rows: a single product fills 125 CTAs for ~18 us and
+// its reduce another ~7 us, six times per layer; grouped, the products of a layer
+// share the machine (and the L2 lines of the operands they have in common).
+// ---------------------------------------------------------------------------
+constexpr int WG_MAX_JOBS = 8;
+struct WgradJob {
+    const float *A; const float *B;   // B == nullptr: column sums of A only
+    float *d_w; float *d_b;
+    int lda, ko, ldb, ki, ld_dw;
+};
+struct WgradGroup {
+    WgradJob job[WG_MAX_JOBS];
+    int n_jobs, rows, chunks, rows_per;   // chunks CTAs per job, rows_per rows each
+};
+
+__global__ void __launch_bounds__(BT)
+wgrad_group_kernel(const __grid_constant__ WgradGroup G, float *__restrict__ partial) {
+    constexpr int WR = 32;
+    __shared__ __align__(16) float As[WR * 68];
+    __shared__ __align__(16) float Bs[WR * 132];
+    // consecutive CTAs: the same rows of different jobs (shared operands hit in L2)
+    const int j_id = blockIdx.x % G.n_jobs, chunk = blockIdx.x / G.n_jobs;
+    const WgradJob &J = G.job[j_id];
+    const float *__restrict__ A = J.A;
+    const float *__restrict__ B = J.B ? J.B : J.A;
+    const int lda = J.lda, ko = J.ko, ldb = J.B ? J.ldb : J.lda, ki = J.B ? J.ki : 1;
+    const int tid = threadIdx.x, tn = tid >> 4, tk = tid & 15;
+    const int r_lo = chunk * G.rows_per, r_hi = min(G.rows, r_lo + G.rows_per);
+    float acc[2][4][4] = {};
+    float bsum[4] = {};
+    const int nj = ki > 64 ? 2 : 1;
+    for (int r0 = r_lo; r0 < r_hi; r0 += WR) {
+        __syncthreads();
+        for (int idx = tid; idx < WR * 64; idx += BT) {
+            int r = idx >> 6, c = idx & 63;
+            As[r * 68 + c] = (r0 + r < r_hi && c < ko) ? A[(size_t)(r0 + r) * lda + c] : 0.0f;
+        }
+        for (int idx = tid; idx < WR * 64 * nj; idx += BT) {
+            int r = idx / (64 * nj), c = idx - r * 64 * nj;
+            Bs[r * 132 + c] = (r0 + r < r_hi && c < ki) ? B[(size_t)(r0 + r) * ldb + c] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < WR; ++r) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&As[r * 68 + 4 * tn]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (j >= nj) break;
+                const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[r * 132 + 4 * tk + 64 * j]);
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    acc[j][x][0] = fmaf(av[x], b4.x, acc[j][x][0]);
+                    acc[j][x][1] = fmaf(av[x], b4.y, acc[j][x][1]);
+                    acc[j][x][2] = fmaf(av[x], b4.z, acc[j][x][2]);
+                    acc[j][x][3] = fmaf(av[x], b4.w, acc[j][x][3]);
+                }
+            }
+            if (tk == 0) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x) bsum[x] += av[x];
+            }
+        }
+    }
+    float *out = partial + ((size_t)j_id * G.chunks + chunk) * WG_PART;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (j >= nj) break;
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+            *reinterpret_cast<float4 *>(&out[(4 * tn + x) * 128 + 4 * tk + 64 * j]) =
+                make_float4(acc[j][x][0], acc[j][x][1], acc[j][x][2], acc[j][x][3]);
+    }
+    if (tk == 0)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) out[64 * 128 + 4 * tn + x] = bsum[x];
+}
+
+// grid (ceil((64*128 + 64) / 256), n_jobs): sum the chunks of every job in chunk
+// order (deterministic), four partial sums in flight per thread
+__global__ void wgrad_group_reduce_kernel(const __grid_constant__ WgradGroup G,
+                                          const float *__restrict__ partial) {
+    const WgradJob &J = G.job[blockIdx.y];
+    const int ko = J.ko, ki = J.B ? J.ki : 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    float *dst;
+    int off;
+    if (idx < ko * ki) {
+        if (J.d_w == nullptr || J.B == nullptr) return;
+        const int n = idx / ki, kk = idx - n * ki;
+        off = n * 128 + kk;
+        dst = J.d_w + (size_t)n * J.ld_dw + kk;
+    } else if (idx < ko * ki + ko) {
+        if (J.d_b == nullptr) return;
+        off = 64 * 128 + (idx - ko * ki);
+        dst = J.d_b + (idx - ko * ki);
+    } else {
+        return;
+    }
+    const float *src = partial + (size_t)blockIdx.y * G.chunks * WG_PART + off;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int c = 0;
+    for (; c + 4 <= G.chunks; c += 4) {
+        s0 += src[(size_t)(c + 0) * WG_PART];
+        s1 += src[(size_t)(c + 1) * WG_PART];
+        s2 += src[(size_t)(c + 2) * WG_PART];
+        s3 += src[(size_t)(c + 3) * WG_PART];
+    }
+    for (; c < G.chunks; ++c) s0 += src[(size_t)c * WG_PART];
+    *dst += (s0 + s1) + (s2 + s3);
+}
+
+// CTAs over all jobs of a group: the scratch `partial` holds WG_GROUP_CTAS blocks
+static int wg_group_ctas() { return num_sms() * 4; }
+
+struct WgradGroupBuilder {
+    WgradGroup G{};
+    void add(const float *A, int lda, int ko, const float *B, int ldb, int ki, float *d_w,
+             int ld_dw, float *d_b) {
+        if ((d_w == nullptr || B == nullptr) && d_b == nullptr) return;
+        WgradJob &J = G.job[G.n_jobs++];
+        J.A = A; J.lda = lda; J.ko = ko; J.B = B; J.ldb = ldb; J.ki = ki;
+        J.d_w = B ? d_w : nullptr; J.ld_dw = ld_dw; J.d_b = d_b;
+    }
+    int launch(int rows, float *partial, cudaStream_t st) {
+        if (rows <= 0 || G.n_jobs == 0) return PVS_OK;
+        int chunks = (rows + 127) / 128;
+        const int cap = wg_group_ctas() / G.n_jobs;
+        if (chunks > cap) chunks = cap;
+        if (chunks < 1) chunks = 1;
+        G.rows = rows;
+        G.rows_per = ((rows + chunks - 1) / chunks + 31) / 32 * 32;
+        G.chunks = (rows + G.rows_per - 1) / G.rows_per;
+        wgrad_group_kernel<<<G.chunks * G.n_jobs, BT, 0, st>>>(G, partial);
+        wgrad_group_reduce_kernel<<<dim3((WG_PART + 255) / 256, G.n_jobs), 256, 0, st>>>(G, partial);
+        return check_launch(2);
+    }
+};
+
+// ---------------------------------------------------------------------------
 // linear backward, data part: g = d_out * act'(v), v recomputed; d_in = g . W
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(BT)
@@ -1099,7 +1241,7 @@ static BwdWorkspace carve_bwd(void *base, int n, int e, uint32_t flags) {
     w.DD = take((int64_t)e * 3);
     w.edge_grid = num_sms();
     w.edge_partial = take((int64_t)w.edge_grid * EP_STRIDE);
-    w.wg_partial = take((int64_t)num_sms() * 2 * WG_PART);
+    w.wg_partial = take((int64_t)wg_group_ctas() * WG_PART);
     w.fwd = (void *)p;
     p += align_up(fwd_recompute_bytes(n, e, flags), 256);
     w.bytes = p - (char *)base;
@@ -1250,24 +1392,17 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
             if (rc) return rc;
         }
     }
-    // node weight gradients
-    rc = launch_wgrad(w.DO, KB, k, w.U, KB, k, n, grads->node_w2, k, grads->node_b2, w.wg_partial, st);
-    if (rc) return rc;
-    rc = launch_wgrad(w.DV, KB, k, h_in, k, k, n, grads->node_w1, 2 * k, grads->node_b1, w.wg_partial, st);
-    if (rc) return rc;
-    rc = launch_wgrad(w.DV, KB, k, fw.M, KB, k, n, grads->node_w1 ? grads->node_w1 + k : nullptr,
-                      2 * k, nullptr, w.wg_partial, st);
-    if (rc) return rc;
-    if ((f & PVS_F_NODE_ATTENTION) && p->natt_w) {
-        rc = launch_wgrad(w.dzn, 1, 1, w.O, KB, k, n, grads->natt_w, k, grads->natt_b,
-                          w.wg_partial, st);
-        if (rc) return rc;
-    }
-    if ((f & PVS_F_RESIDUAL) && (f & (PVS_F_REZERO | PVS_F_GATED_RESIDUAL)) && grads->node_gate) {
-        rc = launch_wgrad(w.gdot, 1, 1, nullptr, 0, 0, n, nullptr, 0, grads->node_gate,
-                          w.wg_partial, st);
-        if (rc) return rc;
-    }
+    // node weight gradients: queued, launched with the edge-L1 ones at the end
+    // of the layer (one grouped launch; none of these operands is overwritten
+    // by the edge stage)
+    WgradGroupBuilder wg;
+    wg.add(w.DO, KB, k, w.U, KB, k, grads->node_w2, k, grads->node_b2);
+    wg.add(w.DV, KB, k, h_in, k, k, grads->node_w1, 2 * k, grads->node_b1);
+    wg.add(w.DV, KB, k, fw.M, KB, k, grads->node_w1 ? grads->node_w1 + k : nullptr, 2 * k, nullptr);
+    if ((f & PVS_F_NODE_ATTENTION) && p->natt_w)
+        wg.add(w.dzn, 1, 1, w.O, KB, k, grads->natt_w, k, grads->natt_b);
+    if ((f & PVS_F_RESIDUAL) && (f & (PVS_F_REZERO | PVS_F_GATED_RESIDUAL)) && grads->node_gate)
+        wg.add(w.gdot, 1, 1, nullptr, 0, 0, nullptr, 0, grads->node_gate);
 
     // ---- edge backward ----
     EdgeBwdArgs eb{};
@@ -1322,10 +1457,8 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
         rc = launch_linear(w.dP, KB, n, k, p->edge_w1, in_e, nullptr, k, PVS_ACT_NONE, d_h_in, k,
                            st, 1, 1);
         if (rc) return rc;
-        rc = launch_wgrad(w.dP, KB, k, h_in, k, k, n, grads->edge_w1, in_e, nullptr, w.wg_partial, st);
-        if (rc) return rc;
-        rc = launch_wgrad(w.dQ, KB, k, nullptr, 0, 0, n, nullptr, 0, grads->edge_b1, w.wg_partial, st);
-        if (rc) return rc;
+        wg.add(w.dP, KB, k, h_in, k, k, grads->edge_w1, in_e, nullptr);
+        wg.add(w.dQ, KB, k, nullptr, 0, 0, nullptr, 0, grads->edge_b1);
     } else {
         rc = launch_linear(w.dP, KB, n, k, p->edge_w1, in_e, nullptr, k, PVS_ACT_NONE, d_h_in, k,
                            st, 1, 1);
@@ -1333,13 +1466,12 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
         rc = launch_linear(w.dQ, KB, n, k, p->edge_w1 + k, in_e, nullptr, k, PVS_ACT_NONE, d_h_in,
                            k, st, 1, 1);
         if (rc) return rc;
-        rc = launch_wgrad(w.dP, KB, k, h_in, k, k, n, grads->edge_w1, in_e, grads->edge_b1,
-                          w.wg_partial, st);
-        if (rc) return rc;
-        rc = launch_wgrad(w.dQ, KB, k, h_in, k, k, n, grads->edge_w1 ? grads->edge_w1 + k : nullptr,
-                          in_e, nullptr, w.wg_partial, st);
-        if (rc) return rc;
+        wg.add(w.dP, KB, k, h_in, k, k, grads->edge_w1, in_e, grads->edge_b1);
+        wg.add(w.dQ, KB, k, h_in, k, k, grads->edge_w1 ? grads->edge_w1 + k : nullptr, in_e,
+               nullptr);
     }
+    rc = wg.launch(n, w.wg_partial, st);
+    if (rc) return rc;
     return PVS_OK;
 }
 

@@ -780,9 +780,12 @@ tiles_compact_kernel(const int32_t *__restrict__ tmp,
 template <typename KeyT>
 __global__ void key_count_kernel(const KeyT *__restrict__ keys, int64_t n_edges,
                                  int n_nodes, int32_t *__restrict__ deg,
-                                 int32_t *__restrict__ bad) {
+                                 int32_t *__restrict__ bad,
+                                 const int32_t *__restrict__ n_valid = nullptr) {
+    // n_valid: device-side count of the keys actually present (a capacity-
+    // bounded edge list is only filled up to row_ptr[n_nodes])
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_edges) return;
+    if (e >= n_edges || (n_valid && e >= *n_valid)) return;
     int64_t k = (int64_t)keys[e];
     if (k < 0 || k >= n_nodes) {
         if (bad) *bad = 1;
@@ -795,9 +798,10 @@ template <typename KeyT>
 __global__ void key_place_kernel(const KeyT *__restrict__ keys, int64_t n_edges,
                                  int n_nodes, const int32_t *__restrict__ ptr,
                                  int32_t *__restrict__ cursor,
-                                 int32_t *__restrict__ perm) {
+                                 int32_t *__restrict__ perm,
+                                 const int32_t *__restrict__ n_valid = nullptr) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_edges) return;
+    if (e >= n_edges || (n_valid && e >= *n_valid)) return;
     int64_t k = (int64_t)keys[e];
     if (k < 0 || k >= n_nodes) return;
     int p = atomicAdd(&cursor[k], 1);
@@ -1137,6 +1141,9 @@ int pvs_csr_transpose(const pvs_graph *g, int32_t *csc_ptr, int32_t *csc_eid,
     cudaStream_t st = (cudaStream_t)stream;
     const int n = g->n_nodes;
     const int64_t E = g->n_edges;
+    // g->n_edges may be the CAPACITY of a graph built without a host read-back
+    // of its edge count; row_ptr[n] is the number of edges actually present
+    const int32_t *n_valid = g->row_ptr ? g->row_ptr + n : nullptr;
     // scratch: deg[n] | cursor[n] | scan scratch
     int32_t *deg = (int32_t *)scratch;
     int32_t *cursor = (int32_t *)((char *)scratch + align_up((int64_t)n * 4, 256));
@@ -1149,13 +1156,13 @@ int pvs_csr_transpose(const pvs_graph *g, int32_t *csc_ptr, int32_t *csc_eid,
     const int T = 256;
     const unsigned nb = (unsigned)((E + T - 1) / T);
     if (E > 0)
-        key_count_kernel<int32_t><<<nb, T, 0, st>>>(g->col, E, n, deg, nullptr);
+        key_count_kernel<int32_t><<<nb, T, 0, st>>>(g->col, E, n, deg, nullptr, n_valid);
     if (E > 0) g_launches += 1;
     rc = exclusive_scan(deg, n, csc_ptr, scan_scratch, st);
     if (rc) return rc;
     if (E > 0 && n > 0) {
         key_place_kernel<int32_t><<<nb, T, 0, st>>>(g->col, E, n, csc_ptr, cursor,
-                                                   csc_eid);
+                                                   csc_eid, n_valid);
         segment_sort_kernel<<<(n + T - 1) / T, T, 0, st>>>(csc_ptr, n, csc_eid);
         g_launches += 2;
     }

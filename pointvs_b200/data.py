@@ -789,12 +789,15 @@ def get_data_loader(data_root, dataset_class=None, receptors=None,
                     types_fname=None, edge_radius=None, prune=False,
                     estimate_bonds=False, bp=None, p_noise=-1, num_workers=4,
                     device=None, device_crop=False, worker_processes=False,
-                    **kwargs):
+                    edge_capacity=None, **kwargs):
     """Signature of the reference's `get_data_loader` (data_loaders.py:483-520).
     `dataset_class` is accepted for call compatibility and ignored: there is
     one dataset here.  As in the reference, classification training draws
     complexes with the class-balancing weighted sampler and every other mode
-    walks the types file in order."""
+    walks the types file in order.  edge_capacity='auto' (or an int) builds
+    capacity-bounded edge lists: no host read-back of the edge count per
+    batch, so training steps queue without a sync; `train_model` checks the
+    overflow flags with the losses, once per log interval."""
     del dataset_class, receptors
     ds = ComplexDataset(
         data_root, compact=compact, augmented_active_count=augmented_actives,
@@ -810,7 +813,8 @@ def get_data_loader(data_root, dataset_class=None, receptors=None,
     sampler = ds.sampler if (ds.model_task == 'classification'
                              and mode == 'train') else None
     return PackedLoader(ds, batch_size, sampler=sampler,
-                        num_workers=num_workers, processes=worker_processes)
+                        num_workers=num_workers, processes=worker_processes,
+                        edge_capacity=edge_capacity)
 
 
 __all__ = ['ComplexDataset', 'PackedLoader', 'get_data_loader',

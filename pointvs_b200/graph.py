@@ -15,6 +15,7 @@ Host-side mirror of the reference's graph construction:
   (data_loaders.py:381-391, 517-520).
 """
 import ctypes as C
+import math
 
 import numpy as np
 import torch
@@ -146,7 +147,8 @@ class CSRGraph:
     def csc(self):
         """(csc_ptr [N+1], csc_eid [E]): CSR edge ids grouped by neighbour."""
         if self._csc is None:
-            self._exact()
+            # no _exact(): the transpose reads the true edge count on the device
+            # (row_ptr[n]), so a capacity-bounded graph stays sync-free
             h = lib()
             dev = self.device
             csc_ptr = torch.empty(self.n_nodes + 1, dtype=torch.int32, device=dev)
@@ -201,6 +203,28 @@ def _device_ints(arr, device):
     return t
 
 
+def auto_edge_capacity(n_atoms, inter_radius, intra_radius):
+    """Upper bound on the directed edges of `n_atoms` protein-ligand atoms:
+    0.375 r^3 neighbours per atom (24 at r = 4 A; heavy-atom + polar-hydrogen
+    densities of crystal structures stay below 0.09 atoms / A^3, i.e. below
+    0.377 r^3 neighbours in a full sphere, and atoms near the surface of the
+    crop have fewer)."""
+    r = max(float(inter_radius), float(intra_radius), 1.0)
+    return int(math.ceil(0.375 * r ** 3)) * int(n_atoms)
+
+
+def _to_device(arr, dtype, device):
+    """Host array -> device tensor through pinned memory, without blocking:
+    a copy from pageable memory would first drain the stream (a hidden sync
+    per batch).  Device tensors pass through."""
+    if torch.is_tensor(arr) and arr.is_cuda:
+        return arr.to(device=device, dtype=dtype)
+    t = torch.as_tensor(arr, dtype=dtype)
+    if device.type != 'cuda' or t.numel() == 0:
+        return t.to(device)
+    return t.contiguous().pin_memory().to(device, non_blocking=True)
+
+
 def radius_graph_batch(coords, bp, complex_ptr, inter_radius=4.0,
                        intra_radius=2.0, with_ref_pos=False, device=None,
                        edge_capacity=None):
@@ -211,11 +235,14 @@ def radius_graph_batch(coords, bp, complex_ptr, inter_radius=4.0,
     order is the stable sort by destination of the reference's edge list.
 
     edge_capacity=None reads the edge count back once (the only host sync) to
-    size col/attr exactly.  With an int (an upper bound on E; 'auto' = 24
-    edges per atom) nothing is read back: `n_edges` of the result is the
-    capacity, `n_edges_dev` the true count on the device, and
+    size col/attr exactly.  With an int (an upper bound on E) or 'auto'
+    (`auto_edge_capacity`: 24 edges per atom at a 4 A cut-off, growing with
+    the cube of the radius) nothing is read back: `n_edges` of the result is
+    the capacity, `n_edges_dev` the true count on the device, and
     `check_overflow()` (a sync, call it whenever convenient) raises if the
-    bound was too small.
+    bound was too small.  Forward, backward and the CSR transpose all take the
+    true count from the device, so a training step on such a graph has no
+    host sync at all.
     """
     device = torch.device(device or 'cuda')
     h = lib()
@@ -250,7 +277,8 @@ def radius_graph_batch(coords, bp, complex_ptr, inter_radius=4.0,
             n_edges = int(row_ptr[-1].item())   # the one host sync
             capacity = n_edges
         else:
-            capacity = 24 * n if edge_capacity == 'auto' else int(edge_capacity)
+            capacity = auto_edge_capacity(n, inter_radius, intra_radius) \
+                if edge_capacity == 'auto' else int(edge_capacity)
             n_edges = capacity
         col = torch.empty(max(1, capacity), dtype=torch.int32, device=device)
         attr = torch.empty(max(1, capacity), dtype=torch.uint8, device=device)
@@ -432,10 +460,12 @@ class PackedBatch:
         """coords f64 [N,3], bp [N], feats f32 [N,F], complex_ptr [B+1]
         (host arrays, or device tensors for coords/bp/feats)."""
         device = torch.device(device or 'cuda')
-        coords_d = torch.as_tensor(coords, dtype=torch.float64).to(device)
+        coords_d = _to_device(coords, torch.float64, device)
+        if isinstance(bp, np.ndarray):
+            bp = _to_device(bp, torch.int32, device)
         csr = radius_graph_batch(coords_d, bp, complex_ptr, inter_radius,
                                  intra_radius, device=device,
                                  edge_capacity=edge_capacity)
-        x = torch.as_tensor(feats, dtype=torch.float32).to(device)
+        x = _to_device(feats, torch.float32, device)
         return PackedBatch(x, coords_d.float(), csr, csr.complex_ptr, y=y,
                            lig_fname=lig_fname, rec_fname=rec_fname)

@@ -12,7 +12,7 @@ coords, bp, feats, cptr = synthetic_batch(0, 16, 1000, 30)
 y = torch.tensor([i % 2 for i in range(16)], dtype=torch.float32, device=dev)
 c,b,f = torch.from_numpy(coords).to(dev), torch.from_numpy(bp).to(dev), torch.from_numpy(feats).to(dev)
 def step():
-    batch = pv.PackedBatch.from_arrays(c, b, f, cptr, 4.0, 4.0, y=y, device=dev)
+    batch = pv.PackedBatch.from_arrays(c, b, f, cptr, 4.0, 4.0, y=y, device=dev, edge_capacity='auto')
     batch.lig_fname = batch.rec_fname = [''] * 16
     yp, yt, _, _ = model.unpack_input_data_and_predict(batch)
     return model.backprop(yt, yp, sync=False)
@@ -35,3 +35,4 @@ torch.zeros, torch.zeros_like, torch.Tensor.zero_ = orig_zeros, orig_zeros_like,
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=25, max_name_column_width=60))
+print(prof.key_averages().table(sort_by='self_cpu_time_total', row_limit=45, max_name_column_width=70))

@@ -31,6 +31,8 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--math', default='fp32', choices=['fp32', 'bf16x3', 'bf16'])
+    ap.add_argument('--exact-edges', action='store_true',
+                    help='size the edge lists exactly (one host sync per step)')
     args = ap.parse_args()
     rank, local_rank, world, dev = parallel.init_from_env()
     kw = dict(dim_input=13, dim_output=1, k=64, num_layers=8,
@@ -54,12 +56,16 @@ def main():
                      torch.from_numpy(bp).to(dev),
                      torch.from_numpy(feats).to(dev), cptr, y))
 
+    overflow = []
+
     def step(i):
         coords, bp, feats, cptr, y = sets[i % 3]
         batch = pv.PackedBatch.from_arrays(coords, bp, feats, cptr, 4.0, 4.0,
-                                           y=y, device=dev)
+                                           y=y, device=dev,
+                                           edge_capacity=None if args.exact_edges else 'auto')
         batch.lig_fname = batch.rec_fname = [''] * args.batch
         y_pred, y_true, _, _ = model.unpack_input_data_and_predict(batch)
+        overflow.append(batch.pvs_csr._overflow)
         return model.backprop(y_true, y_pred, sync=False)
 
     losses = [step(i) for i in range(args.warmup)]
@@ -76,6 +82,7 @@ def main():
     ev1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    assert int(torch.stack(overflow).sum().item()) == 0, 'edge capacity exceeded'
     flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
     same = True
     if world > 1:

@@ -63,11 +63,11 @@ def oracle_forward(model, kw, graph, multitask=False, task='classification',
 
 
 def synthetic_graph(first_seed, n_complexes, n_atoms, n_lig, radii=(4.0, 4.0),
-                    ragged=False, device='cuda'):
+                    ragged=False, device='cuda', edge_capacity=None):
     """PackedBatch (K1-built CSR) for synthetic complexes."""
     from pointvs_b200.graph import PackedBatch
     from pointvs_b200.synthetic import synthetic_batch
     coords, bp, feats, cptr = synthetic_batch(first_seed, n_complexes, n_atoms,
                                               n_lig, ragged=ragged)
     return PackedBatch.from_arrays(coords, bp, feats, cptr, *radii,
-                                   device=device)
+                                   device=device, edge_capacity=edge_capacity)

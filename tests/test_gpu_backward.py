@@ -234,3 +234,57 @@ def test_stacked_training_pass_equals_per_layer_pass(monkeypatch):
         assert (g0[name] is None) == (g1[name] is None), name
         if g0[name] is not None:
             assert torch.equal(g0[name], g1[name]), name
+
+
+@pytest.mark.parametrize('math', ['fp32', 'bf16x3'])
+def test_capacity_bounded_graph_trains_without_a_sync_and_bit_identically(math):
+    """edge_capacity='auto': the edge list is allocated at a bound and the true
+    edge count never leaves the device (forward, backward and the CSR
+    transpose read row_ptr[n]).  Outputs and gradients are bit-identical to
+    the exactly-sized graph, and the graph is still un-trimmed afterwards."""
+    kw = dict(dim_input=13, dim_output=1, graphnorm=False, **VARIANTS['cfg3_k64'])
+    results = []
+    for cap in (None, 'auto'):
+        model = gh.build_model(kw, seed=7, coord_gain=1.0).train()
+        model.set_math(math)
+        graph = gh.synthetic_graph(900, 3, 400, 15, ragged=True,
+                                   edge_capacity=cap)
+        csr = graph.pvs_csr
+        assert csr.exact_edge_count == (cap is None)
+        graph.pos = graph.pos.clone().requires_grad_(True)
+        out = model(graph)
+        out.sum().backward()
+        if cap is not None:
+            assert not csr.exact_edge_count          # nobody forced a read-back
+            assert csr.n_edges > csr.true_edge_count()
+            csr.check_overflow()
+        grads = {n: (None if p.grad is None else p.grad.clone())
+                 for n, p in model.named_parameters()}
+        results.append((out.detach().clone(), graph.pos.grad.clone(), grads))
+    (o0, x0, g0), (o1, x1, g1) = results
+    assert torch.equal(o0, o1) and torch.equal(x0, x1)
+    for name in g0:
+        assert (g0[name] is None) == (g1[name] is None), name
+        if g0[name] is not None:
+            assert torch.equal(g0[name], g1[name]), name
+
+
+def test_train_model_raises_on_edge_capacity_overflow():
+    """A capacity bound that is too small is reported at the next loss drain
+    (not silently trained through)."""
+    import pointvs_b200 as pv
+    from pathlib import Path
+    kw = dict(dim_input=13, dim_output=1, graphnorm=False, **VARIANTS['cfg3_k64'])
+    torch.manual_seed(0)
+    model = pv.SartorrasEGNN(Path('/tmp/pvs_test_overflow'), 1e-3, 0, None, None,
+                             silent=True, **kw).cuda().train()
+
+    def loader(cap):
+        g = gh.synthetic_graph(50, 2, 300, 15, edge_capacity=cap)
+        g.y = torch.tensor([1.0, 0.0], device='cuda')
+        g.lig_fname = g.rec_fname = ['x'] * 2
+        return [g]
+    losses = model.train_model(loader('auto'), epochs=1)
+    assert len(losses) == 1 and np.isfinite(losses[0])
+    with pytest.raises(RuntimeError, match='edge capacity exceeded'):
+        model.train_model(loader(600), epochs=2)
