@@ -43,6 +43,7 @@ namespace pvs {
 namespace {
 
 constexpr int BT = 256;
+constexpr int WG_ISSUER = 128;    // thread that issues the weight-gradient MMAs
 constexpr int KB = 64;
 // TMEM columns
 constexpr uint32_t C_D1 = 0, C_D2 = 64, C_D3 = 128, C_D4 = 192, C_DW2 = 256, C_DWC1 = 320;
@@ -72,7 +73,9 @@ struct BwdTcSmem {
     int e_rowl[TE], e_col[TE], e_attr[TE];
     int rp[TN + 1];
     float xsum[TN][3];
-    uint64_t mbar;
+    float xn[TN][3], dxo[TN][3];                // x_in, d_x_out of the tile's nodes
+    uint64_t mbar;                              // data-gradient GEMMs
+    uint64_t mbar_wg;                           // weight-gradient GEMMs (waited late)
     uint32_t tmem_base;
 };
 
@@ -161,6 +164,22 @@ __device__ __forceinline__ uint32_t sg_off(int r, int ch) {
     return (uint32_t)(r * 128 + ((ch ^ (r & 7)) << 4));
 }
 
+#ifdef PVS_PHASE_PROF
+// Debug build only (scripts/phase_prof.py --bwd): cycles of thread 0 between
+// the phase boundaries of a tile, summed over all CTAs and tiles.
+__device__ unsigned long long g_bwd_phase_cycles[16];
+#define BPH(i)                                                                \
+    do {                                                                      \
+        if (tid == 0) {                                                       \
+            const long long now_ = clock64();                                 \
+            atomicAdd(&g_bwd_phase_cycles[i], (unsigned long long)(now_ - t_prev_)); \
+            t_prev_ = now_;                                                   \
+        }                                                                     \
+    } while (0)
+#else
+#define BPH(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(BT, 1)
 egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -194,7 +213,7 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
         for (int v = 0; v < 5; ++v) S.acc_vec[v][n] = 0.0f;
     }
     if (tid < 2) S.acc_s[tid] = 0.0f;
-    if (tid == 0) mbar_init(&S.mbar, 1);
+    if (tid == 0) { mbar_init(&S.mbar, 1); mbar_init(&S.mbar_wg, 1); }
     if (tid < 32) tmem_alloc<512>(&S.tmem_base);
     fence_proxy_async();
     tc_fence_before();
@@ -202,11 +221,19 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = S.tmem_base;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 32u * hf;
-    uint32_t phase = 0;
+    uint32_t phase = 0, phase_wg = 0;
+    bool wg_pending = false;               // a weight-gradient GEMM still reads S1 / X / M
     const float att_b = (f_att && a.att_b) ? a.att_b[0] : 0.0f;
     // per-thread accumulators that live across tiles: column 32 hf + lane
     float gb2 = 0.f, gbc1 = 0.f, gwc2 = 0.f, gwa = 0.f, gba = 0.f;
     uint32_t acc_w2 = 0, acc_wc1 = 0;      // 0 until the first weight-gradient MMA
+    // d w_r and d T[class] of channels 4 (lane & 15) .. + 3 over the nodes this
+    // half warp sums in S6c
+    constexpr int FAST_CLASSES = 4;
+    const bool fast_classes = a.n_classes <= FAST_CLASSES;
+    float4 awr = make_float4(0.f, 0.f, 0.f, 0.f), aT[FAST_CLASSES];
+#pragma unroll
+    for (int c = 0; c < FAST_CLASSES; ++c) aT[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int n_tiles = *a.n_tiles;
 
     auto ld32 = [&](uint32_t col, float (&v)[32]) {
@@ -236,6 +263,18 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
         phase ^= 1;
         tc_fence_after();
     };
+    // The weight-gradient GEMMs are committed to their own barrier, AFTER the
+    // data GEMM of the same step: the epilogue that needs the data GEMM starts
+    // as soon as that one is done, and the tiles the weight-gradient GEMM reads
+    // are only waited for right before they are overwritten.
+    auto wait_wgrad = [&]() {
+        if (wg_pending) {
+            mbar_wait(&S.mbar_wg, phase_wg);
+            phase_wg ^= 1;
+            tc_fence_after();
+            wg_pending = false;
+        }
+    };
     // make this thread's shared-memory writes visible to the tensor core, then barrier
     auto publish = [&]() {
         fence_proxy_async();
@@ -243,13 +282,69 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
         __syncthreads();
     };
 
+#ifdef PVS_PHASE_PROF
+    long long t_prev_ = clock64();
+#endif
+    // The next tile's node window, first 128 edges and their coordinates are
+    // requested one tile ahead, into registers, in four steps placed where the
+    // current tile waits on the tensor core anyway: each step needs the result
+    // of the one before (tile_ptr -> row_ptr -> col -> x), and taken at the top
+    // of the tile those four dependent global round trips were 16 % of the
+    // kernel.  (TN + 1 <= BT: one row_ptr entry per thread.)
+    static_assert(TN + 1 <= BT && TE <= BT, "one prefetched entry per thread");
+    int nx_n0 = 0, nx_nn = -1, nx_e0 = 0, nx_e1 = 0, nx_rp = 0, nx_col = 0, nx_attr = 0;
+    float nx_xj[3] = {0.f, 0.f, 0.f}, nx_xi[3] = {0.f, 0.f, 0.f}, nx_dxo[3] = {0.f, 0.f, 0.f};
+    auto pf_tile = [&](int tn) {
+        nx_nn = -1;
+        if (tn < n_tiles) {
+            nx_n0 = a.tile_ptr[tn];
+            nx_nn = a.tile_ptr[tn + 1] - nx_n0;
+        }
+    };
+    auto pf_rows = [&]() {
+        if (nx_nn < 0) return;
+        nx_e0 = a.row_ptr[nx_n0];
+        nx_e1 = a.row_ptr[nx_n0 + nx_nn];
+        if (tid <= nx_nn) nx_rp = a.row_ptr[nx_n0 + tid];
+        if (tid < nx_nn) {
+            const int i = nx_n0 + tid;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                nx_xi[c] = a.x_in[3 * i + c];
+                nx_dxo[c] = (f_coords && a.d_x_out) ? a.d_x_out[3 * i + c] : 0.0f;
+            }
+        }
+    };
+    auto pf_edges = [&]() {
+        if (nx_nn < 0 || tid >= TE || nx_e0 + tid >= nx_e1) return;
+        nx_col = a.col[nx_e0 + tid];
+        nx_attr = a.attr ? a.attr[nx_e0 + tid] : 0;
+    };
+    auto pf_coords = [&]() {
+        if (nx_nn < 0 || tid >= TE || nx_e0 + tid >= nx_e1) return;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) nx_xj[c] = a.x_in[3 * nx_col + c];
+    };
+    pf_tile(blockIdx.x);
+    pf_rows();
+    pf_edges();
+    pf_coords();
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int n0 = a.tile_ptr[t], n1 = a.tile_ptr[t + 1];
-        const int nn = n1 - n0;
+        const int n0 = nx_n0, nn = nx_nn;
+        const int my_col = nx_col, my_attr = nx_attr;
+        const float my_xj[3] = {nx_xj[0], nx_xj[1], nx_xj[2]};
         __syncthreads();
-        for (int i = tid; i <= nn; i += BT) S.rp[i] = a.row_ptr[n0 + i];
-        for (int i = tid; i < nn * 3; i += BT) (&S.xsum[0][0])[i] = 0.0f;
+        if (tid <= nn) S.rp[tid] = nx_rp;
+        if (tid < nn) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                S.xn[tid][c] = nx_xi[c];
+                S.dxo[tid][c] = nx_dxo[c];
+                S.xsum[tid][c] = 0.0f;
+            }
+        }
         __syncthreads();
+        pf_tile(t + gridDim.x);
         const int e0 = S.rp[0], e1 = S.rp[nn];
         const int n_chunks = max(1, (e1 - e0 + TE - 1) / TE);
         for (int ch = 0; ch < n_chunks; ++ch) {
@@ -257,6 +352,7 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
             const int ne = min(TE, e1 - c0);
             if (ne > 0) {
             // ---- S0: geometry and d(trans) ----
+            BPH(0);
             if (tid < TE) {
                 if (tid < ne) {
                     const int e = c0 + tid;
@@ -265,14 +361,20 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                         int mid = (lo + hi) >> 1;
                         if (S.rp[mid] <= e) lo = mid; else hi = mid;
                     }
-                    const int i = n0 + lo, j = a.col[e];
-                    const float rx = a.x_in[3 * i] - a.x_in[3 * j];
-                    const float ry = a.x_in[3 * i + 1] - a.x_in[3 * j + 1];
-                    const float rz = a.x_in[3 * i + 2] - a.x_in[3 * j + 2];
+                    const int j = ch == 0 ? my_col : a.col[e];
+                    float xj[3];
+                    if (ch == 0) { xj[0] = my_xj[0]; xj[1] = my_xj[1]; xj[2] = my_xj[2]; }
+                    else {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) xj[c] = a.x_in[3 * j + c];
+                    }
+                    const float rx = S.xn[lo][0] - xj[0];
+                    const float ry = S.xn[lo][1] - xj[1];
+                    const float rz = S.xn[lo][2] - xj[2];
                     const float r = rx * rx + ry * ry + rz * rz;
                     const float invn = f_norm ? 1.0f / (sqrtf(r) + 1e-8f) : 1.0f;
                     S.e_rowl[tid] = lo; S.e_col[tid] = j;
-                    S.e_attr[tid] = a.attr ? a.attr[e] : 0;
+                    S.e_attr[tid] = ch == 0 ? my_attr : (a.attr ? a.attr[e] : 0);
                     S.e_rad[tid] = r;
                     S.e_rx[tid] = rx; S.e_ry[tid] = ry; S.e_rz[tid] = rz;
                     S.e_invn[tid] = invn;
@@ -281,9 +383,9 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                     if (f_coords && a.d_x_out) {
                         const int cnt = S.rp[lo + 1] - S.rp[lo];
                         const float ic = 1.0f / (float)(cnt > 0 ? cnt : 1);
-                        tx = a.d_x_out[3 * i] * ic;
-                        ty = a.d_x_out[3 * i + 1] * ic;
-                        tz = a.d_x_out[3 * i + 2] * ic;
+                        tx = S.dxo[lo][0] * ic;
+                        ty = S.dxo[lo][1] * ic;
+                        tz = S.dxo[lo][2] * ic;
                     }
                     S.e_tx[tid] = tx; S.e_ty[tid] = ty; S.e_tz[tid] = tz;
                 } else {
@@ -300,9 +402,11 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
             }
             __syncthreads();
             // ---- S1: t1 -> s1 (S1 tile), silu'(t1) (SG); 8 lanes per edge row ----
+            BPH(1);
+            wait_wgrad();                  // dW2 of the previous tile read S1 and X
             {
                 const int c = tid & 7, slot = tid >> 3;
-                float4 buf[2][4];
+                float4 buf[4][4];          // all four passes in flight
                 auto issue = [&](int p, float4 (&bq)[4]) {
                     const int r = min(p * 32 + slot, ne - 1);
                     const float4 *pp = reinterpret_cast<const float4 *>(
@@ -312,11 +416,11 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                     bq[0] = __ldg(pp); bq[1] = __ldg(pp + 1);
                     bq[2] = __ldg(qq); bq[3] = __ldg(qq + 1);
                 };
-                issue(0, buf[0]);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) issue(p, buf[p]);
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    if (p + 1 < 4) issue(p + 1, buf[(p + 1) & 1]);
-                    const float4 (&bq)[4] = buf[p & 1];
+                    const float4 (&bq)[4] = buf[p];
                     const int r = p * 32 + slot, re = min(r, ne - 1);
                     const float rad = S.e_rad[re];
                     const int at = S.e_attr[re];
@@ -344,12 +448,15 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
             }
             publish();
             // ---- G1: t2 = s1 . W2^T -> D1 (kept until dt2 is formed) ----
+            BPH(2);
             if (tid == 0) {
                 tc_fence_after();
                 mma_data(tmem_base + C_D1, S.S1, S.W2);
             }
+            if (ch == 0) pf_rows();
             commit_wait();
             // ---- E1: m = silu(t2 + b2) -> M tile; attention logit partial ----
+            BPH(3);
             {
                 float v[32];
                 ld32(C_D1, v);
@@ -367,6 +474,7 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
             }
             publish();
             // ---- G2: p = m . Wc1^T -> D2 ----
+            BPH(4);
             if (f_coords && tid == 0) {
                 tc_fence_after();
                 mma_data(tmem_base + C_D2, S.Mt, S.Wc1);
@@ -380,9 +488,24 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                 S.e_z[tid] = z;
                 S.e_alpha[tid] = al;
             }
+            // dM of this thread's row (needed in E3; requested before the GEMM wait)
+            float dMv[32];
+            auto load_dM = [&]() {
+                const float4 *src = reinterpret_cast<const float4 *>(
+                    a.dM + (size_t)(n0 + S.e_rowl[erow]) * KB + 32 * hf);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (erow < ne) d4 = __ldg(src + i);
+                    dMv[4 * i] = d4.x; dMv[4 * i + 1] = d4.y;
+                    dMv[4 * i + 2] = d4.z; dMv[4 * i + 3] = d4.w;
+                }
+            };
+            if (ch == 0) pf_edges();
             if (f_coords) {
                 commit_wait();
                 // ---- E2: q = silu(p + bc1), craw = wc2 . q; then dp -> X tile ----
+            BPH(5);
                 float q[32], sgp[32];
                 {
                     float v[32];
@@ -398,6 +521,7 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                 }
                 tc_fence_before();
                 __syncthreads();
+                BPH(6);
                 if (tid < TE) {
                     float c = 0.0f, dcraw = 0.0f;
                     if (tid < ne) {
@@ -425,28 +549,30 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                 }
                 publish();
                 // ---- G3: dWc1 += dp^T . m ; G4: dmc = dp . Wc1 -> D3 ----
+            BPH(7);
                 if (tid == 0) {
                     tc_fence_after();
-                    mma_wgrad(tmem_base + C_DWC1, S.Xt, S.Mt, acc_wc1);
                     mma_data(tmem_base + C_D3, S.Xt, S.Wc1T);
+                    umma_commit(&S.mbar);
+                } else if (tid == WG_ISSUER) {
+                    // 24 more instructions: issued from another warp, so that
+                    // neither issuer is late for its own epilogue rows
+                    tc_fence_after();
+                    mma_wgrad(tmem_base + C_DWC1, S.Xt, S.Mt, acc_wc1);
+                    umma_commit(&S.mbar_wg);
                 }
                 acc_wc1 = 1;
-                commit_wait();
+                wg_pending = true;
+                load_dM();                 // in flight during the GEMM
+                mbar_wait(&S.mbar, phase);
+                phase ^= 1;
+                tc_fence_after();
+                BPH(8);
+            } else {
+                load_dM();
             }
             // ---- E3: attention backward, total dm, dt2 -> X tile ----
             {
-                float dMv[32];
-                {
-                    const float4 *src = reinterpret_cast<const float4 *>(
-                        a.dM + (size_t)(n0 + S.e_rowl[erow]) * KB + 32 * hf);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (erow < ne) d4 = __ldg(src + i);
-                        dMv[4 * i] = d4.x; dMv[4 * i + 1] = d4.y;
-                        dMv[4 * i + 2] = d4.z; dMv[4 * i + 3] = d4.w;
-                    }
-                }
                 float m[32], sg2[32];
                 {
                     float v[32];
@@ -485,19 +611,30 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                     dt2[i] = (erow < ne && n < k) ? dm * sg2[i] : 0.0f;
                     m[i] *= dz;                        // d wa contribution
                 }
+                wait_wgrad();              // dWc1 read the X tile (dp) and the M tile
                 store_row(S.Xt, dt2);
                 gb2 += warp_colsum32(dt2, lane);
                 if (f_att) gwa += warp_colsum32(m, lane);
             }
             publish();
             // ---- G5: dW2 += dt2^T . s1 ; G6: ds1 = dt2 . W2 -> D4 ----
+            BPH(9);
             if (tid == 0) {
                 tc_fence_after();
-                mma_wgrad(tmem_base + C_DW2, S.Xt, S.S1, acc_w2);
                 mma_data(tmem_base + C_D4, S.Xt, S.W2T);
+                umma_commit(&S.mbar);
+            } else if (tid == WG_ISSUER) {
+                tc_fence_after();
+                mma_wgrad(tmem_base + C_DW2, S.Xt, S.S1, acc_w2);
+                umma_commit(&S.mbar_wg);
             }
             acc_w2 = 1;
-            commit_wait();
+            wg_pending = true;
+            if (ch == 0) pf_coords();
+            mbar_wait(&S.mbar, phase);
+            phase ^= 1;
+            tc_fence_after();
+            BPH(10);
             // ---- E4: dt1 = ds1 * silu'(t1) -> SG (in place), DT1; d radial partial ----
             {
                 float v[32];
@@ -522,6 +659,7 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
             }
             __syncthreads();
             // ---- S6a: per-edge d(diff): dd = 2 d dr + d(d_hat) / norm ----
+            BPH(11);
             if (tid < TE) {
                 float ddx = 0.f, ddy = 0.f, ddz = 0.f;
                 if (tid < ne) {
@@ -536,9 +674,12 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                 }
                 S.e_ddx[tid] = ddx; S.e_ddy[tid] = ddy; S.e_ddz[tid] = ddz;
             }
-            // ---- S6b: d w_r and d T[class] from the dt1 tile (one owner thread
-            // per channel: deterministic, no atomics) ----
-            if (tid >= TE && tid < TE + 64) {
+            // ---- S6b: d w_r and d T[class] from the dt1 tile.  Up to FAST_CLASSES
+            // edge classes these sums ride along with S6c below (per-lane register
+            // accumulators over all tiles, reduced once at the end); with more
+            // classes one owner thread per channel walks the tile.  Both are
+            // deterministic (fixed order, no atomics). ----
+            if (!fast_classes && tid >= TE && tid < TE + 64) {
                 const int n = tid - TE;
                 const uint8_t *sg = reinterpret_cast<const uint8_t *>(S.SG[n >> 5]);
                 const int chn = (n & 31) >> 2, sub = n & 3;
@@ -553,24 +694,45 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                 S.acc_vec[4][n] += swr;
                 for (int c = 0; c < a.n_classes; ++c) S.acc_T[c][n] += sT[c];
             }
-            // ---- S6c: dP_i = sum over the node's edges of dt1 ----
-            for (int nl = warp; nl < nn; nl += BT / 32) {
+            // ---- S6c: dP_i = sum over the node's edges of dt1; half a warp per
+            // node (16 lanes x 4 channels), 16 nodes at a time ----
+            for (int nl = 2 * warp + (lane >> 4); nl < nn; nl += BT / 16) {
                 const int lo = max(S.rp[nl], c0) - c0;
                 const int hi = min(S.rp[nl + 1], c0 + TE) - c0;
-                const uint8_t *sg = reinterpret_cast<const uint8_t *>(S.SG[lane >> 4]);
-                const int chn = (lane & 15) >> 1, sub = (lane & 1) * 2;
-                float s0 = 0.f, s1 = 0.f;
-                for (int el = lo; el < hi; ++el) {
-                    const float2 d2 = *reinterpret_cast<const float2 *>(
-                        reinterpret_cast<const float *>(sg + sg_off(el, chn)) + sub);
-                    s0 += d2.x; s1 += d2.y;
+                const int l16 = lane & 15;
+                const uint8_t *sg = reinterpret_cast<const uint8_t *>(S.SG[l16 >> 3]);
+                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (fast_classes) {
+                    for (int el = lo; el < hi; ++el) {
+                        const float4 d = *reinterpret_cast<const float4 *>(sg + sg_off(el, l16 & 7));
+                        sum.x += d.x; sum.y += d.y; sum.z += d.z; sum.w += d.w;
+                        const float rad = S.e_rad[el];
+                        awr.x = fmaf(d.x, rad, awr.x); awr.y = fmaf(d.y, rad, awr.y);
+                        awr.z = fmaf(d.z, rad, awr.z); awr.w = fmaf(d.w, rad, awr.w);
+                        const int at = S.e_attr[el];     // uniform over the half warp
+#pragma unroll
+                        for (int c = 0; c < FAST_CLASSES; ++c) {
+                            const float w = (at == c || (c == FAST_CLASSES - 1 && at > c)) ? 1.0f : 0.0f;
+                            aT[c].x = fmaf(d.x, w, aT[c].x); aT[c].y = fmaf(d.y, w, aT[c].y);
+                            aT[c].z = fmaf(d.z, w, aT[c].z); aT[c].w = fmaf(d.w, w, aT[c].w);
+                        }
+                    }
+                } else {
+                    for (int el = lo; el < hi; ++el) {
+                        const float4 d = *reinterpret_cast<const float4 *>(sg + sg_off(el, l16 & 7));
+                        sum.x += d.x; sum.y += d.y; sum.z += d.z; sum.w += d.w;
+                    }
                 }
-                float2 *dst = reinterpret_cast<float2 *>(a.dP + (size_t)(n0 + nl) * KB + 2 * lane);
-                if (ch == 0) *dst = make_float2(s0, s1);
-                else if (hi > lo) { float2 o = *dst; *dst = make_float2(o.x + s0, o.y + s1); }
+                float4 *dst = reinterpret_cast<float4 *>(a.dP + (size_t)(n0 + nl) * KB + 4 * l16);
+                if (ch == 0) *dst = sum;
+                else if (hi > lo) {
+                    const float4 o = *dst;
+                    *dst = make_float4(o.x + sum.x, o.y + sum.y, o.z + sum.z, o.w + sum.w);
+                }
             }
             __syncthreads();
             // ---- S6d: row part of dx ----
+            BPH(12);
             if (tid < nn) {
                 const int lo = max(S.rp[tid], c0) - c0;
                 const int hi = min(S.rp[tid + 1], c0 + TE) - c0;
@@ -581,21 +743,27 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                 S.xsum[tid][0] += sx; S.xsum[tid][1] += sy; S.xsum[tid][2] += sz;
             }
             } else {
-                // edgeless tile: dP = 0
+                // edgeless tile: dP = 0 (and the whole look-ahead in one go)
+                pf_rows();
+                pf_edges();
+                pf_coords();
                 for (int nl = warp; nl < nn; nl += BT / 32)
                     *reinterpret_cast<float2 *>(a.dP + (size_t)(n0 + nl) * KB + 2 * lane) =
                         make_float2(0.f, 0.f);
             }
             __syncthreads();
+            BPH(13);
         }
         if (tid < nn) {
             const int i = n0 + tid;
 #pragma unroll
             for (int c = 0; c < 3; ++c)
                 a.d_x_in[3 * i + c] = (a.d_x_out ? a.d_x_out[3 * i + c] : 0.0f) + S.xsum[tid][c];
+            // (d_x_out itself, not S.dxo: that copy is zero when coordinates are frozen)
         }
     }
     // ---- per-CTA partials (fixed-order reductions: bitwise reproducible) ----
+    wait_wgrad();
     __syncthreads();
     S.red[warp][0][lane] = gb2;
     S.red[warp][1][lane] = gbc1;
@@ -618,6 +786,26 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
         S.acc_s[1] = 0.0f;
     }
     __syncthreads();
+    if (fast_classes) {
+        // the S6c riders: warp partials -> channel totals, in warp order (the SG
+        // tile is free by now)
+        float *wp = reinterpret_cast<float *>(S.SG[0]);        // [16][1 + FAST_CLASSES][64]
+        const int slot = 2 * warp + (lane >> 4), l16 = lane & 15;
+        *reinterpret_cast<float4 *>(&wp[(slot * (1 + FAST_CLASSES)) * 64 + 4 * l16]) = awr;
+#pragma unroll
+        for (int c = 0; c < FAST_CLASSES; ++c)
+            *reinterpret_cast<float4 *>(
+                &wp[(slot * (1 + FAST_CLASSES) + 1 + c) * 64 + 4 * l16]) = aT[c];
+        __syncthreads();
+        for (int idx = tid; idx < (1 + FAST_CLASSES) * 64; idx += BT) {
+            const int v = idx >> 6, n = idx & 63;
+            float s_ = 0.0f;
+            for (int w = 0; w < BT / 16; ++w) s_ += wp[(w * (1 + FAST_CLASSES) + v) * 64 + n];
+            if (v == 0) S.acc_vec[4][n] += s_;
+            else S.acc_T[v - 1][n] += s_;
+        }
+        __syncthreads();
+    }
     float *out = a.partial + (size_t)blockIdx.x * EP_STRIDE;
     // weight-gradient accumulators: UMMA M = 64 puts row n on TMEM lane
     // 32 (n / 16) + n % 16, so lanes 0..15 of warps 0..3 read 16 rows each
@@ -654,6 +842,18 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
 }
 
 }  // namespace
+
+#ifdef PVS_PHASE_PROF
+extern "C" int pvs_debug_bwd_phase_cycles(unsigned long long *out, int reset) {
+    cudaDeviceSynchronize();
+    if (out) cudaMemcpyFromSymbol(out, g_bwd_phase_cycles, sizeof(g_bwd_phase_cycles));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_bwd_phase_cycles, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 bool edge_bwd_tc_supported(const EdgeBwdArgs &a) {
     const bool eres = (a.flags & PVS_F_EDGE_RESIDUAL) && a.m_prev != nullptr;

@@ -71,14 +71,67 @@ def run(math, steps):
     print(json.dumps(res, indent=1))
 
 
+BWD_PHASES = ['0 tile setup (row_ptr window)', '1 S0 geometry', '2 S1 gather + SiLU -> S1/SG',
+              '3 G1 wait', '4 E1 m -> M tile', '5 G2 wait', '6 E2a q, craw',
+              '7 E2b dcraw, dp -> X tile', '8 G3+G4 wait', '9 E3 attention bwd, dt2 -> X tile',
+              '10 G5+G6 wait', '11 E4 dt1 -> SG, DT1', '12 S6a-c dd, d w_r/T, dP', '13 S6d dx rows']
+
+
+def run_bwd(math, steps):
+    """Phase shares of the tcgen05 edge BACKWARD kernel over training steps of
+    the 16-complex batch (scripts/train_bench.py's workload)."""
+    os.environ['PVS_B200_LIB'] = str(PROF_LIB)
+    sys.path.insert(0, str(ROOT))
+    import torch
+    import pointvs_b200 as pv
+    from pointvs_b200 import _cabi
+    from pointvs_b200.synthetic import synthetic_batch
+    kw = dict(dim_input=13, dim_output=1, k=64, num_layers=8, edge_attention=True,
+              node_attention=True, residual=True, normalize=True, tanh=True,
+              graphnorm=False, model_task='classification')
+    model = pv.MultitaskSatorrasEGNN(Path('/tmp/pvs_train'), 1e-3, 1e-4, None, None,
+                                     silent=True, **kw).cuda().train()
+    model.set_math(math)
+    model.set_record_side_channels(False)
+    coords, bp, feats, cptr = synthetic_batch(0, 16, 1000, 30)
+    y = torch.tensor([i % 2 for i in range(16)], dtype=torch.float32, device='cuda')
+    c, b, f = (torch.from_numpy(a_).cuda() for a_ in (coords, bp, feats))
+    lib = _cabi.lib()
+    lib.pvs_debug_bwd_phase_cycles.argtypes = [C.c_void_p, C.c_int]
+
+    def step():
+        batch = pv.PackedBatch.from_arrays(c, b, f, cptr, 4.0, 4.0, y=y, device='cuda',
+                                           edge_capacity='auto')
+        batch.lig_fname = batch.rec_fname = [''] * 16
+        yp, yt, _, _ = model.unpack_input_data_and_predict(batch)
+        model.backprop(yt, yp, sync=False)
+    for _ in range(2):
+        step()
+    lib.pvs_debug_bwd_phase_cycles(None, 1)
+    for _ in range(steps):
+        step()
+    out = (C.c_ulonglong * 16)()
+    lib.pvs_debug_bwd_phase_cycles(C.cast(out, C.c_void_p), 0)
+    cyc = [int(out[i]) for i in range(14)]
+    tot = sum(cyc)
+    res = {BWD_PHASES[i]: round(cyc[i] / tot, 4) for i in range(14)}
+    res['cta_cycles_per_launch'] = tot // (steps * 8)
+    res['cycles_per_cta_per_launch'] = tot // (steps * 8 * 148)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--build', action='store_true')
     ap.add_argument('--run', action='store_true')
+    ap.add_argument('--bwd', action='store_true',
+                    help='with --run: the edge backward kernel over training steps')
     ap.add_argument('--math', default='bf16x3')
     ap.add_argument('--steps', type=int, default=3)
     a = ap.parse_args()
     if a.build:
         build()
-    if a.run:
+    if a.run and a.bwd:
+        run_bwd(a.math, a.steps)
+    elif a.run:
         run(a.math, a.steps)
