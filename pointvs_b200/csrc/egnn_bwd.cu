@@ -32,7 +32,6 @@ constexpr int LDT = KB + 4;       // smem tile pitch
 // ---------------------------------------------------------------------------
 // wgrad: partial[cta] = A[rows, ko<=64]^T . B[rows, ki<=128] (+ column sums of A)
 // ---------------------------------------------------------------------------
-constexpr int WG_PART = 64 * 128 + 64;
 
 __global__ void __launch_bounds__(BT)
 wgrad_kernel(const float *__restrict__ A, int lda, int ko,
@@ -145,17 +144,6 @@ static int launch_wgrad(const float *A, int lda, int ko, const float *B, int ldb
 // its reduce another ~7 us, six times per layer; grouped, the products of a layer
 // share the machine (and the L2 lines of the operands they have in common).
 // ---------------------------------------------------------------------------
-constexpr int WG_MAX_JOBS = 8;
-struct WgradJob {
-    const float *A; const float *B;   // B == nullptr: column sums of A only
-    float *d_w; float *d_b;
-    int lda, ko, ldb, ki, ld_dw;
-};
-struct WgradGroup {
-    WgradJob job[WG_MAX_JOBS];
-    int n_jobs, rows, chunks, rows_per;   // chunks CTAs per job, rows_per rows each
-};
-
 __global__ void __launch_bounds__(BT)
 wgrad_group_kernel(const __grid_constant__ WgradGroup G, float *__restrict__ partial) {
     constexpr int WR = 32;
@@ -265,8 +253,16 @@ struct WgradGroupBuilder {
         J.A = A; J.lda = lda; J.ko = ko; J.B = B; J.ldb = ldb; J.ki = ki;
         J.d_w = B ? d_w : nullptr; J.ld_dw = ld_dw; J.d_b = d_b;
     }
-    int launch(int rows, float *partial, cudaStream_t st) {
+    // tc: the products on tcgen05 (wgrad_tc.cu, bf16x3) instead of FFMA
+    int launch(int rows, float *partial, cudaStream_t st, bool tc) {
         if (rows <= 0 || G.n_jobs == 0) return PVS_OK;
+        if (tc) {
+            const int rc = launch_wgrad_group_tc(G, rows, wg_group_ctas(), partial, st);
+            if (rc) return rc;
+            wgrad_group_reduce_kernel<<<dim3((WG_PART + 255) / 256, G.n_jobs), 256, 0, st>>>(
+                G, partial);
+            return check_launch(2);
+        }
         int chunks = (rows + 127) / 128;
         const int cap = wg_group_ctas() / G.n_jobs;
         if (chunks > cap) chunks = cap;
@@ -1470,7 +1466,7 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
         wg.add(w.dQ, KB, k, h_in, k, k, grads->edge_w1 ? grads->edge_w1 + k : nullptr, in_e,
                nullptr);
     }
-    rc = wg.launch(n, w.wg_partial, st);
+    rc = wg.launch(n, w.wg_partial, st, cfg->math != PVS_MATH_FP32);
     if (rc) return rc;
     return PVS_OK;
 }

@@ -37,4 +37,24 @@ struct EdgeBwdArgs {
 bool edge_bwd_tc_supported(const EdgeBwdArgs &a);
 int launch_edge_bwd_tc(const EdgeBwdArgs &a, int grid, cudaStream_t st);
 
+// Grouped weight gradients: up to WG_MAX_JOBS products d_w += A^T B (+ column
+// sums of A into d_b) over the same rows, one launch + one reduce (egnn_bwd.cu:
+// FFMA; wgrad_tc.cu: tcgen05).  Per-CTA partial block: [64][128] products, then
+// 64 column sums.
+constexpr int WG_MAX_JOBS = 8;
+constexpr int WG_PART = 64 * 128 + 64;
+struct WgradJob {
+    const float *A; const float *B;   // B == nullptr: column sums of A only
+    float *d_w; float *d_b;
+    int lda, ko, ldb, ki, ld_dw;
+};
+struct WgradGroup {
+    WgradJob job[WG_MAX_JOBS];
+    int n_jobs, rows, chunks, rows_per;   // chunks CTAs per job, rows_per rows each
+};
+// Fills G.chunks / G.rows_per (multiples of 128 rows, at most max_ctas CTAs) and
+// launches the tcgen05 kernel; every job needs ko, ki <= 64.
+int launch_wgrad_group_tc(WgradGroup &G, int rows, int max_ctas, float *partial,
+                          cudaStream_t st);
+
 }  // namespace pvs
