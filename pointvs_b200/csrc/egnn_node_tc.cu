@@ -24,6 +24,22 @@ __device__ __forceinline__ void nt_group_sync(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(NT_GROUP_THREADS) : "memory");
 }
 
+// Row partition of the node kernels: every 4-warp group of the grid gets an
+// equal share of the rows and walks it in equal tiles of at most 128 rows.
+// (Fixed 128-row tiles dealt round-robin left 1000 tiles on 740 groups for the
+// 128 x 1000-atom batch: a quarter of the groups did two tiles, the rest one,
+// and the kernel took two tile times.)
+struct RowShare { int begin, end, tile_rows; };
+__device__ __forceinline__ RowShare row_share(int n_rows, int group_id, int n_groups) {
+    const int per = (n_rows + n_groups - 1) / n_groups;
+    RowShare r;
+    r.begin = min(n_rows, group_id * per);
+    r.end = min(n_rows, r.begin + per);
+    const int tiles = max(1, (per + NT_ROWS - 1) / NT_ROWS);
+    r.tile_rows = (per + tiles - 1) / tiles;
+    return r;
+}
+
 // rows [row0, row0 + 128) x 64 columns of `src` (pitch ld, `cols` valid columns,
 // `n_rows` valid rows overall) -> bf16 hi/lo swizzled A tiles.  8 lanes per row.
 template <bool X3>
@@ -113,11 +129,11 @@ node_pre_tc_kernel(const NodePreArgs a) {
     const uint32_t tmem_grp = tmem_base + (uint32_t)g * 128u;
     const uint32_t tmem_lane = tmem_grp + ((uint32_t)(warp * 32) << 16);
     uint32_t phase = 0;
-    const int n_tiles = (a.n_nodes + NT_ROWS - 1) / NT_ROWS;
-    for (int t = blockIdx.x * NP_GROUPS + g; t < n_tiles; t += gridDim.x * NP_GROUPS) {
-        const int row0 = t * NT_ROWS;
+    const RowShare rs = row_share(a.n_nodes, blockIdx.x * NP_GROUPS + g, gridDim.x * NP_GROUPS);
+    for (int row0 = rs.begin; row0 < rs.end; row0 += rs.tile_rows) {
+        const int row_end = min(rs.end, row0 + rs.tile_rows);
         nt_group_sync(g);   // staging of the previous tile fully stored
-        load_block<X3>(A_hi, A_lo, a.h, k, k, row0, a.n_nodes, tid);
+        load_block<X3>(A_hi, A_lo, a.h, k, k, row0, row_end, tid);
         fence_proxy_async();
         tc_fence_before();
         nt_group_sync(g);
@@ -160,7 +176,7 @@ node_pre_tc_kernel(const NodePreArgs a) {
 #pragma unroll 4
                 for (int p = 0; p < NT_ROWS / 8; ++p) {
                     const int row = p * 8 + slot;
-                    if (row0 + row >= a.n_nodes) continue;
+                    if (row0 + row >= row_end) continue;
                     const float *sp = reinterpret_cast<const float *>(row < 64 ? A_hi : A_lo);
                     const float4 v = *stage_ptr(const_cast<float *>(sp), row & 63, c4);
                     *reinterpret_cast<float4 *>(dst + (size_t)(row0 + row) * 64 + 4 * c4) = v;
@@ -274,13 +290,13 @@ node_tc_kernel(const NodeTcArgs a) {
     const bool f_res = a.flags & PVS_F_RESIDUAL;
     const float natt_b = (f_natt && a.natt_b) ? a.natt_b[0] : 0.0f;
     const float gate = a.node_gate ? a.node_gate[0] : 1.0f;
-    const int n_tiles = (a.n_nodes + NT_ROWS - 1) / NT_ROWS;
-    for (int t = blockIdx.x * NM_GROUPS + g; t < n_tiles; t += gridDim.x * NM_GROUPS) {
-        const int row0 = t * NT_ROWS;
+    const RowShare rs = row_share(a.n_nodes, blockIdx.x * NM_GROUPS + g, gridDim.x * NM_GROUPS);
+    for (int row0 = rs.begin; row0 < rs.end; row0 += rs.tile_rows) {
+        const int row_end = min(rs.end, row0 + rs.tile_rows);
         nt_group_sync(g);
         if (a.phase != 2) {
             // ---- v = Wn1 [h ; M]: two K blocks through the same A tiles ----
-            load_block<X3>(A_hi, A_lo, a.h_in, k, k, row0, a.n_nodes, tid);
+            load_block<X3>(A_hi, A_lo, a.h_in, k, k, row0, row_end, tid);
             fence_proxy_async();
             tc_fence_before();
             nt_group_sync(g);
@@ -291,7 +307,7 @@ node_tc_kernel(const NodeTcArgs a) {
             }
             mbar_wait(&S.mbar[g], phase);
             phase ^= 1;
-            load_block<X3>(A_hi, A_lo, a.M, 64, 64, row0, a.n_nodes, tid);
+            load_block<X3>(A_hi, A_lo, a.M, 64, 64, row0, row_end, tid);
             fence_proxy_async();
             tc_fence_before();
             nt_group_sync(g);
@@ -327,7 +343,7 @@ node_tc_kernel(const NodeTcArgs a) {
 #pragma unroll 4
             for (int p = 0; p < NT_ROWS / 8; ++p) {
                 const int row = p * 8 + slot;
-                if (row0 + row >= a.n_nodes) continue;
+                if (row0 + row >= row_end) continue;
                 const float *sp = reinterpret_cast<const float *>(row < 64 ? A_hi : A_lo);
                 *reinterpret_cast<float4 *>(a.V + (size_t)(row0 + row) * 64 + 4 * c4) =
                     *stage_ptr(const_cast<float *>(sp), row & 63, c4);
@@ -335,7 +351,7 @@ node_tc_kernel(const NodeTcArgs a) {
             continue;
         }
         if (a.phase == 2) {
-            load_block_gn<X3>(A_hi, A_lo, a.V, S.ga, S.gb, row0, a.n_nodes, tid);
+            load_block_gn<X3>(A_hi, A_lo, a.V, S.ga, S.gb, row0, row_end, tid);
         } else {
             // ---- u = silu(v + b1) -> A tiles ----
             {
@@ -378,7 +394,7 @@ node_tc_kernel(const NodeTcArgs a) {
         // a row of h is read as full 256-byte lines instead of per-thread rows.
         {
             const int r = tid;
-            const bool ok = row0 + r < a.n_nodes;
+            const bool ok = row0 + r < row_end;
             // A tiles are free (GEMM 2 has completed): 64 rows of fp32 staging in
             // each 16 KB tile
             float *st = reinterpret_cast<float *>(r < 64 ? A_hi : A_lo);
@@ -417,7 +433,7 @@ node_tc_kernel(const NodeTcArgs a) {
 #pragma unroll 4
             for (int p = 0; p < NT_ROWS / 8; ++p) {
                 const int row = p * 8 + slot;
-                if (row0 + row >= a.n_nodes) continue;
+                if (row0 + row >= row_end) continue;
                 const float *sp = reinterpret_cast<const float *>(row < 64 ? A_hi : A_lo);
                 float4 v = *stage_ptr(const_cast<float *>(sp), row & 63, c4);
                 const float s = S.srow[g][row];
@@ -462,9 +478,10 @@ int launch_node_pre_tc(const float *h, const float *edge_w1, const float *edge_b
                        cudaStream_t st) {
     NodePreArgs a{h, edge_w1, edge_b1, P, Q, n_nodes, k, in_e, perm};
     const size_t smem = sizeof(NpSmem);
-    const int tiles = (n_nodes + NT_ROWS - 1) / NT_ROWS;
+    // one persistent CTA per SM; fewer only when a group's share would fall
+    // under 16 rows
     int grid = num_sms();
-    const int need = (tiles + NP_GROUPS - 1) / NP_GROUPS;
+    const int need = (n_nodes + 16 * NP_GROUPS - 1) / (16 * NP_GROUPS);
     if (need < grid) grid = need;
     if (grid < 1) grid = 1;
     int rc;
@@ -492,9 +509,10 @@ int launch_node_tc(const float *h_in, const float *M, float *h_out, float *natt_
     a.node_gate = p->node_gate;
     a.n_nodes = n_nodes; a.k = k; a.flags = flags; a.att_act = att_act;
     const size_t smem = sizeof(NmSmem);
-    const int tiles = (n_nodes + NT_ROWS - 1) / NT_ROWS;
+    // one persistent CTA per SM; fewer only when a group's share would fall
+    // under 16 rows
     int grid = num_sms();
-    const int need = (tiles + NM_GROUPS - 1) / NM_GROUPS;
+    const int need = (n_nodes + 16 * NM_GROUPS - 1) / (16 * NM_GROUPS);
     if (need < grid) grid = need;
     if (grid < 1) grid = 1;
     int rc;
