@@ -69,6 +69,19 @@ def run(math, steps):
     res = {PHASES[i]: round(cyc[i] / tot, 4) for i in range(8)}
     res['total_group_cycles_per_step'] = tot // steps
     print(json.dumps(res, indent=1))
+    if hasattr(lib, 'pvs_debug_node_phase_cycles'):
+        lib.pvs_debug_node_phase_cycles.argtypes = [C.c_void_p, C.c_int]
+        lib.pvs_debug_node_phase_cycles(C.cast(out, C.c_void_p), 0)
+        names = ['0 prologue (weights, TMEM)', '1 h block -> A', '2 GEMM 1a wait',
+                 '3 M block -> A', '4 GEMM 1b wait', '5 epilogue 1 (SiLU -> A)',
+                 '6 GEMM 2 wait', '7 epilogue 2 (-> staging)', '8 store pass']
+        cyc = [int(out[i]) for i in range(9)]
+        tot = sum(cyc)
+        res = {names[i]: round(cyc[i] / tot, 4) for i in range(9)}
+        # cumulative over (warm-up + steps) passes; shares are what matters
+        res['group_cycles_per_launch'] = tot // ((steps + 2) * 8 * 148 * 5)
+        print('node_tc_kernel (all passes since load):')
+        print(json.dumps(res, indent=1))
 
 
 BWD_PHASES = ['0 tile setup (row_ptr window)', '1 S0 geometry', '2 S1 gather + SiLU -> S1/SG',
