@@ -760,7 +760,7 @@ def train_block(args, torch, dist, dev, rank, world, barrier, max_over_ranks,
         'batch_per_gpu': b, 'n_gpus': world,
         'forward_math': args.math,
         'backward_math': 'fp32 FFMA' if args.math == 'fp32' else
-                         'edge stage on tcgen05 (bf16x3), node stage / weight grads fp32 FFMA',
+                         'edge stage and all weight gradients on tcgen05 (bf16x3), node-stage data gradients fp32 FFMA',
         'parallelism': f'data-parallel x{world}: per-layer gradient-arena '
                        'all-reduce (NCCL, AVG) overlapped with backward'
                        if world > 1 else 'single GPU',

@@ -179,7 +179,7 @@ int pvs_version(void);
 uint32_t pvs_capabilities(void);
 const char *pvs_status_string(int status);
 int pvs_last_cuda_error(void);
-/* kernels launched by this library on the calling thread since load */
+/* kernels launched by this library (all host threads) since load */
 int64_t pvs_launch_count(void);
 
 /* ---- K1: radius graph --------------------------------------------------

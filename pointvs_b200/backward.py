@@ -42,6 +42,54 @@ def _zeros_like_or_none(p):
     return None if p is None else torch.zeros_like(p, dtype=torch.float32)
 
 
+def _unused_fields(layer, no_dx, no_m_prev):
+    """Parameters that cannot influence the loss get no gradient at all (None),
+    as under the reference's autograd: an optimiser with weight decay skips
+    them instead of decaying them.  That is the coordinate MLP of a layer
+    whose output coordinates nobody consumes (the last layer), or which does
+    not update coordinates; and the edge gate of a layer without incoming
+    messages."""
+    unused = ()
+    if no_dx or not layer.use_coords:
+        unused += ('coord_w1', 'coord_b1', 'coord_w2')
+    if no_m_prev:
+        unused += ('edge_gate',)
+    return unused
+
+
+def _bwd_workspace(cfg, n, e, dev):
+    """Scratch of pvs_egnn_layer_bwd: never escapes the call and every use is
+    ordered on the stream, so one grow-only buffer serves all layers."""
+    nbytes = int(lib().pvs_egnn_layer_bwd_workspace_bytes(n, e, C.byref(cfg)))
+    return _cabi.scratch('layer_bwd', nbytes, dev)
+
+
+class _LayerBwdPlan:
+    """What egnn_layer_backward needs again on every step while the layer's
+    parameters and the gradient arena stay where they are: the pointer block of
+    the gradient slots, their keys and span."""
+
+    def __init__(self, arena, pstruct, gstruct, params, in_arena, grads):
+        self.arena, self.pstruct, self.gstruct = arena, pstruct, gstruct
+        self._keep = grads                      # the views the pointers refer to
+        self.keys = frozenset(p.data_ptr() for p in in_arena)
+        self.span = arena.span(in_arena)
+        self.nones = (None,) * len(params)
+        self._by_field = {name: p.data_ptr()
+                          for name, p in zip(_cabi.PARAM_FIELDS, params)
+                          if p is not None}
+        self._granted = {}
+
+    def granted(self, unused):
+        keys = self._granted.get(unused)
+        if keys is None:
+            drop = {self._by_field[name] for name in unused
+                    if name in self._by_field}
+            keys = frozenset(self.keys - drop)
+            self._granted[unused] = keys
+        return keys
+
+
 def egnn_layer_backward(ctx, d_h, d_x, d_m):
     layer, csr = ctx.layer, ctx.csr
     h, x, m_prev, *params = ctx.saved_tensors
@@ -57,10 +105,31 @@ def egnn_layer_backward(ctx, d_h, d_x, d_m):
     d_m = None if d_m is None else d_m.contiguous().float()
     csc_ptr, csc_eid = csr.csc()
 
-    pstruct = _cabi.LayerParams(*[
-        ptr(None if p is None else p.detach().contiguous()) for p in params])
-    by_name = dict(zip(_cabi.PARAM_FIELDS, params))
+    pstruct = layer.c_params(params)
     arena = ARENA
+    unused = _unused_fields(layer, no_dx, m_prev is None)
+    plan = layer.__dict__.get('_bwd_plan')
+    if arena is not None and plan is not None and plan.arena is arena \
+            and plan.pstruct is pstruct and arena.hand_out_all(plan.keys):
+        # steady state of a training run: every gradient of the layer has an
+        # arena slot, and the pointer block built on an earlier step is reused
+        d_h_in = torch.empty_like(h)
+        d_x_in = torch.empty_like(x)
+        d_m_prev = torch.zeros_like(m_prev) if m_prev is not None else None
+        ws = _bwd_workspace(cfg, n, e, dev)
+        g = csr.c_struct()
+        with torch.cuda.device(dev):
+            check(lib().pvs_egnn_layer_bwd(
+                C.byref(g), ptr(csc_ptr), ptr(csc_eid), C.byref(cfg),
+                C.byref(pstruct), ptr(h), ptr(x), ptr(m_prev), ptr(d_h), ptr(d_x),
+                ptr(d_m), ptr(d_h_in), ptr(d_x_in), ptr(d_m_prev),
+                C.byref(plan.gstruct), ptr(ws), C.c_int64(ws.numel()), stream()),
+                'pvs_egnn_layer_bwd')
+        if arena.reduce_in_backward:
+            arena.reduce_async(*plan.span)
+        arena.grant_all(plan.granted(unused))
+        return (None, None, None, None, d_h_in, d_x_in, d_m_prev, *plan.nones)
+    by_name = dict(zip(_cabi.PARAM_FIELDS, params))
     grads, in_arena = {}, []
     if arena is not None:
         # the model's gradient arena: slots are already zero
@@ -85,8 +154,7 @@ def egnn_layer_backward(ctx, d_h, d_x, d_m):
     d_h_in = torch.empty_like(h)
     d_x_in = torch.empty_like(x)
     d_m_prev = torch.zeros_like(m_prev) if m_prev is not None else None
-    nbytes = int(lib().pvs_egnn_layer_bwd_workspace_bytes(n, e, C.byref(cfg)))
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ws = _bwd_workspace(cfg, n, e, dev)
     g = csr.c_struct()
     with torch.cuda.device(dev):
         check(lib().pvs_egnn_layer_bwd(
@@ -99,6 +167,12 @@ def egnn_layer_backward(ctx, d_h, d_x, d_m):
         # data-parallel: this layer's slice of the arena is complete -- average
         # it over the ranks while the next layer's backward runs
         arena.reduce_async(*arena.span(in_arena))
+    if arena is not None and not rest \
+            and layer.__dict__.get('_c_params', (None, None))[1] is pstruct:
+        # every gradient of the layer sits in the arena: remember the pointer
+        # block for the following steps
+        layer.__dict__['_bwd_plan'] = _LayerBwdPlan(arena, pstruct, gstruct, params,
+                                                    in_arena, grads)
     # inputs of _EGNNLayerFn.forward: layer, csr, want_m, want_side, h, x,
     # m_prev, *params
     # Parameters that cannot influence the loss get no gradient at all (None),
@@ -106,11 +180,6 @@ def egnn_layer_backward(ctx, d_h, d_x, d_m):
     # them instead of decaying them.  That is the coordinate MLP of a layer
     # whose output coordinates nobody consumes (the last layer), or which does
     # not update coordinates.
-    unused = set()
-    if no_dx or not layer.use_coords:
-        unused.update(('coord_w1', 'coord_b1', 'coord_w2'))
-    if m_prev is None:          # first layer: no incoming messages to gate
-        unused.add('edge_gate')
     arena_ptrs = {p.data_ptr() for p in in_arena}
     param_grads = []
     for name, p in zip(_cabi.PARAM_FIELDS, params):

@@ -208,7 +208,13 @@ class PointNeuralNetworkBase(nn.Module):
                 loss.backward()
             arena.attach_grads()
         self.sync_gradients()
-        torch.nn.utils.clip_grad_value_(self.parameters(), 1.0)
+        if arena is None:
+            torch.nn.utils.clip_grad_value_(self.parameters(), 1.0)
+        else:
+            # clip_grad_value_(parameters, 1.0) as one clamp over the arena
+            rest = arena.clamp_(1.0)
+            if rest:
+                torch.nn.utils.clip_grad_value_(rest, 1.0)
         self.optimiser.step()
         if not sync:
             return loss.detach()

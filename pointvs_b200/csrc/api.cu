@@ -6,7 +6,7 @@
 
 namespace pvs {
 thread_local int g_last_cuda_error = 0;
-thread_local int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
 
 int num_sms() {
     static thread_local int cached_dev = -1, cached = 0;
@@ -71,6 +71,6 @@ const char *pvs_status_string(int status) {
 
 int pvs_last_cuda_error(void) { return pvs::g_last_cuda_error; }
 
-int64_t pvs_launch_count(void) { return pvs::g_launches; }
+int64_t pvs_launch_count(void) { return pvs::g_launches.load(std::memory_order_relaxed); }
 
 }  // extern "C"

@@ -3,12 +3,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "pvs_b200.h"
 
 namespace pvs {
 
 extern thread_local int g_last_cuda_error;
-extern thread_local int64_t g_launches;
+// process-wide: the backward runs on autograd's worker thread
+extern std::atomic<int64_t> g_launches;
 
 // call after a group of `n` kernel launches
 inline int check_launch(int n = 1) {

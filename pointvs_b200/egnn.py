@@ -91,9 +91,7 @@ class _EGNNLayerFn(torch.autograd.Function):
         h = h.contiguous()
         x = x.contiguous()
         m_prev = None if m_prev is None else m_prev.contiguous()
-        pstruct = _cabi.LayerParams(*[
-            ptr(None if p is None else p.detach().contiguous())
-            for p in params])
+        pstruct = layer.c_params(params)
         h_out = torch.empty_like(h)
         x_out = torch.empty_like(x) if layer.use_coords else None
         m_out = torch.empty((e, k), dtype=torch.float32, device=dev) \
@@ -289,6 +287,23 @@ class EGNNLayer(nn.Module):
         return _cabi.LayerConfig(self.hidden_nf, self.edges_in_d,
                                  self.c_flags(), _cabi.ACT[act],
                                  _cabi.MATH[self.math], 0, None, None, None)
+
+    def c_params(self, params):
+        """struct pvs_layer_params of `params` (PARAM_FIELDS order), cached on
+        the parameters' storage addresses: twenty pointer fields per call are a
+        measurable part of a training step's host time."""
+        key = tuple(0 if p is None else p.data_ptr() for p in params)
+        cached = self.__dict__.get('_c_params')
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        if any(p is not None and not p.is_contiguous() for p in params):
+            keep = [None if p is None else p.detach().contiguous() for p in params]
+            st = _cabi.LayerParams(*[ptr(p) for p in keep])
+            st._keep = keep
+            return st
+        st = _cabi.LayerParams(*[C.c_void_p(a) if a else None for a in key])
+        self.__dict__['_c_params'] = (key, st)
+        return st
 
     def param_list(self):
         """Parameters in _cabi.PARAM_FIELDS order (None where absent)."""

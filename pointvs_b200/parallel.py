@@ -96,12 +96,37 @@ class GradArena:
                       for p, (o, n, shape) in ((p, self.slots[p.data_ptr()])
                                                for p in self.params)}
         self._granted, self._assigned = set(), set()
+        self._ptrs = [p.data_ptr() for p in self.params]
+        self._all_keys = set(self._ptrs)
 
-    def matches(self, module):
-        ps = [p for p in module.parameters() if p.requires_grad]
-        return len(ps) == len(self.params) and all(
-            p.data_ptr() in self.slots and p.device == self.flat.device
-            for p in ps)
+    def matches(self, module, full=False):
+        """Is this still the arena of `module`'s parameters?  The per-step
+        check only looks at the parameters the arena already holds (storage
+        moved by `.to()`, or frozen since): walking `module.parameters()` costs
+        more host time than the rest of `begin_step`.  A parameter that was
+        frozen when the arena was built and is trainable now simply gets its
+        gradient through plain autograd.  full=True walks the module."""
+        if full:
+            ps = [p for p in module.parameters() if p.requires_grad]
+            return len(ps) == len(self.params) and all(
+                p.data_ptr() in self.slots and p.device == self.flat.device
+                for p in ps)
+        ptrs = self._ptrs
+        for i, p in enumerate(self.params):
+            if p.data_ptr() != ptrs[i] or not p.requires_grad:
+                return False
+        return True
+
+    def clamp_(self, clip_value):
+        """`clip_grad_value_` over every gradient that lives in the arena: one
+        kernel over the flat buffer (slots without a gradient this step are
+        zero).  Returns the parameters whose gradient is NOT an arena view, for
+        the caller to clip the usual way."""
+        self.flat.clamp_(-clip_value, clip_value)
+        if self._assigned == self._all_keys:
+            return []
+        return [p for p in self.params
+                if p.grad is not None and p.data_ptr() not in self._assigned]
 
     def begin_step(self):
         """Zero every slot (one kernel) and forget the previous step.  Gradients
@@ -132,6 +157,18 @@ class GradArena:
             return None
         self._handed.add(key)
         return self.views[key]
+
+    def hand_out_all(self, keys):
+        """Fast path of a backward pass with a cached plan: hand out the slots
+        `keys` (a frozenset of data_ptrs) in one go.  False (and nothing
+        changed) if any of them has already been handed out in this step."""
+        if not self._handed.isdisjoint(keys):
+            return False
+        self._handed |= keys
+        return True
+
+    def grant_all(self, keys):
+        self._granted |= keys
 
     def grant(self, param):
         """The backward pass that was handed `param`'s slot reports that the
