@@ -397,6 +397,14 @@ int pvs_egnn_model_fwd(const pvs_graph *graph, const pvs_model_desc *model,
  * too. */
 int pvs_csr_transpose(const pvs_graph *graph, int32_t *csc_ptr,
                       int32_t *csc_eid, void *scratch, void *stream);
+/* Same grouping for a SYMMETRIC graph (every radius graph of K1: i-j is an
+ * edge iff j-i is): the edges arriving at node j are the reverses of row j,
+ * so csc_ptr == row_ptr and csc_eid[p] = position of j in the row of col[p]
+ * (of its r-th occurrence for the r-th occurrence of col[p] in row j: a pair
+ * within both cut-offs is listed twice); one pass, no counting sort.  *asymmetric (device, may be NULL) is set to 1
+ * if some edge has no reverse (the entry then refers to the edge itself). */
+int pvs_csr_transpose_symmetric(const pvs_graph *graph, int32_t *csc_eid,
+                                int32_t *asymmetric, void *stream);
 int64_t pvs_egnn_layer_bwd_workspace_bytes(int32_t n_nodes, int32_t n_edges,
                                            const pvs_layer_config *cfg);
 int pvs_egnn_layer_bwd(const pvs_graph *graph, const int32_t *csc_ptr,

@@ -438,13 +438,19 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
     const float natt_b = (f_natt && a.natt_b) ? a.natt_b[0] : 0.0f;
     const float gate = a.node_gate ? a.node_gate[0] : 1.0f;
     const float G = fmaxf(gate, 0.0f);
-    const int n_tiles = (a.n_nodes + 63) / 64;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int r0 = t * 64;
+    // equal share of the rows per CTA, walked in equal tiles of <= 64 rows (250
+    // fixed tiles on 148 CTAs was two waves, the second 70 % empty)
+    const int per_cta = (a.n_nodes + gridDim.x - 1) / gridDim.x;
+    const int share_lo = min(a.n_nodes, (int)blockIdx.x * per_cta);
+    const int share_hi = min(a.n_nodes, share_lo + per_cta);
+    const int tiles_here = max(1, (per_cta + 63) / 64);
+    const int tile_rows = (per_cta + tiles_here - 1) / tiles_here;
+    for (int r0 = share_lo; r0 < share_hi; r0 += tile_rows) {
+        const int row_end = min(share_hi, r0 + tile_rows);
         __syncthreads();
         for (int idx = tid; idx < 64 * KB; idx += BT) {
             int r = idx >> 6, c = idx & 63;
-            bool ok = r0 + r < a.n_nodes;
+            bool ok = r0 + r < row_end;
             IN[r * LDIN + c] = (ok && c < k) ? a.h_in[(size_t)(r0 + r) * k + c] : 0.0f;
             IN[r * LDIN + KB + c] = ok ? a.M[(size_t)(r0 + r) * KB + c] : 0.0f;
         }
@@ -455,7 +461,7 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
             for (int i = 0; i < 4; ++i) {
                 const int r = rg + 16 * i;
                 float4 dy = make_float4(0.f, 0.f, 0.f, 0.f), v4 = dy;
-                const bool ok = r0 + r < a.n_nodes;
+                const bool ok = r0 + r < row_end;
                 if (ok) {
                     dy = *reinterpret_cast<const float4 *>(&a.DY[(size_t)(r0 + r) * KB + 4 * cg]);
                     v4 = *reinterpret_cast<const float4 *>(&a.V[(size_t)(r0 + r) * KB + 4 * cg]);
@@ -486,7 +492,7 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
                 const int r = rg + 16 * i;
                 float u[4];
                 float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (phase == 1 && r0 + r < a.n_nodes)
+                if (phase == 1 && r0 + r < row_end)
                     v4 = *reinterpret_cast<const float4 *>(&a.V[(size_t)(r0 + r) * KB + 4 * cg]);
                 const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
@@ -499,7 +505,7 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
                 }
                 *reinterpret_cast<float4 *>(&Us[r * LDT + 4 * cg]) =
                     make_float4(u[0], u[1], u[2], u[3]);
-                if (r0 + r < a.n_nodes)
+                if (r0 + r < row_end)
                     *reinterpret_cast<float4 *>(&a.U[(size_t)(r0 + r) * KB + 4 * cg]) =
                         make_float4(u[0], u[1], u[2], u[3]);
             }
@@ -512,7 +518,7 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int r = rg + 16 * i;
-                const bool ok = r0 + r < a.n_nodes;
+                const bool ok = r0 + r < row_end;
                 float o[4], gh[4], hv[4];
                 float zdot = 0.0f;
 #pragma unroll
@@ -582,7 +588,7 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
                 if (phase == 1) {
                     // dv here is dy = dL/d(GraphNorm output): hand it, and
                     // dy * c_hat, to the batch-wide reductions
-                    if (r0 + r < a.n_nodes) {
+                    if (r0 + r < row_end) {
                         const float4 v4 = *reinterpret_cast<const float4 *>(
                             &a.V[(size_t)(r0 + r) * KB + 4 * cg]);
                         const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
@@ -601,7 +607,7 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
                 }
                 *reinterpret_cast<float4 *>(&Gs[r * LDT + 4 * cg]) =
                     make_float4(dv[0], dv[1], dv[2], dv[3]);
-                if (r0 + r < a.n_nodes)
+                if (r0 + r < row_end)
                     *reinterpret_cast<float4 *>(&a.DV[(size_t)(r0 + r) * KB + 4 * cg]) =
                         make_float4(dv[0], dv[1], dv[2], dv[3]);
             }
@@ -616,7 +622,7 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int r = r0 + rg + 16 * i;
-                if (r >= a.n_nodes) continue;
+                if (r >= row_end) continue;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int n = 4 * cg + c;
@@ -1359,7 +1365,7 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
                        2 * 64 * LDT + 10 * 64) * sizeof(float);
         rc = ensure_smem(egnn_node_bwd_kernel, smem);
         if (rc) return rc;
-        const int grid = persistent_grid((n + 63) / 64, 1);
+        const int grid = persistent_grid((n + 15) / 16, 1);
         if (!graphnorm) {
             na.phase = 0;
             egnn_node_bwd_kernel<<<grid, BT, smem, st>>>(na);

@@ -808,6 +808,38 @@ __global__ void key_place_kernel(const KeyT *__restrict__ keys, int64_t n_edges,
     perm[ptr[k] + p] = (int32_t)e;
 }
 
+// symmetric graph: the edge arriving at j from i = col[p] (p in row j) is the
+// entry of row i whose column is j.  One warp per node j, a lane per entry of
+// its row; rows are short (~15), so the search is a plain scan.
+__global__ void csc_symmetric_kernel(const int32_t *__restrict__ row_ptr,
+                                     const int32_t *__restrict__ col, int n_nodes,
+                                     int32_t *__restrict__ csc_eid,
+                                     int32_t *__restrict__ asymmetric) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= n_nodes) return;
+    const int lane = threadIdx.x & 31;
+    const int lo = row_ptr[j], hi = row_ptr[j + 1];
+    for (int p = lo + lane; p < hi; p += 32) {
+        const int i = col[p];
+        // a pair can be listed twice (once as an inter-, once as an intra-
+        // molecular edge when both cut-offs admit it): the r-th i in row j
+        // pairs with the r-th j in row i
+        int rank = 0;
+        for (int q = lo; q < p; ++q) rank += col[q] == i;
+        int found = -1;
+        if (i >= 0 && i < n_nodes) {
+            const int qlo = row_ptr[i], qhi = row_ptr[i + 1];
+            for (int q = qlo; q < qhi; ++q)
+                if (col[q] == j && rank-- == 0) { found = q; break; }
+        }
+        if (found < 0) {
+            found = p;
+            if (asymmetric) *asymmetric = 1;
+        }
+        csc_eid[p] = found;
+    }
+}
+
 // restore the caller's order inside every group (=> stable sort by key)
 __global__ void segment_sort_kernel(const int32_t *__restrict__ ptr, int n_nodes,
                                     int32_t *__restrict__ perm) {
@@ -1167,6 +1199,18 @@ int pvs_csr_transpose(const pvs_graph *g, int32_t *csc_ptr, int32_t *csc_eid,
         g_launches += 2;
     }
     return check_launch(0);
+}
+
+int pvs_csr_transpose_symmetric(const pvs_graph *g, int32_t *csc_eid, int32_t *asymmetric,
+                                void *stream) {
+    if (!g || g->n_nodes < 0 || g->n_edges < 0) return PVS_ERR_INVALID_ARG;
+    if (g->n_nodes == 0 || g->n_edges == 0) return PVS_OK;
+    if (!g->row_ptr || !g->col || !csc_eid) return PVS_ERR_INVALID_ARG;
+    const int warps_per_block = 8;
+    csc_symmetric_kernel<<<(g->n_nodes + warps_per_block - 1) / warps_per_block,
+                           32 * warps_per_block, 0, (cudaStream_t)stream>>>(
+        g->row_ptr, g->col, g->n_nodes, csc_eid, asymmetric);
+    return check_launch();
 }
 
 int pvs_batch_to_ptr(const int64_t *batch, int32_t n_nodes, int32_t n_graphs,

@@ -42,6 +42,7 @@ class CSRGraph:
         self._inv_perm = None
         self._csc = None
         self.exact_edge_count = True
+        self.symmetric = False    # set by K1: i-j is an edge iff j-i is
         self.n_edges_dev = None
         self._overflow = None
         # work-tile partitions, built on first use: node-aligned tiles for the
@@ -146,6 +147,21 @@ class CSRGraph:
 
     def csc(self):
         """(csc_ptr [N+1], csc_eid [E]): CSR edge ids grouped by neighbour."""
+        if self._csc is None and self.symmetric:
+            # radius graphs are symmetric: csc_ptr IS row_ptr, and the edge ids
+            # come from one search pass (no counting sort, 85 -> 10 us).  An
+            # edge without a reverse raises the graph's overflow flag.
+            csc_eid = torch.empty(max(1, self.n_edges), dtype=torch.int32,
+                                  device=self.device)
+            if self._overflow is None:
+                self._overflow = torch.zeros(1, dtype=torch.int32,
+                                             device=self.device)
+            g = self.c_struct(node_tiles=False, packed_tiles=False)
+            with torch.cuda.device(self.device):
+                check(lib().pvs_csr_transpose_symmetric(
+                    C.byref(g), ptr(csc_eid), ptr(self._overflow), stream()),
+                    'pvs_csr_transpose_symmetric')
+            self._csc = (self.row_ptr, csc_eid)
         if self._csc is None:
             # no _exact(): the transpose reads the true edge count on the device
             # (row_ptr[n]), so a capacity-bounded graph stays sync-free
@@ -298,6 +314,7 @@ def radius_graph_batch(coords, bp, complex_ptr, inter_radius=4.0,
     g.complex_ptr_host = cptr_host
     g.n_edges_dev = row_ptr[-1:]
     g.exact_edge_count = edge_capacity is None
+    g.symmetric = True
     g._overflow = overflow
     return g
 

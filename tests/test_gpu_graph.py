@@ -278,3 +278,35 @@ def test_mask_reuse_and_recompute_fill_agree():
     assert a.n_edges == b.n_edges
     assert torch.equal(a.row_ptr, b.row_ptr)
     assert torch.equal(a.col, b.col) and torch.equal(a.attr, b.attr)
+
+
+def test_symmetric_transpose_matches_counting_sort():
+    """K1 graphs are symmetric: pvs_csr_transpose_symmetric (csc_ptr = row_ptr,
+    reverse edge found by a scan) groups exactly the edges the general
+    counting-sort transpose groups, for exact and capacity-bounded graphs."""
+    import torch
+    from tests import gpu_helpers as gh
+    for cap in (None, 'auto'):
+        csr = gh.synthetic_graph(321, 5, 700, 25, ragged=True,
+                                 edge_capacity=cap).pvs_csr
+        assert csr.symmetric
+        ptr_s, eid_s = csr.csc()
+        csr._csc, csr.symmetric = None, False
+        ptr_g, eid_g = csr.csc()
+        e = int(csr.true_edge_count())
+        assert torch.equal(ptr_s.cpu(), ptr_g.cpu())
+        assert int(ptr_g[-1]) == e
+        grp = torch.repeat_interleave(
+            torch.arange(csr.n_nodes, device='cuda'),
+            (ptr_g[1:] - ptr_g[:-1]).long())
+        key = grp * (e + 1) + eid_s[:e].long()
+        assert torch.equal(eid_s[:e][torch.argsort(key)].cpu(), eid_g[:e].cpu())
+        # every edge id appears once, and it is the reverse edge
+        assert torch.equal(torch.sort(eid_s[:e]).values.cpu(),
+                           torch.arange(e, dtype=torch.int32))
+        col = csr.col[:e].long()
+        rows = torch.repeat_interleave(
+            torch.arange(csr.n_nodes, device='cuda'),
+            (csr.row_ptr[1:] - csr.row_ptr[:-1]).long())
+        assert torch.equal(col[eid_s[:e].long()], rows)
+        assert int(csr._overflow.item()) == 0
