@@ -275,6 +275,133 @@ def egnn_stack_backward(ctx, d_h, d_x):
     return (None, None, d_h_in, d_x_in, *out)
 
 
+class _StackGradPlan:
+    """Gradient pointer block of a stacked backward for one gradient arena."""
+
+    def __init__(self, plan, arena):
+        layers, params = plan.layers, plan.params
+        L, per = len(layers), len(_cabi.PARAM_FIELDS)
+        self.ok = all(p is None or not p.requires_grad or
+                      p.data_ptr() in arena.slots for p in params)
+        if not self.ok:
+            return
+        live = [p for p in params if p is not None and p.requires_grad]
+        self.keys = frozenset(p.data_ptr() for p in live)
+        self.ok = len(self.keys) == len(live)      # a parameter shared by layers
+        if not self.ok:
+            return
+        self.gstructs = (_cabi.LayerGrads * L)()
+        for i in range(L):
+            ps = params[i * per:(i + 1) * per]
+            self.gstructs[i] = _cabi.LayerGrads(*[
+                ptr(arena.views[p.data_ptr()])
+                if (p is not None and p.requires_grad) else None for p in ps])
+        self.span = arena.span(live)
+        self._granted = {}
+        self._plan = plan
+
+    def granted(self, no_dx):
+        keys = self._granted.get(no_dx)
+        if keys is None:
+            keys = frozenset(self.keys - _stack_unused_keys(self._plan, no_dx))
+            self._granted[no_dx] = keys
+        return keys
+
+
+def _stack_unused_keys(plan, no_dx):
+    """data_ptrs of the parameters that cannot influence the loss in a stacked
+    pass (same rules as egnn_layer_backward): every edge gate (no incoming
+    messages), the coordinate MLP of a layer that does not update coordinates
+    or -- the last layer -- whose coordinates nobody consumes."""
+    per = len(_cabi.PARAM_FIELDS)
+    L = len(plan.layers)
+    drop = set()
+    for i, layer in enumerate(plan.layers):
+        unused = ['edge_gate']
+        if not layer.use_coords or (no_dx and i == L - 1):
+            unused += ['coord_w1', 'coord_b1', 'coord_w2']
+        for name in unused:
+            p = plan.params[i * per + _cabi.PARAM_FIELDS.index(name)]
+            if p is not None:
+                drop.add(p.data_ptr())
+    return drop
+
+
+def egnn_stack_backward_lean(ctx, d_h, d_x):
+    """Backward of _EGNNStackLeanFn.  Parameter gradients go into the gradient
+    arena (steady state of `backprop()`: cached pointer block, no per-parameter
+    Python work), or are accumulated into `p.grad` here when there is no arena
+    or it does not hold every parameter."""
+    plan, csr = ctx.plan, ctx.csr
+    layers = plan.layers
+    L, per = len(layers), len(_cabi.PARAM_FIELDS)
+    H, X, ws = ctx.H, ctx.X, ctx.ws
+    n, e = csr.n_nodes, csr.n_edges
+    dev = H.device
+    d_h = torch.zeros_like(H[L]) if d_h is None else d_h.contiguous().float()
+    no_dx = d_x is None
+    d_x = None if no_dx else d_x.contiguous().float()
+    csc_ptr, csc_eid = csr.csc()
+    arena = ARENA
+    gp = None
+    if arena is not None:
+        gp = plan.grad_plans.get(id(arena))
+        if gp is None or gp.arena_ref() is not arena:
+            gp = _StackGradPlan(plan, arena)
+            gp.arena_ref = _weak(arena)
+            plan.grad_plans = {id(arena): gp}
+        if not gp.ok or not arena.hand_out_all(gp.keys):
+            gp = None
+    flat, manual = None, []
+    if gp is not None:
+        gstructs = gp.gstructs
+    else:
+        # no arena (or not every parameter in it): zero-filled gradients of our
+        # own, handed to `p.grad` below
+        live = [(i, p) for i, p in enumerate(plan.params)
+                if p is not None and p.requires_grad]
+        flat = torch.zeros(sum(p.numel() for _, p in live) or 1,
+                           dtype=torch.float32, device=dev)
+        views, off = {}, 0
+        for i, p in live:
+            views[i] = flat[off:off + p.numel()]
+            off += p.numel()
+            manual.append((i, p))
+        gstructs = (_cabi.LayerGrads * L)()
+        for li in range(L):
+            gstructs[li] = _cabi.LayerGrads(*[
+                ptr(views.get(li * per + j)) for j in range(per)])
+    d_h_in = torch.empty_like(H[0])
+    d_x_in = torch.empty_like(X[0])
+    nbytes = int(lib().pvs_egnn_stack_bwd_workspace_bytes(n, e, L, plan.cfgs))
+    bws = _cabi.scratch('stack_bwd', nbytes, dev)
+    g = csr.c_struct()
+    with torch.cuda.device(dev):
+        check(lib().pvs_egnn_stack_bwd(
+            C.byref(g), ptr(csc_ptr), ptr(csc_eid), L, plan.cfgs, plan.pstructs,
+            gstructs, ptr(H), ptr(X), ptr(ws), C.c_int64(ctx.stride), ptr(d_h),
+            ptr(d_x), ptr(d_h_in), ptr(d_x_in), ptr(bws), C.c_int64(bws.numel()),
+            stream()), 'pvs_egnn_stack_bwd')
+    if gp is not None:
+        if arena.reduce_in_backward:
+            arena.reduce_async(*gp.span)
+        arena.grant_all(gp.granted(no_dx))
+    else:
+        drop = _stack_unused_keys(plan, no_dx)
+        with torch.no_grad():
+            for i, p in manual:
+                if p.data_ptr() in drop:
+                    continue
+                gview = views[i].view(p.shape)
+                p.grad = gview if p.grad is None else p.grad + gview
+    return (None, None, d_h_in, d_x_in, None)
+
+
+def _weak(obj):
+    import weakref
+    return weakref.ref(obj)
+
+
 def linear_backward(ctx, d_out):
     inp, w, out = ctx.saved_tensors
     bias = ctx.bias_ref

@@ -195,6 +195,10 @@ class PointNeuralNetworkBase(nn.Module):
         caller, so the host can run ahead of the device (N1)."""
         loss = self.get_loss(y_true, y_pred)
         arena = self._arena_for_step(loss)
+        # from now on the forward passes of this model may take the lean
+        # training path (egnn._EGNNStackLeanFn): its parameter gradients reach
+        # `p.grad` through the arena below instead of through autograd
+        self._lean_training = arena is not None
         if arena is None:
             self.optimiser.zero_grad()
             loss.backward()

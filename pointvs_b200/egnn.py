@@ -190,6 +190,88 @@ class _EGNNStackFn(torch.autograd.Function):
         return _bw.egnn_stack_backward(ctx, d_h, d_x)
 
 
+class _StackPlan:
+    """Everything the lean training pass needs again on every step while the
+    layers' parameters stay where they are: the struct arrays of
+    pvs_egnn_stack_fwd / _bwd, and (per gradient arena) the gradient pointer
+    block.  Cached on the model, keyed on the parameters' storage addresses."""
+
+    def __init__(self, layers):
+        self.layers = tuple(layers)
+        L = len(self.layers)
+        self.params = [p for layer in self.layers for p in layer.param_list()]
+        self.key = self.make_key(self.params, self.layers)
+        self.cfgs = (_cabi.LayerConfig * L)()
+        self.pstructs = (_cabi.LayerParams * L)()
+        for i, layer in enumerate(self.layers):
+            self.cfgs[i] = layer.c_config()
+            self.pstructs[i] = layer.c_params(layer.param_list())
+        self.anchor = next((p for p in self.params
+                            if p is not None and p.requires_grad), None)
+        self.grad_plans = {}
+
+    @staticmethod
+    def make_key(params, layers):
+        return (tuple(0 if p is None else p.data_ptr() for p in params),
+                tuple(p is not None and p.requires_grad for p in params),
+                tuple((l.math, l.c_flags()) for l in layers))
+
+    @classmethod
+    def of(cls, model, layers):
+        plan = model.__dict__.get('_stack_plan')
+        if plan is not None and len(plan.layers) == len(layers) and all(
+                a is b for a, b in zip(plan.layers, layers)):
+            # the Parameter objects of a module survive `.to()` / state-dict
+            # loads (only their storage moves), so the cached list is checked
+            # instead of walking the modules again
+            if cls.make_key(plan.params, layers) == plan.key:
+                return plan
+        plan = cls(layers)
+        model.__dict__['_stack_plan'] = plan
+        return plan
+
+
+class _EGNNStackLeanFn(torch.autograd.Function):
+    """The stacked training pass for models trained through `backprop()`:
+    only h and x (and one anchor parameter, so that the outputs require
+    grad) are autograd inputs.  Parameter gradients never travel through
+    autograd: the backward kernels write them into the model's gradient arena
+    (parallel.GradArena), or -- outside `backprop()` -- they are accumulated
+    into `p.grad` by hand, as AccumulateGrad would.  Host time per step: two
+    library calls instead of sixteen Functions with 27 inputs each."""
+
+    @staticmethod
+    def forward(ctx, plan, csr, h, x, _anchor):
+        ctx.set_materialize_grads(False)
+        layers = plan.layers
+        L = len(layers)
+        n, e, k = csr.n_nodes, csr.n_edges, layers[0].hidden_nf
+        dev = h.device
+        H = torch.empty((L + 1, n, k), dtype=torch.float32, device=dev)
+        X = torch.empty((L + 1, n, 3), dtype=torch.float32, device=dev)
+        H[0].copy_(h)
+        X[0].copy_(x)
+        stride = int(lib().pvs_egnn_stack_layer_ws_stride(n, e, L, plan.cfgs))
+        if stride < 0:
+            raise _cabi.PvsError('unsupported layer configuration for the '
+                                 'stacked training pass')
+        ws = torch.empty(max(1, L * stride), dtype=torch.uint8, device=dev)
+        tc = layers[0].math != 'fp32'
+        g = csr.c_struct(node_tiles=True, packed_tiles=tc)
+        with torch.cuda.device(dev):
+            check(lib().pvs_egnn_stack_fwd(
+                C.byref(g), L, plan.cfgs, plan.pstructs, ptr(H), ptr(X), ptr(ws),
+                C.c_int64(stride), stream()), 'pvs_egnn_stack_fwd')
+        ctx.plan, ctx.csr, ctx.stride = plan, csr, stride
+        ctx.H, ctx.X, ctx.ws = H, X, ws
+        return H[L], X[L]
+
+    @staticmethod
+    def backward(ctx, d_h, d_x):
+        from . import backward as _bw
+        return _bw.egnn_stack_backward_lean(ctx, d_h, d_x)
+
+
 class EGNNLayer(nn.Module):
     """Mirror of EGNNLayer (egnn_satorras.py:23-206)."""
     # pylint: disable = R, W, C
@@ -694,12 +776,15 @@ class SartorrasEGNN(PNNGeometricBase):
                 h.requires_grad or any(p.requires_grad
                                        for p in egnn_layers[0].parameters())):
             return False
-        # Opt-in (PVS_STACK_TRAIN=1): measured on B200 the step is bound by the
-        # GPU side of its ~350 small launches, not by the sixteen Python calls
-        # (8.1 ms per 16-complex step this way, 7.7 ms per layer), so the
-        # per-layer path -- which also overlaps the gradient all-reduce layer
-        # by layer -- stays the default.
-        if os.environ.get('PVS_STACK_TRAIN', '0') in ('', '0'):
+        # PVS_STACK_TRAIN=1 forces the stacked pass, =0 forbids it; by default
+        # it is used by models that are being trained through `backprop()`
+        # (base.py sets `_lean_training`), in its lean form: the device time of
+        # a step is the same either way, the host time is less than half
+        # (sixteen autograd Functions with 27 inputs each -> two calls), which
+        # decides the step time whenever the host is the slower side.
+        env = os.environ.get('PVS_STACK_TRAIN', '')
+        if env == '0' or (env in ('', None) and
+                          not getattr(self, '_lean_training', False)):
             return False
         return all(not l.edge_residual and not l.record_side_channels and
                    l.math == egnn_layers[0].math and
@@ -727,9 +812,14 @@ class SartorrasEGNN(PNNGeometricBase):
         m = None
         egnn_layers = list(self.layers)[1:]
         if self._stack_ok(egnn_layers, h, _want_messages):
-            flat = [p for layer in egnn_layers for p in layer.param_list()]
-            h, x = _EGNNStackFn.apply(tuple(egnn_layers), csr, h.contiguous(),
-                                      x.contiguous(), *flat)
+            if getattr(self, '_lean_training', False):
+                plan = _StackPlan.of(self, egnn_layers)
+                h, x = _EGNNStackLeanFn.apply(plan, csr, h.contiguous(),
+                                              x.contiguous(), plan.anchor)
+            else:
+                flat = [p for layer in egnn_layers for p in layer.param_list()]
+                h, x = _EGNNStackFn.apply(tuple(egnn_layers), csr,
+                                          h.contiguous(), x.contiguous(), *flat)
             egnn_layers = []
         for i, layer in enumerate(egnn_layers):
             last = i == len(egnn_layers) - 1

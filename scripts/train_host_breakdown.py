@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Host-side time of one training step by section (no device syncs inside the
 step): tells whether the step is paced by the host or by the device."""
-import sys, time, collections, math
+import os, sys, time, collections, math
 sys.path.insert(0, '/root/repo')
 import torch
 from pathlib import Path
@@ -16,6 +16,7 @@ dev = 'cuda'
 model = pv.MultitaskSatorrasEGNN(Path('/tmp/pvs_train'), 1e-3, 1e-4, None, None,
                                  silent=True, **kw).to(dev).train()
 model.set_math('bf16x3'); model.set_record_side_channels(False)
+model._lean_training = os.environ.get('LEAN', '1') == '1'
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 coords, bp, feats, cptr = synthetic_batch(0, B, 1000, 30)
 y = torch.tensor([i % 2 for i in range(B)], dtype=torch.float32, device=dev)

@@ -288,3 +288,61 @@ def test_train_model_raises_on_edge_capacity_overflow():
     assert len(losses) == 1 and np.isfinite(losses[0])
     with pytest.raises(RuntimeError, match='edge capacity exceeded'):
         model.train_model(loader(600), epochs=2)
+
+
+def test_lean_stacked_pass_equals_per_layer_pass(monkeypatch):
+    """The lean training pass (egnn._EGNNStackLeanFn: parameters are not
+    autograd inputs, their gradients are accumulated into `p.grad` by the
+    backward itself) gives bit-identical outputs and gradients to the
+    per-layer pass, also when called twice (gradients accumulate)."""
+    kw = dict(dim_input=13, dim_output=1, graphnorm=False, **VARIANTS['cfg3_k64'])
+    results = []
+    for lean in (False, True):
+        monkeypatch.setenv('PVS_STACK_TRAIN', '' if lean else '0')
+        model = gh.build_model(kw, seed=7, coord_gain=1.0).train()
+        model.set_math('bf16x3')
+        model._lean_training = lean
+        for _ in range(2):
+            graph = gh.synthetic_graph(900, 2, 400, 15, edge_capacity='auto')
+            graph.pos = graph.pos.clone().requires_grad_(True)
+            out = model(graph)
+            out.sum().backward()
+        grads = {n: (None if p.grad is None else p.grad.clone())
+                 for n, p in model.named_parameters()}
+        results.append((out.detach().clone(), graph.pos.grad.clone(), grads))
+    (o0, x0, g0), (o1, x1, g1) = results
+    assert torch.equal(o0, o1) and torch.equal(x0, x1)
+    for name in g0:
+        assert (g0[name] is None) == (g1[name] is None), name
+        if g0[name] is not None:
+            assert torch.equal(g0[name], g1[name]), name
+
+
+def test_backprop_lean_path_trains_like_the_per_layer_path(monkeypatch):
+    """Three `backprop()` steps (arena + fused Adam): the default path (lean
+    stacked pass from the second step on) and the per-layer path end with
+    bit-identical parameters."""
+    import pointvs_b200 as pv
+    from pathlib import Path
+    kw = dict(dim_input=13, dim_output=1, graphnorm=False, **VARIANTS['cfg3_k64'])
+    finals = []
+    for env in ('0', ''):
+        monkeypatch.setenv('PVS_STACK_TRAIN', env)
+        torch.manual_seed(0)
+        model = pv.SartorrasEGNN(Path('/tmp/pvs_test_lean'), 1e-3, 1e-4, None, None,
+                                 silent=True, **kw).cuda().train()
+        model.set_math('bf16x3')
+        model.set_record_side_channels(False)
+        losses = []
+        for s_ in range(3):
+            graph = gh.synthetic_graph(50 + s_, 4, 300, 15, edge_capacity='auto')
+            graph.y = torch.tensor([1.0, 0.0, 1.0, 0.0], device='cuda')
+            graph.lig_fname = graph.rec_fname = ['x'] * 4
+            y_pred, y_true, _, _ = model.unpack_input_data_and_predict(graph)
+            losses.append(model.backprop(y_true, y_pred))
+        assert getattr(model, '_lean_training', False)
+        finals.append((losses, [p.detach().clone() for p in model.parameters()]))
+    (l0, p0), (l1, p1) = finals
+    assert l0 == l1
+    for a, b in zip(p0, p1):
+        assert torch.equal(a, b)
