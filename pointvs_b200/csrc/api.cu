@@ -7,6 +7,7 @@
 namespace pvs {
 thread_local int g_last_cuda_error = 0;
 std::atomic<int64_t> g_launches{0};
+thread_local bool g_pdl_chain = false;
 
 int num_sms() {
     static thread_local int cached_dev = -1, cached = 0;

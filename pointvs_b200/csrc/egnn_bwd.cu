@@ -19,6 +19,8 @@
 //   csc_gather dQ_j = sum dt1, dx_j -= sum dd
 //   wgrad / finalize: dW = A^T B for the node-level weights, reduce per-CTA
 //              partials, dh += dP.W1a + dQ.W1b
+#include <cstdlib>
+
 #include "egnn_common.cuh"
 #include "egnn_bwd_common.cuh"
 #include "tile_gemm.cuh"
@@ -211,6 +213,8 @@ wgrad_group_kernel(const __grid_constant__ WgradGroup G, float *__restrict__ par
 // order (deterministic), four partial sums in flight per thread
 __global__ void wgrad_group_reduce_kernel(const __grid_constant__ WgradGroup G,
                                           const float *__restrict__ partial) {
+    pdl_wait();                  // chain kernel: see pvs_common.cuh
+    pdl_launch_dependents();
     const WgradJob &J = G.job[blockIdx.y];
     const int ko = J.ko, ki = J.B ? J.ki : 1;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -259,8 +263,8 @@ struct WgradGroupBuilder {
         if (tc) {
             const int rc = launch_wgrad_group_tc(G, rows, wg_group_ctas(), partial, st);
             if (rc) return rc;
-            wgrad_group_reduce_kernel<<<dim3((WG_PART + 255) / 256, G.n_jobs), 256, 0, st>>>(
-                G, partial);
+            launch_chained(wgrad_group_reduce_kernel, dim3((WG_PART + 255) / 256, G.n_jobs),
+                           dim3(256), 0, st, G, (const float *)partial);
             return check_launch(2);
         }
         int chunks = (rows + 127) / 128;
@@ -420,6 +424,10 @@ egnn_node_bwd_kernel(const NodeBwdArgs a) {
         bool ok = n < k && (kk < KB ? kk < k : (kk - KB) < k);
         W1n[idx] = ok ? a.node_w1[(size_t)n * 2 * k + src] : 0.0f;
     }
+    // the weight tiles above are static over the step; everything below may
+    // come from the kernel just before this one
+    pdl_wait();                  // chain kernel: see pvs_common.cuh
+    pdl_launch_dependents();
     for (int n = tid; n < 64; n += BT) {
         b1[n] = n < k ? a.node_b1[n] : 0.0f;
         b2[n] = n < k ? a.node_b2[n] : 0.0f;
@@ -1111,6 +1119,8 @@ egnn_edge_bwd_kernel(const EdgeBwdArgs a) {
 __global__ void edge_bwd_reduce_kernel(const float *__restrict__ partial, int n_cta,
                                        pvs_layer_grads g, int k, int in_e, int col_r,
                                        int n_classes) {
+    pdl_wait();                  // chain kernel: see pvs_common.cuh
+    pdl_launch_dependents();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= EP_STRIDE) return;
     float s = 0.0f;
@@ -1147,6 +1157,8 @@ __global__ void __launch_bounds__(256)
 csc_gather_kernel(const int32_t *__restrict__ csc_ptr, const int32_t *__restrict__ csc_eid,
                   int n_nodes, const float *__restrict__ DT1, const float *__restrict__ DD,
                   float *__restrict__ dQ, float *__restrict__ d_x_in) {
+    pdl_wait();                  // chain kernel: see pvs_common.cuh
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (j >= n_nodes) return;
@@ -1332,6 +1344,15 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
         return PVS_ERR_WORKSPACE;
 
     cudaStream_t st = (cudaStream_t)stream;
+    // the backward kernels of a layer form a launch chain (pvs_common.cuh)
+    struct ChainScope {
+        bool prev;
+        ChainScope() : prev(g_pdl_chain) {
+            static const bool off = getenv("PVS_NO_PDL") != nullptr;
+            g_pdl_chain = !off;
+        }
+        ~ChainScope() { g_pdl_chain = prev; }
+    } chain_scope;
     const int k = cfg->k, n = g->n_nodes, E = g->n_edges;
     const bool perm = f & PVS_F_PERM_INVARIANT;
     const int in_e = (perm ? k : 2 * k) + 1 + cfg->n_edge_classes;
@@ -1368,7 +1389,7 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
         const int grid = persistent_grid((n + 15) / 16, 1);
         if (!graphnorm) {
             na.phase = 0;
-            egnn_node_bwd_kernel<<<grid, BT, smem, st>>>(na);
+            launch_chained(egnn_node_bwd_kernel, dim3(grid), dim3(BT), smem, st, na);
             rc = check_launch();
             if (rc) return rc;
         } else {
@@ -1440,9 +1461,11 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
             if (rc) return rc;
             egnn_edge_bwd_kernel<<<w.edge_grid, BT, smem, st>>>(eb);
         }
-        edge_bwd_reduce_kernel<<<(EP_STRIDE + 255) / 256, 256, 0, st>>>(
-            w.edge_partial, w.edge_grid, *grads, k, in_e, col_r, cfg->n_edge_classes);
-        csc_gather_kernel<<<(n + 7) / 8, 256, 0, st>>>(csc_ptr, csc_eid, n, w.DT1, w.DD, w.dQ, d_x_in);
+        launch_chained(edge_bwd_reduce_kernel, dim3((EP_STRIDE + 255) / 256), dim3(256), 0, st,
+                       (const float *)w.edge_partial, w.edge_grid, *grads, k, in_e, col_r,
+                       cfg->n_edge_classes);
+        launch_chained(csc_gather_kernel, dim3((n + 7) / 8), dim3(256), 0, st, csc_ptr, csc_eid, n,
+                       (const float *)w.DT1, (const float *)w.DD, w.dQ, d_x_in);
         rc = check_launch(3);
         if (rc) return rc;
     }

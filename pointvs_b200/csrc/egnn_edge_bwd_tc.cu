@@ -325,6 +325,11 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) nx_xj[c] = a.x_in[3 * nx_col + c];
     };
+    // Everything above reads only what is static over the backward pass
+    // (weights, graph, forward activations); d_x_out and dM come from kernels
+    // earlier in the chain.
+    pdl_wait();
+    pdl_launch_dependents();
     pf_tile(blockIdx.x);
     pf_rows();
     pf_edges();
@@ -867,7 +872,7 @@ int launch_edge_bwd_tc(const EdgeBwdArgs &a, int grid, cudaStream_t st) {
     const size_t smem = sizeof(BwdTcSmem) + 1024;
     const int rc = ensure_smem(egnn_edge_bwd_tc_kernel, smem);
     if (rc) return rc;
-    egnn_edge_bwd_tc_kernel<<<grid, BT, smem, st>>>(a);
+    launch_chained(egnn_edge_bwd_tc_kernel, dim3(grid), dim3(BT), smem, st, a);
     return PVS_OK;
 }
 

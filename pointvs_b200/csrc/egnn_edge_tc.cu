@@ -146,6 +146,7 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
     // SWIZZLE_128B tiles need 1024-byte alignment; the kernel has no static
     // shared memory, so the dynamic window starts at its (aligned) base.
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    pdl_launch_dependents();
     constexpr int TC_GROUPS = TcCfg<MODE>::GROUPS, TC_THREADS = TcCfg<MODE>::THREADS;
     constexpr bool X3 = TcCfg<MODE>::A_LO;            // hi + lo activation tiles
     constexpr bool F16 = TcCfg<MODE>::F16;            // fp16 operands
@@ -227,6 +228,7 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
             pf_nb = a.ptile_last[t0];
         }
     }
+    pdl_wait();      // P, Q, x, m_prev of the kernels before this one
     for (int t = blockIdx.x * TC_GROUPS + g; t < n_tiles; t += t_stride) {
         const int E0 = t * TE, E1 = min(E0 + TE, E_total);
         if (!PF) {
@@ -610,6 +612,8 @@ egnn_edge_tc_kernel(const EdgeArgs a) {
 // reduction and adds the partials of the following tiles in tile order.
 __global__ void __launch_bounds__(256)
 edge_tile_fixup_kernel(const EdgeArgs a, int do_m, int do_x) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int n_tiles = *a.n_ptiles;
     if (t >= n_tiles - 1) return;                  // the last tile has no successor
@@ -660,7 +664,9 @@ static int launch_mode(const EdgeArgs &a, int n_ptiles_cap, cudaStream_t st) {
     if (grid < 1) grid = 1;
     const int rc = ensure_smem(egnn_edge_tc_kernel<MODE>, smem);
     if (rc) return rc;
-    egnn_edge_tc_kernel<MODE><<<grid, TcCfg<MODE>::THREADS, smem, st>>>(a);
+    if (launch_chained(egnn_edge_tc_kernel<MODE>, dim3(grid), dim3(TcCfg<MODE>::THREADS), smem, st,
+                       a) != cudaSuccess)
+        return check_launch(0);
     return PVS_OK;
 }
 
@@ -682,7 +688,8 @@ int launch_edge_tc(const EdgeArgs &a, int n_ptiles_cap, int mode, cudaStream_t s
     const bool softmax = (a.flags & PVS_F_EDGE_ATTENTION) && (a.flags & PVS_F_SOFTMAX_ATTENTION);
     const int do_m = softmax ? 0 : 1, do_x = a.x_out != nullptr ? 1 : 0;
     if (do_m || do_x)
-        edge_tile_fixup_kernel<<<(n_ptiles_cap + 7) / 8, 256, 0, st>>>(a, do_m, do_x);
+        launch_chained(edge_tile_fixup_kernel, dim3((n_ptiles_cap + 7) / 8), dim3(256), 0, st, a,
+                       do_m, do_x);
     return check_launch(do_m || do_x ? 2 : 1);
 }
 

@@ -34,6 +34,8 @@ linear_fwd_kernel(const float *__restrict__ in, int ld_in, int rows, int ki,
                   const float *__restrict__ b, int ko, int act,
                   float *__restrict__ out, int ld_out, int w_in_major,
                   int accumulate) {
+    pdl_wait();                  // chain kernel: see pvs_common.cuh
+    pdl_launch_dependents();
     extern __shared__ __align__(16) float smem[];
     constexpr int LDW = 64 * NJ4;
     const int KIP = (ki + 3) & ~3;
@@ -621,15 +623,13 @@ int launch_linear(const float *in, int ld_in, int rows, int ki,
     if (nj4 == 1) {
         rc = ensure_smem(linear_fwd_kernel<1>, smem);
         if (rc) return rc;
-        linear_fwd_kernel<1><<<grid, FWD_THREADS, smem, st>>>(
-            in, ld_in, rows, ki, w, ld_w, b, ko, act, out, ld_out, w_in_major,
-            accumulate);
+        launch_chained(linear_fwd_kernel<1>, dim3(grid), dim3(FWD_THREADS), smem, st, in, ld_in,
+                       rows, ki, w, ld_w, b, ko, act, out, ld_out, w_in_major, accumulate);
     } else {
         rc = ensure_smem(linear_fwd_kernel<2>, smem);
         if (rc) return rc;
-        linear_fwd_kernel<2><<<grid, FWD_THREADS, smem, st>>>(
-            in, ld_in, rows, ki, w, ld_w, b, ko, act, out, ld_out, w_in_major,
-            accumulate);
+        launch_chained(linear_fwd_kernel<2>, dim3(grid), dim3(FWD_THREADS), smem, st, in, ld_in,
+                       rows, ki, w, ld_w, b, ko, act, out, ld_out, w_in_major, accumulate);
     }
     return check_launch();
 }

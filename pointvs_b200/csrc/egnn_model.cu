@@ -1,6 +1,8 @@
 // Whole-model scoring pass: one C call per step (pvs_egnn_model_fwd).
 // Composition only -- every kernel is launched through the same code paths as
 // the per-layer entry points.
+#include <cstdlib>
+
 #include "egnn_common.cuh"
 
 using namespace pvs;
@@ -12,6 +14,14 @@ struct ModelWs {
     void *layer_ws;
     int64_t layer_ws_bytes;
     int64_t bytes;
+};
+
+struct ChainScope {
+    ChainScope() {
+        static const bool off = getenv("PVS_NO_PDL") != nullptr;   // A/B switch
+        g_pdl_chain = !off;
+    }
+    ~ChainScope() { g_pdl_chain = false; }
 };
 
 bool any_edge_residual(const pvs_model_desc *md) {
@@ -96,6 +106,12 @@ int pvs_egnn_model_fwd(const pvs_graph *g, const pvs_model_desc *md, const float
     const float *x_cur = x_in;
     const float *m_cur = nullptr;
     int hb = 0, xb = 0, mb = 0;
+    // from here to the end of the layer loop the tcgen05 kernels are launched
+    // with programmatic stream serialization: each one's prologue runs under
+    // the tail of the one before (pvs_common.cuh).  Every kernel of the chain
+    // waits for its predecessor before touching its data, and none of them
+    // writes what a prologue reads (weights, graph structure).
+    ChainScope chain_scope;
     for (int l = 0; l < md->n_layers; ++l) {
         const pvs_layer_config &cfg = md->layer_cfg[l];
         const bool coords = cfg.flags & PVS_F_UPDATE_COORDS;
@@ -167,6 +183,7 @@ int pvs_egnn_stack_fwd(const pvs_graph *g, int32_t n_layers, const pvs_layer_con
     if (layer_ws_stride < stack_layer_ws_stride(n, g->n_edges, n_layers, cfgs))
         return PVS_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    ChainScope chain_scope;      // as in pvs_egnn_model_fwd
     for (int l = 0; l < n_layers; ++l) {
         if (cfgs[l].k != k) return PVS_ERR_INVALID_ARG;
         if (cfgs[l].flags & PVS_F_EDGE_RESIDUAL) return PVS_ERR_INVALID_ARG;   // per-layer path

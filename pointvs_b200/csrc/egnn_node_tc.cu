@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(NP_THREADS, 1)
 node_pre_tc_kernel(const NodePreArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     NpSmem &S = *reinterpret_cast<NpSmem *>(smem_dyn);
+    pdl_launch_dependents();
     if ((smem_u32(smem_dyn) & 1023u) != 0u) __trap();
     const int g = threadIdx.x / NT_GROUP_THREADS, tid = threadIdx.x % NT_GROUP_THREADS;
     const int warp = tid >> 5;
@@ -169,6 +170,7 @@ node_pre_tc_kernel(const NodePreArgs a) {
     const uint32_t tmem_lane = tmem_grp + ((uint32_t)(warp * 32) << 16);
     uint32_t phase = 0;
     const RowShare rs = row_share(a.n_nodes, blockIdx.x * NP_GROUPS + g, gridDim.x * NP_GROUPS);
+    pdl_wait();      // h of the kernel before this one; P / Q still read by the edge kernel
     for (int row0 = rs.begin; row0 < rs.end; row0 += rs.tile_rows) {
         const int row_end = min(rs.end, row0 + rs.tile_rows);
         nt_group_sync(g);   // staging of the previous tile fully stored
@@ -300,6 +302,7 @@ __global__ void __launch_bounds__(NM_THREADS, 1)
 node_tc_kernel(const NodeTcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     NmSmem &S = *reinterpret_cast<NmSmem *>(smem_dyn);
+    pdl_launch_dependents();
     if ((smem_u32(smem_dyn) & 1023u) != 0u) __trap();
     const int g = threadIdx.x / NT_GROUP_THREADS, tid = threadIdx.x % NT_GROUP_THREADS;
 #ifdef PVS_PHASE_PROF
@@ -342,6 +345,7 @@ node_tc_kernel(const NodeTcArgs a) {
     const float gate = a.node_gate ? a.node_gate[0] : 1.0f;
     NPH(0);   // prologue: weight tiles, TMEM
     const RowShare rs = row_share(a.n_nodes, blockIdx.x * NM_GROUPS + g, gridDim.x * NM_GROUPS);
+    pdl_wait();      // M (and h) of the kernels before this one
     for (int row0 = rs.begin; row0 < rs.end; row0 += rs.tile_rows) {
         const int row_end = min(rs.end, row0 + rs.tile_rows);
         nt_group_sync(g);
@@ -550,11 +554,11 @@ int launch_node_pre_tc(const float *h, const float *edge_w1, const float *edge_b
     if (mode != PVS_MATH_BF16) {   // BF16X3, and the node stages of FP16X2
         rc = ensure_smem(node_pre_tc_kernel<true>, smem);
         if (rc) return rc;
-        node_pre_tc_kernel<true><<<grid, NP_THREADS, smem, st>>>(a);
+        launch_chained(node_pre_tc_kernel<true>, dim3(grid), dim3(NP_THREADS), smem, st, a);
     } else {
         rc = ensure_smem(node_pre_tc_kernel<false>, smem);
         if (rc) return rc;
-        node_pre_tc_kernel<false><<<grid, NP_THREADS, smem, st>>>(a);
+        launch_chained(node_pre_tc_kernel<false>, dim3(grid), dim3(NP_THREADS), smem, st, a);
     }
     return check_launch();
 }
@@ -581,11 +585,11 @@ int launch_node_tc(const float *h_in, const float *M, float *h_out, float *natt_
     if (mode != PVS_MATH_BF16) {   // BF16X3, and the node stages of FP16X2
         rc = ensure_smem(node_tc_kernel<true>, smem);
         if (rc) return rc;
-        node_tc_kernel<true><<<grid, NM_THREADS, smem, st>>>(a);
+        launch_chained(node_tc_kernel<true>, dim3(grid), dim3(NM_THREADS), smem, st, a);
     } else {
         rc = ensure_smem(node_tc_kernel<false>, smem);
         if (rc) return rc;
-        node_tc_kernel<false><<<grid, NM_THREADS, smem, st>>>(a);
+        launch_chained(node_tc_kernel<false>, dim3(grid), dim3(NM_THREADS), smem, st, a);
     }
     return check_launch();
 }

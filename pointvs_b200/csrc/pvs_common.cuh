@@ -32,6 +32,38 @@ inline int cuda_call(cudaError_t e) {
     return PVS_OK;
 }
 
+// Programmatic dependent launch (sm_90+).  A kernel of the scoring chain calls
+// pdl_launch_dependents() first thing and pdl_wait() after its prologue (weight
+// tiles, TMEM, barriers: nothing a predecessor writes) and before it touches
+// anything a predecessor produces or still reads.  Launched with
+// launch_chained(..., chained = true) the next kernel's CTAs then start on the
+// SMs the previous kernel has already left and run their prologue under its
+// tail; launched the ordinary way both calls are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+// true while pvs_egnn_model_fwd / pvs_egnn_stack_fwd issue their layer chain
+extern thread_local bool g_pdl_chain;
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                  cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl_chain ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int num_sms();
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device,
 // size): it is a driver call and was being issued before every launch.

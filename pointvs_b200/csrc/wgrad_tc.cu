@@ -73,6 +73,8 @@ wgrad_group_tc_kernel(const __grid_constant__ WgradGroup G, float *__restrict__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
+    pdl_wait();                  // chain kernel: see pvs_common.cuh
+    pdl_launch_dependents();
 
     float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     uint32_t phase = 0, acc = 0;
@@ -176,7 +178,7 @@ int launch_wgrad_group_tc(WgradGroup &G, int rows, int max_ctas, float *partial,
     const size_t smem = sizeof(WgTcSmem) + 1024;
     const int rc = ensure_smem(wgrad_group_tc_kernel, smem);
     if (rc) return rc;
-    wgrad_group_tc_kernel<<<G.chunks * G.n_jobs, WT, smem, st>>>(G, partial);
+    launch_chained(wgrad_group_tc_kernel, dim3(G.chunks * G.n_jobs), dim3(WT), smem, st, G, partial);
     return PVS_OK;
 }
 
