@@ -12,6 +12,6 @@ for tool in $TOOLS; do
         python scripts/sanitize_pass.py --math $m ${SAN_ARGS} \
         > gpurun_out/sanitize_${tool}_${m}.log 2>&1
     echo "sanitize $tool $m exit $?" | tee -a gpurun_out/sanitize_${tool}_${m}.log
-    grep -E "ERROR SUMMARY|RACECHECK SUMMARY|forward ok|backward ok|Error|hazard" gpurun_out/sanitize_${tool}_${m}.log | head -8
+    grep -E "ERROR SUMMARY|RACECHECK SUMMARY|forward ok|backward ok|backprop ok|Error|hazard" gpurun_out/sanitize_${tool}_${m}.log | head -8
   done
 done

@@ -55,6 +55,25 @@ def main():
         gn = sum(float(p.grad.abs().sum()) for p in model.parameters()
                  if p.grad is not None)
         print('backward ok', float(loss), gn)
+        # the training loop's own path: capacity-bounded graph (no host sync),
+        # gradient arena, lean stacked pass from the second step on, symmetric
+        # CSC, grouped weight gradients, arena clamp + fused Adam
+        model2 = pv.MultitaskSatorrasEGNN(Path('/tmp/pvs_sanitize'), 1e-3, 1e-4, None,
+                                          None, silent=True, model_task='classification',
+                                          **kw).cuda().train()
+        model2.set_math(a.math)
+        model2.set_record_side_channels(False)
+        ytrue = torch.tensor([float(i % 2) for i in range(a.complexes)], device='cuda')
+        losses = []
+        for _ in range(3):
+            b2 = pv.PackedBatch.from_arrays(coords, bp, feats, cptr, 4.0, 4.0, y=ytrue,
+                                            device='cuda', edge_capacity='auto')
+            b2.lig_fname = b2.rec_fname = [''] * a.complexes
+            yp, yt, _, _ = model2.unpack_input_data_and_predict(b2)
+            losses.append(float(model2.backprop(yt, yp, sync=False)))
+        torch.cuda.synchronize()
+        b2.pvs_csr.check_overflow()
+        print('backprop ok', losses, 'lean', getattr(model2, '_lean_training', False))
 
 
 if __name__ == '__main__':
