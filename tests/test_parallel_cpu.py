@@ -100,3 +100,73 @@ def test_two_rank_gloo(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / 'ok0').exists() and (tmp_path / 'ok1').exists()
+
+
+def _tiny_module():
+    import torch
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3),
+                               torch.nn.Linear(3, 2))
+
+
+def test_arena_spans_are_adjacent_and_merge_into_buckets(monkeypatch):
+    """Layer spans include their alignment padding, so consecutive spans touch
+    and `reduce_async` merges them until a bucket is full; `finish_reduce`
+    covers the rest in ONE call (no few-float gaps reduced one by one)."""
+    from pointvs_b200.parallel import GradArena
+    m = _tiny_module()
+    arena = GradArena(m)
+    spans = [arena.span(list(layer.parameters())) for layer in m]
+    for (lo0, hi0), (lo1, _) in zip(spans, spans[1:]):
+        assert hi0 == lo1                      # padded end == next slot's offset
+    assert spans[0][0] == 0 and spans[-1][1] == arena.numel
+    calls = []
+    monkeypatch.setattr(arena, '_world', lambda: 2)
+    monkeypatch.setattr(arena, '_all_reduce',
+                        lambda lo, hi: (calls.append((lo, hi)),
+                                        arena._reduced.append((lo, hi))))
+    arena.bucket_floats = spans[2][1] - spans[1][0]      # layers 2 + 1 fill a bucket
+    for lo, hi in reversed(spans):                       # backward order
+        arena.reduce_async(lo, hi)
+    # layers 2 and 1 merged into one call; layer 0 alone is a bucket
+    assert calls == [(spans[1][0], spans[2][1]), spans[0]]
+    arena.finish_reduce()
+    assert len(calls) == 2                               # nothing left over
+    # a bucket larger than the arena: nothing is issued from inside backward and
+    # the unfinished bucket goes out as ONE call at the end
+    del calls[:]
+    arena.bucket_floats = 10 * arena.numel
+    for lo, hi in reversed(spans):
+        arena.reduce_async(lo, hi)
+    assert calls == []
+    arena.finish_reduce()
+    assert calls == [(0, arena.numel)]
+
+
+def test_arena_clamp_equals_clip_grad_value():
+    import torch
+    from pointvs_b200.parallel import GradArena
+    m = _tiny_module()
+    arena = GradArena(m)
+    arena.begin_step()
+    g = torch.Generator().manual_seed(1)
+    for p in m.parameters():
+        v = arena.grad_view(p)
+        v.copy_(torch.randn(p.shape, generator=g) * 3)
+        arena.grant(p)
+    arena.attach_grads()
+    want = [p.grad.clone().clamp_(-1.0, 1.0) for p in m.parameters()]
+    assert arena.clamp_(1.0) == []
+    for p, w in zip(m.parameters(), want):
+        assert p.grad.data_ptr() == arena.view(p).data_ptr()
+        assert torch.equal(p.grad, w)
+    assert arena.matches(m) and arena.matches(m, full=True)
+    m[0].weight.requires_grad_(False)
+    assert not arena.matches(m)
+
+
+def test_auto_edge_capacity_grows_with_the_radius():
+    from pointvs_b200.graph import auto_edge_capacity
+    assert auto_edge_capacity(1000, 4.0, 4.0) == 24 * 1000
+    assert auto_edge_capacity(1000, 4.0, 2.0) == 24 * 1000
+    assert auto_edge_capacity(10, 6.0, 4.0) == 81 * 10
