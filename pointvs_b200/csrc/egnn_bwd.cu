@@ -987,7 +987,7 @@ egnn_edge_bwd_kernel(const EdgeBwdArgs a) {
                     const float d2 = acc[i][0][2] * sg.z, d3 = acc[i][0][3] * sg.w;
                     *reinterpret_cast<float4 *>(&S.B3[r * LDT + 4 * cg]) = make_float4(d0, d1, d2, d3);
                     if (r < ne)
-                        *reinterpret_cast<float4 *>(&a.DT1[(size_t)(c0 + r) * KB + 4 * cg]) =
+                        *reinterpret_cast<float4 *>(&a.DT1[dt1_at(a.dt1_rows, c0 + r, 4 * cg)]) =
                             make_float4(d0, d1, d2, d3);
                     float dot = S.wr[4 * cg] * d0 + S.wr[4 * cg + 1] * d1 +
                                 S.wr[4 * cg + 2] * d2 + S.wr[4 * cg + 3] * d3;
@@ -1155,7 +1155,8 @@ __global__ void edge_bwd_reduce_kernel(const float *__restrict__ partial, int n_
 // dQ_j = sum_{e : col(e) = j} dt1_e ; dx_j -= sum dd_e.  One warp per node.
 __global__ void __launch_bounds__(256)
 csc_gather_kernel(const int32_t *__restrict__ csc_ptr, const int32_t *__restrict__ csc_eid,
-                  int n_nodes, const float *__restrict__ DT1, const float *__restrict__ DD,
+                  int n_nodes, const float *__restrict__ DT1, int64_t dt1_rows,
+                  const float *__restrict__ DD,
                   float *__restrict__ dQ, float *__restrict__ d_x_in) {
     pdl_wait();                  // chain kernel: see pvs_common.cuh
     pdl_launch_dependents();
@@ -1166,7 +1167,7 @@ csc_gather_kernel(const int32_t *__restrict__ csc_ptr, const int32_t *__restrict
     float s0 = 0.f, s1 = 0.f, sd = 0.f;
     for (int p = lo; p < hi; ++p) {
         const int e = csc_eid[p];
-        const float2 d2 = __ldg(reinterpret_cast<const float2 *>(DT1 + (size_t)e * KB + 2 * lane));
+        const float2 d2 = __ldg(reinterpret_cast<const float2 *>(DT1 + dt1_at(dt1_rows, e, 2 * lane)));
         s0 += d2.x; s1 += d2.y;
         if (lane < 3) sd += DD[(size_t)e * 3 + lane];
     }
@@ -1440,7 +1441,7 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
         eb.alpha_in = fw.z_ws; eb.seg_s = w.seg_s;
     }
     eb.d_x_out = d_x_out; eb.d_m_out = d_m_out;
-    eb.dP = w.dP; eb.DT1 = w.DT1; eb.DD = w.DD; eb.d_x_in = d_x_in; eb.d_m_prev = d_m_prev;
+    eb.dP = w.dP; eb.DT1 = w.DT1; eb.dt1_rows = E; eb.DD = w.DD; eb.d_x_in = d_x_in; eb.d_m_prev = d_m_prev;
     eb.partial = w.edge_partial;
     eb.edge_w1 = p->edge_w1; eb.edge_w2 = p->edge_w2; eb.edge_b2 = p->edge_b2;
     eb.coord_w1 = p->coord_w1 ? p->coord_w1 : p->edge_w2;
@@ -1465,7 +1466,7 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
                        (const float *)w.edge_partial, w.edge_grid, *grads, k, in_e, col_r,
                        cfg->n_edge_classes);
         launch_chained(csc_gather_kernel, dim3((n + 7) / 8), dim3(256), 0, st, csc_ptr, csc_eid, n,
-                       (const float *)w.DT1, (const float *)w.DD, w.dQ, d_x_in);
+                       (const float *)w.DT1, (int64_t)E, (const float *)w.DD, w.dQ, d_x_in);
         rc = check_launch(3);
         if (rc) return rc;
     }

@@ -17,7 +17,8 @@ struct EdgeBwdArgs {
     const float *d_x_out;   // [N][3] or null
     const float *d_m_out;   // [E][k] or null
     float *dP;              // [N][64]
-    float *DT1;             // [E][64]
+    float *DT1;             // two planes [2][dt1_rows][32] (dt1_at below)
+    int64_t dt1_rows;       // rows per plane (the workspace's edge capacity)
     float *DD;              // [E][3]
     float *d_x_in;          // [N][3]
     float *d_m_prev;        // [E][k] or null
@@ -30,6 +31,17 @@ struct EdgeBwdArgs {
     uint32_t flags;
     int att_act;
 };
+
+// dt1 (gradient of the first edge layer's pre-activation, [E][64]) round-trips
+// HBM between the edge backward and the CSC gather.  It is stored as two planes
+// of 32 channels, each row 128 bytes with its 16-byte chunks XOR-swizzled by the
+// low bits of the GLOBAL edge index: that is byte for byte the shared-memory
+// image of the tcgen05 kernel's dt1 tile, so a tile leaves the SM as two bulk
+// asynchronous copies (TMA engine) instead of 2048 per-thread 16-byte stores.
+__host__ __device__ __forceinline__ int64_t dt1_at(int64_t dt1_rows, int64_t e, int n) {
+    const int ch = (n & 31) >> 2;
+    return (int64_t)(n >> 5) * dt1_rows * 32 + e * 32 + (((ch ^ (int)(e & 7)) << 2) | (n & 3));
+}
 
 // tcgen05 edge backward (egnn_edge_bwd_tc.cu).  Supports the configurations
 // without edge residual / softmax attention / incoming message gradients; the

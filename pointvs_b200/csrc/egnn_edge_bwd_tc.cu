@@ -160,8 +160,24 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 }
 
 // byte offset of 16-byte chunk `ch` (4 floats) of row r in an SG half tile
-__device__ __forceinline__ uint32_t sg_off(int r, int ch) {
-    return (uint32_t)(r * 128 + ((ch ^ (r & 7)) << 4));
+// (swizzled by the GLOBAL edge index, rot = first edge of the chunk & 7, so that
+// the tile is the image of its rows in the DT1 planes: dt1_at)
+__device__ __forceinline__ uint32_t sg_off(int r, int ch, int rot) {
+    return (uint32_t)(r * 128 + ((ch ^ ((r + rot) & 7)) << 4));
+}
+constexpr int DT1_ISSUER = 64;    // thread that issues the bulk stores of the dt1 tile
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() {      // sources may be overwritten
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {       // writes complete
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 #ifdef PVS_PHASE_PROF
@@ -355,9 +371,11 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int c0 = e0 + ch * TE;
             const int ne = min(TE, e1 - c0);
+            const int rot = c0 & 7;
             if (ne > 0) {
             // ---- S0: geometry and d(trans) ----
             BPH(0);
+            if (tid == DT1_ISSUER) bulk_wait_read();   // previous dt1 tile has left SG
             if (tid < TE) {
                 if (tid < ne) {
                     const int e = c0 + tid;
@@ -445,9 +463,9 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                     *reinterpret_cast<uint4 *>(S.S1[0] + swz(r, c)) = hi;
                     *reinterpret_cast<uint4 *>(S.S1[1] + swz(r, c)) = lo;
                     uint8_t *sg = reinterpret_cast<uint8_t *>(S.SG[c >> 2]);
-                    *reinterpret_cast<float4 *>(sg + sg_off(r, (2 * c) & 7)) =
+                    *reinterpret_cast<float4 *>(sg + sg_off(r, (2 * c) & 7, rot)) =
                         make_float4(sgv[0], sgv[1], sgv[2], sgv[3]);
-                    *reinterpret_cast<float4 *>(sg + sg_off(r, (2 * c + 1) & 7)) =
+                    *reinterpret_cast<float4 *>(sg + sg_off(r, (2 * c + 1) & 7, rot)) =
                         make_float4(sgv[4], sgv[5], sgv[6], sgv[7]);
                 }
             }
@@ -648,21 +666,27 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                 float dot = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    float4 *cell = reinterpret_cast<float4 *>(sg + sg_off(erow, j));
+                    float4 *cell = reinterpret_cast<float4 *>(sg + sg_off(erow, j, rot));
                     const float4 g4 = *cell;
                     const float4 d4 = make_float4(v[4 * j] * g4.x, v[4 * j + 1] * g4.y,
                                                   v[4 * j + 2] * g4.z, v[4 * j + 3] * g4.w);
                     *cell = d4;
-                    if (erow < ne)
-                        *reinterpret_cast<float4 *>(
-                            &a.DT1[(size_t)(c0 + erow) * KB + 32 * hf + 4 * j]) = d4;
                     const float4 w4 = *reinterpret_cast<const float4 *>(&S.wr[32 * hf + 4 * j]);
                     dot += w4.x * d4.x + w4.y * d4.y + w4.z * d4.z + w4.w * d4.w;
                 }
                 S.p_r[hf][erow] = dot;
                 tc_fence_before();
+                fence_proxy_async();       // the dt1 tile is read by the bulk copies below
             }
             __syncthreads();
+            // the dt1 tile -> its rows of the two DT1 planes (dt1_at): ne x 128 bytes
+            // each, contiguous in HBM and in shared memory
+            if (tid == DT1_ISSUER) {
+                bulk_store(a.DT1 + (size_t)c0 * 32, S.SG[0], (uint32_t)ne * 128u);
+                bulk_store(a.DT1 + (size_t)a.dt1_rows * 32 + (size_t)c0 * 32, S.SG[1],
+                           (uint32_t)ne * 128u);
+                bulk_commit();
+            }
             // ---- S6a: per-edge d(diff): dd = 2 d dr + d(d_hat) / norm ----
             BPH(11);
             if (tid < TE) {
@@ -690,7 +714,7 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                 const int chn = (n & 31) >> 2, sub = n & 3;
                 float swr = 0.0f, sT[PVS_MAX_EDGE_CLASSES] = {};
                 for (int el = 0; el < ne; ++el) {
-                    const float d = reinterpret_cast<const float *>(sg + sg_off(el, chn))[sub];
+                    const float d = reinterpret_cast<const float *>(sg + sg_off(el, chn, rot))[sub];
                     swr = fmaf(d, S.e_rad[el], swr);
                     const int at = S.e_attr[el];
 #pragma unroll
@@ -709,7 +733,7 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                 float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (fast_classes) {
                     for (int el = lo; el < hi; ++el) {
-                        const float4 d = *reinterpret_cast<const float4 *>(sg + sg_off(el, l16 & 7));
+                        const float4 d = *reinterpret_cast<const float4 *>(sg + sg_off(el, l16 & 7, rot));
                         sum.x += d.x; sum.y += d.y; sum.z += d.z; sum.w += d.w;
                         const float rad = S.e_rad[el];
                         awr.x = fmaf(d.x, rad, awr.x); awr.y = fmaf(d.y, rad, awr.y);
@@ -724,7 +748,7 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                     }
                 } else {
                     for (int el = lo; el < hi; ++el) {
-                        const float4 d = *reinterpret_cast<const float4 *>(sg + sg_off(el, l16 & 7));
+                        const float4 d = *reinterpret_cast<const float4 *>(sg + sg_off(el, l16 & 7, rot));
                         sum.x += d.x; sum.y += d.y; sum.z += d.z; sum.w += d.w;
                     }
                 }
@@ -768,6 +792,7 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
         }
     }
     // ---- per-CTA partials (fixed-order reductions: bitwise reproducible) ----
+    if (tid == DT1_ISSUER) bulk_wait_all();
     wait_wgrad();
     __syncthreads();
     S.red[warp][0][lane] = gb2;
