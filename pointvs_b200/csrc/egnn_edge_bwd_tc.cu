@@ -42,7 +42,19 @@ namespace pvs {
 
 namespace {
 
-constexpr int BT = 256;
+// Column split of the row-per-thread epilogues: CQ warps share a TMEM lane
+// quarter, each thread owns one edge row and CW = 64 / CQ accumulator columns.
+// CQ = 2: 8 warps, 221 registers.  CQ = 4 (16 warps at 128 registers, built with
+// -DPVS_BWD_CQ=4) passes the same tests and is 1.7 % SLOWER on the training step:
+// the per-row dot products then need a four-way exchange and every barrier
+// waits for twice the warps, which costs more than the shorter per-thread
+// chains save (profiles/r02_experiments/README.md).
+#ifndef PVS_BWD_CQ
+#define PVS_BWD_CQ 2
+#endif
+constexpr int CQ = PVS_BWD_CQ;
+constexpr int CW = 64 / CQ;
+constexpr int BT = 128 * CQ;
 constexpr int WG_ISSUER = 128;    // thread that issues the weight-gradient MMAs
 constexpr int KB = 64;
 // TMEM columns
@@ -63,13 +75,15 @@ struct BwdTcSmem {
     float acc_vec[5][64];                       // db2, dbc1, dwc2, dwa, dwr
     float acc_T[PVS_MAX_EDGE_CLASSES][64];
     float acc_s[2];                             // dba, dgate (unused here)
-    float red[8][4][32];                        // per-warp column sums at the end
     float e_rad[TE], e_dx[TE], e_dy[TE], e_dz[TE];      // normalised diff
     float e_rx[TE], e_ry[TE], e_rz[TE], e_invn[TE];     // raw diff, 1/(sqrt r + eps)
     float e_tx[TE], e_ty[TE], e_tz[TE];                 // d trans
     float e_z[TE], e_alpha[TE], e_dza[TE], e_c[TE], e_dcraw[TE], e_dr[TE];
     float e_ddx[TE], e_ddy[TE], e_ddz[TE];
-    float p_z[2][TE], p_c[2][TE], p_a[2][TE], p_r[2][TE];   // column-half partials
+    // column-split partials of the per-row dot products.  Two arrays serve four
+    // uses: z (E1) / a (E3) and c (E2) / r (E4) are separated by CTA barriers,
+    // z and c are not (only an mbarrier wait lies between them).
+    float p_za[CQ][TE], p_cr[CQ][TE];
     int e_rowl[TE], e_col[TE], e_attr[TE];
     int rp[TN + 1];
     float xsum[TN][3];
@@ -78,6 +92,8 @@ struct BwdTcSmem {
     uint64_t mbar_wg;                           // weight-gradient GEMMs (waited late)
     uint32_t tmem_base;
 };
+
+static_assert(sizeof(BwdTcSmem) + 1024 <= 232448, "BwdTcSmem exceeds the 227 KB opt-in limit");
 
 // W^T block -> swizzled bf16 hi / lo tile: tile row n (= input channel of W),
 // K index = output channel:  tile[n][kk] = W[kk][n]
@@ -143,11 +159,14 @@ __device__ __forceinline__ void silu_pair(float t, float &s, float &g) {
     g = sg * (1.0f + t * (1.0f - sg));
 }
 
-// Column sums over the 32 rows of a warp: lane l returns sum_rows v_row[l].
-// Recursive halving: 31 shuffles; the order of the additions is fixed.
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+// Column sums over the 32 rows of a warp of N (= 32 or 16) values per row: lane
+// l returns sum_rows v_row[l % N].  Recursive halving over the low lane bits,
+// then (N = 16) one exchange across lane bit 4; the order of the additions is
+// fixed.
+template <int N>
+__device__ __forceinline__ float warp_colsum(float (&v)[N], int lane) {
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
+    for (int o = N / 2; o >= 1; o >>= 1) {
         const bool up = lane & o;
 #pragma unroll
         for (int i = 0; i < o; ++i) {
@@ -156,7 +175,10 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
     }
-    return v[0];
+    float r = v[0];
+#pragma unroll
+    for (int o = N; o < 32; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    return r;
 }
 
 // byte offset of 16-byte chunk `ch` (4 floats) of row r in an SG half tile
@@ -203,7 +225,7 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
     if ((smem_u32(smem_dyn) & 1023u) != 0u) __trap();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int erow = 32 * (warp & 3) + lane;      // edge row of this thread (epilogues)
-    const int hf = warp >> 2;                     // column half
+    const int cq = warp >> 2;                     // column block: columns [CW cq, CW cq + CW)
     const int k = a.k;
     const bool f_att = a.flags & PVS_F_EDGE_ATTENTION;
     const bool f_coords = a.flags & PVS_F_UPDATE_COORDS;
@@ -236,11 +258,11 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = S.tmem_base;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 32u * hf;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(CW * cq);
     uint32_t phase = 0, phase_wg = 0;
     bool wg_pending = false;               // a weight-gradient GEMM still reads S1 / X / M
     const float att_b = (f_att && a.att_b) ? a.att_b[0] : 0.0f;
-    // per-thread accumulators that live across tiles: column 32 hf + lane
+    // per-thread accumulators that live across tiles: column CW cq + lane % CW
     float gb2 = 0.f, gbc1 = 0.f, gwc2 = 0.f, gwa = 0.f, gba = 0.f;
     uint32_t acc_w2 = 0, acc_wc1 = 0;      // 0 until the first weight-gradient MMA
     // d w_r and d T[class] of channels 4 (lane & 15) .. + 3 over the nodes this
@@ -252,23 +274,26 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
     for (int c = 0; c < FAST_CLASSES; ++c) aT[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int n_tiles = *a.n_tiles;
 
-    auto ld32 = [&](uint32_t col, float (&v)[32]) {
-        float lo16[16], hi16[16];
-        tmem_ld16(tmem_lane + col, lo16);
-        tmem_ld16(tmem_lane + col + 16, hi16);
+    auto ld32 = [&](uint32_t col, float (&v)[CW]) {      // this thread's CW columns
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { v[i] = lo16[i]; v[16 + i] = hi16[i]; }
+        for (int b = 0; b < CW / 16; ++b) {
+            float t16[16];
+            tmem_ld16(tmem_lane + col + 16 * b, t16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[16 * b + i] = t16[i];
+        }
     };
-    // 32 channels of this thread's row -> bf16 hi / lo tile (chunks 4 hf .. 4 hf + 3)
-    auto store_row = [&](uint8_t (*tile)[TE * 128], const float (&v)[32]) {
+    // CW channels of this thread's row -> bf16 hi / lo tile (16-byte chunks
+    // (CW / 8) cq ...)
+    auto store_row = [&](uint8_t (*tile)[TE * 128], const float (&v)[CW]) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < CW / 8; ++j) {
             float2 p[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) p[i] = make_float2(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
             uint4 hi, lo;
             split8p<true>(p, hi, lo);
-            const uint32_t off = swz(erow, 4 * hf + j);
+            const uint32_t off = swz(erow, (CW / 8) * cq + j);
             *reinterpret_cast<uint4 *>(tile[0] + off) = hi;
             *reinterpret_cast<uint4 *>(tile[1] + off) = lo;
         }
@@ -429,9 +454,10 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
             wait_wgrad();                  // dW2 of the previous tile read S1 and X
             {
                 const int c = tid & 7, slot = tid >> 3;
-                float4 buf[4][4];          // all four passes in flight
+                constexpr int SLOTS = BT / 8, PASSES = TE / SLOTS;   // rows per pass, passes
+                float4 buf[PASSES][4];     // all passes in flight
                 auto issue = [&](int p, float4 (&bq)[4]) {
-                    const int r = min(p * 32 + slot, ne - 1);
+                    const int r = min(p * SLOTS + slot, ne - 1);
                     const float4 *pp = reinterpret_cast<const float4 *>(
                         a.P + (size_t)(n0 + S.e_rowl[r]) * KB + 8 * c);
                     const float4 *qq = reinterpret_cast<const float4 *>(
@@ -440,11 +466,11 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                     bq[2] = __ldg(qq); bq[3] = __ldg(qq + 1);
                 };
 #pragma unroll
-                for (int p = 0; p < 4; ++p) issue(p, buf[p]);
+                for (int p = 0; p < PASSES; ++p) issue(p, buf[p]);
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
+                for (int p = 0; p < PASSES; ++p) {
                     const float4 (&bq)[4] = buf[p];
-                    const int r = p * 32 + slot, re = min(r, ne - 1);
+                    const int r = p * SLOTS + slot, re = min(r, ne - 1);
                     const float rad = S.e_rad[re];
                     const int at = S.e_attr[re];
                     const float pv[8] = {bq[0].x, bq[0].y, bq[0].z, bq[0].w,
@@ -481,19 +507,19 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
             // ---- E1: m = silu(t2 + b2) -> M tile; attention logit partial ----
             BPH(3);
             {
-                float v[32];
+                float v[CW];
                 ld32(C_D1, v);
                 float dot = 0.0f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int n = 32 * hf + i;
+                for (int i = 0; i < CW; ++i) {
+                    const int n = CW * cq + i;
                     float s, g;
                     silu_pair(v[i] + S.b2[n], s, g);
                     v[i] = s;
                     dot = fmaf(S.wa[n], s, dot);
                 }
                 store_row(S.Mt, v);
-                S.p_z[hf][erow] = dot;
+                S.p_za[cq][erow] = dot;
             }
             publish();
             // ---- G2: p = m . Wc1^T -> D2 ----
@@ -505,19 +531,21 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
             if (tid < TE) {
                 float z = 0.0f, al = 1.0f;
                 if (f_att) {
-                    z = S.p_z[0][tid] + S.p_z[1][tid] + att_b;
+                    z = att_b;
+#pragma unroll
+                    for (int b = 0; b < CQ; ++b) z += S.p_za[b][tid];
                     al = apply_act(z, a.att_act);
                 }
                 S.e_z[tid] = z;
                 S.e_alpha[tid] = al;
             }
             // dM of this thread's row (needed in E3; requested before the GEMM wait)
-            float dMv[32];
+            float dMv[CW];
             auto load_dM = [&]() {
                 const float4 *src = reinterpret_cast<const float4 *>(
-                    a.dM + (size_t)(n0 + S.e_rowl[erow]) * KB + 32 * hf);
+                    a.dM + (size_t)(n0 + S.e_rowl[erow]) * KB + CW * cq);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < CW / 4; ++i) {
                     float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (erow < ne) d4 = __ldg(src + i);
                     dMv[4 * i] = d4.x; dMv[4 * i + 1] = d4.y;
@@ -529,18 +557,18 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                 commit_wait();
                 // ---- E2: q = silu(p + bc1), craw = wc2 . q; then dp -> X tile ----
             BPH(5);
-                float q[32], sgp[32];
+                float q[CW], sgp[CW];
                 {
-                    float v[32];
+                    float v[CW];
                     ld32(C_D2, v);
                     float dot = 0.0f;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int n = 32 * hf + i;
+                    for (int i = 0; i < CW; ++i) {
+                        const int n = CW * cq + i;
                         silu_pair(v[i] + S.bc1[n], q[i], sgp[i]);
                         dot = fmaf(S.wc2[n], q[i], dot);
                     }
-                    S.p_c[hf][erow] = dot;
+                    S.p_cr[cq][erow] = dot;
                 }
                 tc_fence_before();
                 __syncthreads();
@@ -548,7 +576,9 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                 if (tid < TE) {
                     float c = 0.0f, dcraw = 0.0f;
                     if (tid < ne) {
-                        const float craw = S.p_c[0][tid] + S.p_c[1][tid];
+                        float craw = 0.0f;
+#pragma unroll
+                        for (int b = 0; b < CQ; ++b) craw += S.p_cr[b][tid];
                         c = (a.flags & PVS_F_TANH) ? tanhf(craw) : craw;
                         const float dc = S.e_tx[tid] * S.e_dx[tid] + S.e_ty[tid] * S.e_dy[tid] +
                                          S.e_tz[tid] * S.e_dz[tid];
@@ -560,15 +590,15 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                 __syncthreads();
                 {
                     const float dcr = S.e_dcraw[erow];
-                    float dp[32];
+                    float dp[CW];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        dp[i] = dcr * S.wc2[32 * hf + i] * sgp[i];
+                    for (int i = 0; i < CW; ++i) {
+                        dp[i] = dcr * S.wc2[CW * cq + i] * sgp[i];
                         q[i] *= dcr;                   // d wc2 contribution
                     }
                     store_row(S.Xt, dp);
-                    gbc1 += warp_colsum32(dp, lane);
-                    gwc2 += warp_colsum32(q, lane);
+                    gbc1 += warp_colsum<CW>(dp, lane);
+                    gwc2 += warp_colsum<CW>(q, lane);
                 }
                 publish();
                 // ---- G3: dWc1 += dp^T . m ; G4: dmc = dp . Wc1 -> D3 ----
@@ -596,23 +626,25 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
             }
             // ---- E3: attention backward, total dm, dt2 -> X tile ----
             {
-                float m[32], sg2[32];
+                float m[CW], sg2[CW];
                 {
-                    float v[32];
+                    float v[CW];
                     ld32(C_D1, v);
                     float dot = 0.0f;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        silu_pair(v[i] + S.b2[32 * hf + i], m[i], sg2[i]);
+                    for (int i = 0; i < CW; ++i) {
+                        silu_pair(v[i] + S.b2[CW * cq + i], m[i], sg2[i]);
                         dot = fmaf(dMv[i], m[i], dot);
                     }
-                    S.p_a[hf][erow] = dot;
+                    S.p_za[cq][erow] = dot;
                 }
                 __syncthreads();
                 if (f_att && tid < TE) {
                     float dza = 0.0f;
                     if (tid < ne) {
-                        const float dot = S.p_a[0][tid] + S.p_a[1][tid];
+                        float dot = 0.0f;
+#pragma unroll
+                        for (int b = 0; b < CQ; ++b) dot += S.p_za[b][tid];
                         dza = dot * act_grad(S.e_z[tid], S.e_alpha[tid], a.att_act);
                         gba += dza;
                     }
@@ -621,23 +653,23 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                 __syncthreads();
                 const float al = S.e_alpha[erow];
                 const float dz = f_att ? S.e_dza[erow] : 0.0f;
-                float dt2[32];
+                float dt2[CW];
                 if (f_coords) ld32(C_D3, dt2);       // dm of the coordinate branch
                 else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) dt2[i] = 0.0f;
+                    for (int i = 0; i < CW; ++i) dt2[i] = 0.0f;
                 }
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int n = 32 * hf + i;
+                for (int i = 0; i < CW; ++i) {
+                    const int n = CW * cq + i;
                     const float dm = dt2[i] + al * dMv[i] + dz * S.wa[n];
                     dt2[i] = (erow < ne && n < k) ? dm * sg2[i] : 0.0f;
                     m[i] *= dz;                        // d wa contribution
                 }
                 wait_wgrad();              // dWc1 read the X tile (dp) and the M tile
                 store_row(S.Xt, dt2);
-                gb2 += warp_colsum32(dt2, lane);
-                if (f_att) gwa += warp_colsum32(m, lane);
+                gb2 += warp_colsum<CW>(dt2, lane);
+                if (f_att) gwa += warp_colsum<CW>(m, lane);
             }
             publish();
             // ---- G5: dW2 += dt2^T . s1 ; G6: ds1 = dt2 . W2 -> D4 ----
@@ -660,21 +692,23 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
             BPH(10);
             // ---- E4: dt1 = ds1 * silu'(t1) -> SG (in place), DT1; d radial partial ----
             {
-                float v[32];
+                float v[CW];
                 ld32(C_D4, v);
-                uint8_t *sg = reinterpret_cast<uint8_t *>(S.SG[hf]);
+                // columns CW cq ..: half tile (CW cq) / 32, chunks ((CW cq) % 32) / 4 ...
+                uint8_t *sg = reinterpret_cast<uint8_t *>(S.SG[(CW * cq) >> 5]);
+                const int ch0 = ((CW * cq) & 31) >> 2;
                 float dot = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 *cell = reinterpret_cast<float4 *>(sg + sg_off(erow, j, rot));
+                for (int j = 0; j < CW / 4; ++j) {
+                    float4 *cell = reinterpret_cast<float4 *>(sg + sg_off(erow, ch0 + j, rot));
                     const float4 g4 = *cell;
                     const float4 d4 = make_float4(v[4 * j] * g4.x, v[4 * j + 1] * g4.y,
                                                   v[4 * j + 2] * g4.z, v[4 * j + 3] * g4.w);
                     *cell = d4;
-                    const float4 w4 = *reinterpret_cast<const float4 *>(&S.wr[32 * hf + 4 * j]);
+                    const float4 w4 = *reinterpret_cast<const float4 *>(&S.wr[CW * cq + 4 * j]);
                     dot += w4.x * d4.x + w4.y * d4.y + w4.z * d4.z + w4.w * d4.w;
                 }
-                S.p_r[hf][erow] = dot;
+                S.p_cr[cq][erow] = dot;
                 tc_fence_before();
                 fence_proxy_async();       // the dt1 tile is read by the bulk copies below
             }
@@ -693,7 +727,10 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
                 float ddx = 0.f, ddy = 0.f, ddz = 0.f;
                 if (tid < ne) {
                     const float c = f_coords ? S.e_c[tid] : 0.0f;
-                    const float dr2 = 2.0f * (S.p_r[0][tid] + S.p_r[1][tid]);
+                    float drs = 0.0f;
+#pragma unroll
+                    for (int b = 0; b < CQ; ++b) drs += S.p_cr[b][tid];
+                    const float dr2 = 2.0f * drs;
                     const float invn = S.e_invn[tid];   // norm is detached (:184)
                     ddx = fmaf(dr2, S.e_rx[tid], S.e_tx[tid] * c * invn);
                     ddy = fmaf(dr2, S.e_ry[tid], S.e_ty[tid] * c * invn);
@@ -795,23 +832,25 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
     if (tid == DT1_ISSUER) bulk_wait_all();
     wait_wgrad();
     __syncthreads();
-    S.red[warp][0][lane] = gb2;
-    S.red[warp][1][lane] = gbc1;
-    S.red[warp][2][lane] = gwc2;
-    S.red[warp][3][lane] = gwa;
+    // per-warp column sums, [BT / 32][4][32] floats in the X tile (free by now)
+    float (*red)[4][32] = reinterpret_cast<float (*)[4][32]>(S.Xt[0]);
+    red[warp][0][lane] = gb2;
+    red[warp][1][lane] = gbc1;
+    red[warp][2][lane] = gwc2;
+    red[warp][3][lane] = gwa;
     gba = warp_sum(gba);
-    if (lane == 0) S.p_z[0][warp] = gba;
+    if (lane == 0) S.p_za[0][warp] = gba;
     __syncthreads();
-    {
+    if (tid < 256) {
         const int v = tid >> 6, n = tid & 63;   // 4 vectors x 64 channels
-        const int h = n >> 5;
+        const int b = n / CW;                   // column block: warps 4 b .. 4 b + 3
         float s = 0.0f;
-        for (int w = 0; w < 4; ++w) s += S.red[4 * h + w][v][n & 31];
+        for (int w = 0; w < 4; ++w) s += red[4 * b + w][v][n % CW];
         S.acc_vec[v][n] = s;
     }
     if (tid == 0) {
         float s0 = 0.0f;
-        for (int wi = 0; wi < 4; ++wi) s0 += S.p_z[0][wi];   // warps 0..3 hold edges
+        for (int wi = 0; wi < 4; ++wi) s0 += S.p_za[0][wi];   // warps 0..3 hold edges
         S.acc_s[0] = s0;
         S.acc_s[1] = 0.0f;
     }
@@ -819,7 +858,10 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
     if (fast_classes) {
         // the S6c riders: warp partials -> channel totals, in warp order (the SG
         // tile is free by now)
-        float *wp = reinterpret_cast<float *>(S.SG[0]);        // [16][1 + FAST_CLASSES][64]
+        // [BT / 16][1 + FAST_CLASSES][64] floats in the activation tiles (free by now)
+        static_assert(sizeof(float) * (BT / 16) * (1 + FAST_CLASSES) * 64 <= 6 * TE * 128,
+                      "rider scratch fits the activation tiles");
+        float *wp = reinterpret_cast<float *>(S.S1[0]);
         const int slot = 2 * warp + (lane >> 4), l16 = lane & 15;
         *reinterpret_cast<float4 *>(&wp[(slot * (1 + FAST_CLASSES)) * 64 + 4 * l16]) = awr;
 #pragma unroll
