@@ -12,6 +12,10 @@
 // TMEM, one thread per row in the epilogue, several independent 4-warp groups
 // per persistent CTA sharing the weight tiles.  Outputs are staged through
 // shared memory so global stores are full 256-byte rows.
+#include <cstdlib>
+
+#include <cuda.h>       // CUtensorMap (types only: the encoder comes from the runtime)
+
 #include "egnn_common.cuh"
 #include "tc_common.cuh"
 
@@ -56,13 +60,23 @@ __device__ __forceinline__ void nt_group_sync(int g) {
 // 128 x 1000-atom batch: a quarter of the groups did two tiles, the rest one,
 // and the kernel took two tile times.)
 struct RowShare { int begin, end, tile_rows; };
-__device__ __forceinline__ RowShare row_share(int n_rows, int group_id, int n_groups) {
+// rows per tile and tiles per group (host: the box height of the TMA stores)
+__host__ __device__ inline void row_share_tiling(int n_rows, int n_groups, int *tile_rows,
+                                                 int *tiles) {
     const int per = (n_rows + n_groups - 1) / n_groups;
+    *tiles = per > NT_ROWS ? (per + NT_ROWS - 1) / NT_ROWS : 1;
+    const int tr = (per + *tiles - 1) / *tiles;
+    *tile_rows = tr > 1 ? tr : 1;
+}
+__device__ __forceinline__ RowShare row_share(int n_rows, int group_id, int n_groups) {
     RowShare r;
-    r.begin = min(n_rows, group_id * per);
+    int tiles;
+    row_share_tiling(n_rows, n_groups, &r.tile_rows, &tiles);
+    // whole tiles only: every tile of the grid has tile_rows rows (the box of
+    // the TMA stores) except where the array ends
+    const int per = tiles * r.tile_rows;
+    r.begin = (int)min((long long)n_rows, (long long)group_id * per);
     r.end = min(n_rows, r.begin + per);
-    const int tiles = max(1, (per + NT_ROWS - 1) / NT_ROWS);
-    r.tile_rows = (per + tiles - 1) / tiles;
     return r;
 }
 
@@ -121,6 +135,58 @@ __device__ __forceinline__ float4 *stage_ptr(float *stage, int r, int c4) {
 }
 
 // ---------------------------------------------------------------------------
+// TMA tensor stores of fp32 output tiles.  A [rows][64] fp32 output leaves a
+// tile as 32-column boxes: in shared memory a box is rows x 128 bytes with the
+// 16-byte chunks XOR-swizzled by the row (SWIZZLE_128B: the same swz() the bf16
+// operand tiles use, so row-per-thread writes are conflict free), and the
+// tensor map un-swizzles it on the way to the row-major array in HBM.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, const void *smem, int c0,
+                                             int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_wait_read() {     // <= N groups still reading smem
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_wait_all() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// [n_rows][64] fp32 row-major array -> tensor map with boxes of 32 columns x
+// box_rows rows, SWIZZLE_128B.  false if the driver entry point is unavailable.
+static bool make_rows_tensor_map(CUtensorMap *tm, const float *base, int n_rows, int box_rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                 const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) !=
+                cudaSuccess || q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return (EncodeFn)fn;
+    }();
+    if (!encode || n_rows < 1 || box_rows < 1 || box_rows > 256 ||
+        (reinterpret_cast<uintptr_t>(base) & 15))
+        return false;
+    const cuuint64_t dims[2] = {64, (cuuint64_t)n_rows};
+    const cuuint64_t strides[1] = {64 * sizeof(float)};
+    const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+           CUDA_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------
 // node_pre: P, Q
 // ---------------------------------------------------------------------------
 constexpr int NP_GROUPS = 4;
@@ -137,16 +203,18 @@ struct __align__(1024) NpSmem {
 };
 
 struct NodePreArgs {
+    CUtensorMap tm_p, tm_q;   // P and Q as [N][64] fp32, boxes of 32 columns x tile_rows rows
     const float *h;       // [N][k]
     const float *edge_w1; // [k][in_e]
     const float *edge_b1; // [k]
     float *P, *Q;         // [N][64]
     int n_nodes, k, in_e, perm_invariant;
+    int use_tma;          // P / Q tiles leave through the tensor maps
 };
 
 template <bool X3>
 __global__ void __launch_bounds__(NP_THREADS, 1)
-node_pre_tc_kernel(const NodePreArgs a) {
+node_pre_tc_kernel(const __grid_constant__ NodePreArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     NpSmem &S = *reinterpret_cast<NpSmem *>(smem_dyn);
     pdl_launch_dependents();
@@ -186,7 +254,47 @@ node_pre_tc_kernel(const NodePreArgs a) {
         mbar_wait(&S.mbar[g], phase);
         phase ^= 1;
         tc_fence_after();
-        // The A tiles are free once the MMA has completed: each 16 KB tile stages
+        if (a.use_tma) {
+            // The A tiles are free once the MMA has completed.  Four boxes of 32
+            // columns (P low, P high, Q low, Q high) alternate between them: a
+            // thread writes its row of the box (swizzled, conflict free), one
+            // thread hands the box to the TMA engine, and the next box is
+            // written while that store drains.
+#pragma unroll 1
+            for (int sq = 0; sq < 4; ++sq) {
+                uint8_t *buf = (sq & 1) ? A_lo : A_hi;
+                if (sq >= 2) {                    // the store issued two boxes ago has
+                    if (tid == 0) tma_wait_read<1>();   // finished reading this buffer
+                    nt_group_sync(g);
+                }
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    float acc[16];
+                    tmem_ld16(tmem_lane + 32 * sq + 16 * b, acc);
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4) {
+                        float4 o = make_float4(acc[4 * v4], acc[4 * v4 + 1], acc[4 * v4 + 2],
+                                               acc[4 * v4 + 3]);
+                        if (sq < 2) {
+                            const float4 bb = *reinterpret_cast<const float4 *>(
+                                &S.b1[32 * sq + 16 * b + 4 * v4]);
+                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                        }
+                        *reinterpret_cast<float4 *>(buf + swz(tid, 4 * b + v4)) = o;
+                    }
+                }
+                fence_proxy_async();
+                nt_group_sync(g);
+                if (tid == 0) {
+                    tma_store_2d(sq < 2 ? &a.tm_p : &a.tm_q, buf, 32 * (sq & 1), row0);
+                    tma_commit();
+                }
+            }
+            if (tid == 0) tma_wait_read<0>();     // before the next tile refills the A tiles
+            tc_fence_before();
+            continue;
+        }
+        // (thread-store path: tensor maps unavailable)  Each 16 KB tile stages
         // 64 rows of fp32 output (rows 0..63 in A_hi, 64..127 in A_lo), P first,
         // then Q.
 #pragma unroll 1
@@ -227,6 +335,7 @@ node_pre_tc_kernel(const NodePreArgs a) {
         }
         tc_fence_before();
     }
+    if (a.use_tma && tid == 0) tma_wait_all();     // the tiles have reached HBM
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32) tmem_dealloc<512>(tmem_base);
@@ -542,7 +651,9 @@ node_tc_kernel(const NodeTcArgs a) {
 int launch_node_pre_tc(const float *h, const float *edge_w1, const float *edge_b1, float *P,
                        float *Q, int n_nodes, int k, int in_e, int perm, int mode,
                        cudaStream_t st) {
-    NodePreArgs a{h, edge_w1, edge_b1, P, Q, n_nodes, k, in_e, perm};
+    NodePreArgs a{};
+    a.h = h; a.edge_w1 = edge_w1; a.edge_b1 = edge_b1; a.P = P; a.Q = Q;
+    a.n_nodes = n_nodes; a.k = k; a.in_e = in_e; a.perm_invariant = perm;
     const size_t smem = sizeof(NpSmem);
     // one persistent CTA per SM; fewer only when a group's share would fall
     // under 16 rows
@@ -550,6 +661,13 @@ int launch_node_pre_tc(const float *h, const float *edge_w1, const float *edge_b
     const int need = (n_nodes + 16 * NP_GROUPS - 1) / (16 * NP_GROUPS);
     if (need < grid) grid = need;
     if (grid < 1) grid = 1;
+    // P and Q leave their tiles through tensor maps (boxes of tile_rows rows);
+    // PVS_NO_TMA=1 keeps the thread-store path (A/B switch)
+    static const bool no_tma = getenv("PVS_NO_TMA") != nullptr;
+    int tile_rows, tiles;
+    row_share_tiling(n_nodes, grid * NP_GROUPS, &tile_rows, &tiles);
+    a.use_tma = !no_tma && make_rows_tensor_map(&a.tm_p, P, n_nodes, tile_rows) &&
+                make_rows_tensor_map(&a.tm_q, Q, n_nodes, tile_rows);
     int rc;
     if (mode != PVS_MATH_BF16) {   // BF16X3, and the node stages of FP16X2
         rc = ensure_smem(node_pre_tc_kernel<true>, smem);
