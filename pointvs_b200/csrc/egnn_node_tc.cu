@@ -360,6 +360,8 @@ struct __align__(1024) NmSmem {
 };
 
 struct NodeTcArgs {
+    CUtensorMap tm_h;    // h_out as [N][64] fp32 (k == 64), boxes of 32 columns x tile_rows
+    int use_tma;         // h_out tiles leave through tm_h
     const float *h_in;   // [N][k]
     const float *M;      // [N][64]
     float *h_out;        // [N][k]
@@ -408,7 +410,7 @@ __device__ __forceinline__ void load_block_gn(uint8_t *A_hi, uint8_t *A_lo,
 
 template <bool X3>
 __global__ void __launch_bounds__(NM_THREADS, 1)
-node_tc_kernel(const NodeTcArgs a) {
+node_tc_kernel(const __grid_constant__ NodeTcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     NmSmem &S = *reinterpret_cast<NmSmem *>(smem_dyn);
     pdl_launch_dependents();
@@ -558,6 +560,74 @@ node_tc_kernel(const NodeTcArgs a) {
         phase ^= 1;
         tc_fence_after();
         NPH(6);   // GEMM 2
+        if (a.use_tma) {
+            // ---- k == 64: the thread owns its whole row, so the attention logit
+            // is thread-local; a second pass over TMEM forms
+            // h' = residual(h, s (D + b2)) straight into two 32-column boxes
+            // (SWIZZLE_128B, conflict free) which the TMA engine stores.  h is
+            // read per thread (a 256-byte row each, L2-hot from the A-tile load).
+            const int r = tid;
+            const bool ok = row0 + r < row_end;
+            float s = 1.0f;
+            if (f_natt) {
+                float dot = 0.0f;
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {
+                    float acc[16];
+                    tmem_ld16(tmem_lane + 16 * q, acc);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        dot = fmaf(S.wn[16 * q + i], acc[i] + S.b2[16 * q + i], dot);
+                }
+                const float zn = dot + natt_b;
+                s = (a.flags & PVS_F_SOFTMAX_ATTENTION) ? zn : apply_act(zn, a.att_act);
+                if (a.natt_out && ok) a.natt_out[row0 + r] = s;
+            }
+            const float4 *hrow = reinterpret_cast<const float4 *>(
+                a.h_in + (size_t)(row0 + (ok ? r : 0)) * 64);
+            const float G = fmaxf(gate, 0.0f);
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                float acc[16];
+                tmem_ld16(tmem_lane + 16 * q, acc);
+                uint8_t *buf = q < 2 ? A_hi : A_lo;
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    const int n = 16 * q + 4 * v4;
+                    float o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) o[i] = s * (acc[4 * v4 + i] + S.b2[n + i]);
+                    if (f_res) {
+                        const float4 h4 = __ldg(hrow + 4 * q + v4);
+                        const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (a.flags & PVS_F_REZERO) o[i] = hv[i] + gate * o[i];
+                            else if (a.flags & PVS_F_GATED_RESIDUAL)
+                                o[i] = G * o[i] + (1.0f - G) * hv[i];
+                            else o[i] = hv[i] + o[i];
+                        }
+                    }
+                    *reinterpret_cast<float4 *>(buf + swz(r, 4 * (q & 1) + v4)) =
+                        make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            nt_group_sync(g);
+            NPH(7);
+            if (tid == 0) {
+                tma_store_2d(&a.tm_h, A_hi, 0, row0);
+                tma_store_2d(&a.tm_h, A_lo, 32, row0);
+                tma_commit();
+                tma_wait_read<0>();    // the loop-top barrier then frees the A tiles
+            }
+#ifdef PVS_PHASE_PROF
+            nt_group_sync(g);
+#endif
+            NPH(8);
+            continue;
+        }
         // ---- o = D + b2 and the node-attention logit in ONE pass over TMEM
         // (thread per row); o goes to the fp32 staging tile unscaled.  The
         // attention factor and the residual are applied in the store pass, where
@@ -643,6 +713,7 @@ node_tc_kernel(const NodeTcArgs a) {
 #endif
         NPH(8);   // store pass
     }
+    if (a.use_tma && tid == 0) tma_wait_all();     // the tiles have reached HBM
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32) tmem_dealloc<512>(tmem_base);
@@ -699,6 +770,19 @@ int launch_node_tc(const float *h_in, const float *M, float *h_out, float *natt_
     const int need = (n_nodes + 16 * NM_GROUPS - 1) / (16 * NM_GROUPS);
     if (need < grid) grid = need;
     if (grid < 1) grid = 1;
+    // Opt-in (PVS_NODE_TC_TMA=1): h' through a tensor map when it is a [N][64]
+    // array (k == 64).  Measured 1.4 % SLOWER on the scoring pass than the
+    // staged thread stores: the residual then needs h per thread (a 256-byte row
+    // each instead of full lines per half warp) and a second pass over TMEM,
+    // which costs more than the store pass it removes (node_pre, whose output
+    // needs neither, gains 0.4 % from its TMA stores).
+    static const bool tma = getenv("PVS_NODE_TC_TMA") != nullptr;
+    a.use_tma = 0;
+    if (tma && k == 64 && phase != 1 && h_out != nullptr) {
+        int tile_rows, tiles;
+        row_share_tiling(n_nodes, grid * NM_GROUPS, &tile_rows, &tiles);
+        a.use_tma = make_rows_tensor_map(&a.tm_h, h_out, n_nodes, tile_rows) ? 1 : 0;
+    }
     int rc;
     if (mode != PVS_MATH_BF16) {   // BF16X3, and the node stages of FP16X2
         rc = ensure_smem(node_tc_kernel<true>, smem);
