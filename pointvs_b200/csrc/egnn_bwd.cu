@@ -1486,12 +1486,18 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
         wg.add(w.dP, KB, k, h_in, k, k, grads->edge_w1, in_e, nullptr);
         wg.add(w.dQ, KB, k, nullptr, 0, 0, nullptr, 0, grads->edge_b1);
     } else {
-        rc = launch_linear(w.dP, KB, n, k, p->edge_w1, in_e, nullptr, k, PVS_ACT_NONE, d_h_in, k,
-                           st, 1, 1);
-        if (rc) return rc;
-        rc = launch_linear(w.dQ, KB, n, k, p->edge_w1 + k, in_e, nullptr, k, PVS_ACT_NONE, d_h_in,
-                           k, st, 1, 1);
-        if (rc) return rc;
+        if (cfg->math != PVS_MATH_FP32) {
+            // one tcgen05 pass (K = 128 as two blocks) instead of two FFMA launches
+            rc = launch_dgrad_pq_tc(w.dP, w.dQ, p->edge_w1, d_h_in, n, k, in_e, st);
+            if (rc) return rc;
+        } else {
+            rc = launch_linear(w.dP, KB, n, k, p->edge_w1, in_e, nullptr, k, PVS_ACT_NONE, d_h_in,
+                               k, st, 1, 1);
+            if (rc) return rc;
+            rc = launch_linear(w.dQ, KB, n, k, p->edge_w1 + k, in_e, nullptr, k, PVS_ACT_NONE,
+                               d_h_in, k, st, 1, 1);
+            if (rc) return rc;
+        }
         wg.add(w.dP, KB, k, h_in, k, k, grads->edge_w1, in_e, grads->edge_b1);
         wg.add(w.dQ, KB, k, h_in, k, k, grads->edge_w1 ? grads->edge_w1 + k : nullptr, in_e,
                nullptr);

@@ -62,6 +62,9 @@ int fwd_recompute(const pvs_graph *g, const pvs_layer_config *cfg, const pvs_lay
 // P, Q, M of a layer as pvs_egnn_layer_fwd left them in its workspace
 FwdWorkspace fwd_saved(const void *saved_workspace, int n, int e, uint32_t flags);
 // tensor-core node stages (egnn_node_tc.cu); mode = PVS_MATH_BF16X3 / BF16
+// K3: d_h[N][k] += dP[N][64] . W1a + dQ[N][64] . W1b on tcgen05 (bf16x3)
+int launch_dgrad_pq_tc(const float *dP, const float *dQ, const float *edge_w1, float *d_h,
+                       int n_nodes, int k, int in_e, cudaStream_t st);
 int launch_node_pre_tc(const float *h, const float *edge_w1, const float *edge_b1, float *P,
                        float *Q, int n_nodes, int k, int in_e, int perm, int mode,
                        cudaStream_t st);

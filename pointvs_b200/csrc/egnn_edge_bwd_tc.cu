@@ -95,26 +95,6 @@ struct BwdTcSmem {
 
 static_assert(sizeof(BwdTcSmem) + 1024 <= 232448, "BwdTcSmem exceeds the 227 KB opt-in limit");
 
-// W^T block -> swizzled bf16 hi / lo tile: tile row n (= input channel of W),
-// K index = output channel:  tile[n][kk] = W[kk][n]
-__device__ void load_weight_tiles_T(uint8_t *hi_tile, uint8_t *lo_tile,
-                                    const float *__restrict__ W, int ld, int n_valid,
-                                    int k_valid) {
-    for (int idx = threadIdx.x; idx < 64 * 8; idx += blockDim.x) {
-        const int n = idx >> 3, c = idx & 7;
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int kk = 8 * c + i;
-            v[i] = (n < n_valid && kk < k_valid) ? W[(size_t)kk * ld + n] : 0.0f;
-        }
-        uint4 hi, lo;
-        split8<true>(v, hi, lo);
-        *reinterpret_cast<uint4 *>(hi_tile + swz(n, c)) = hi;
-        *reinterpret_cast<uint4 *>(lo_tile + swz(n, c)) = lo;
-    }
-}
-
 // instruction descriptor of the weight-gradient MMAs: M = 64, N = 64, bf16,
 // fp32 accumulate, A and B MN-major (bits 15, 16)
 constexpr uint32_t IDESC_WGRAD = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |

@@ -719,6 +719,141 @@ node_tc_kernel(const __grid_constant__ NodeTcArgs a) {
     if (threadIdx.x < 32) tmem_dealloc<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------
+// K3, first edge layer (factorised): d_h += dP . W1a + dQ . W1b
+// ---------------------------------------------------------------------------
+// The transpose of node_pre (K = 128 as two blocks of 64, N = 64), same shape
+// as the first stage of node_tc: dP rows, then dQ rows, through the same A
+// tiles into one accumulator; B = W1a^T / W1b^T.  Replaces two FFMA linear
+// launches per layer (14 us each at 16 k nodes, launch- and latency-bound).
+constexpr int DG_GROUPS = 5;
+constexpr int DG_THREADS = DG_GROUPS * NT_GROUP_THREADS;
+
+struct __align__(1024) DgSmem {
+    uint8_t A_hi[DG_GROUPS][NT_ROWS * 128];
+    uint8_t A_lo[DG_GROUPS][NT_ROWS * 128];
+    uint8_t Wa_hi[64 * 128], Wa_lo[64 * 128];   // tile[c][j] = W1a[j][c]
+    uint8_t Wb_hi[64 * 128], Wb_lo[64 * 128];
+    uint64_t mbar[DG_GROUPS];
+    uint32_t tmem_base;
+};
+
+struct DgradPqArgs {
+    const float *dP, *dQ;     // [N][64]
+    const float *edge_w1;     // [k][in_e]: W1a = columns 0..k-1, W1b = columns k..2k-1
+    float *d_h;               // [N][k], accumulated into
+    int n_nodes, k, in_e;
+};
+
+__global__ void __launch_bounds__(DG_THREADS, 1)
+dgrad_pq_tc_kernel(const DgradPqArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    DgSmem &S = *reinterpret_cast<DgSmem *>(smem_dyn);
+    if ((smem_u32(smem_dyn) & 1023u) != 0u) __trap();
+    const int g = threadIdx.x / NT_GROUP_THREADS, tid = threadIdx.x % NT_GROUP_THREADS;
+    const int warp = tid >> 5;
+    uint8_t *A_hi = S.A_hi[g], *A_lo = S.A_lo[g];
+    const int k = a.k;
+    load_weight_tiles_T(S.Wa_hi, S.Wa_lo, a.edge_w1, a.in_e, k, k);
+    load_weight_tiles_T(S.Wb_hi, S.Wb_lo, a.edge_w1 + k, a.in_e, k, k);
+    if (tid == 0) mbar_init(&S.mbar[g], 1);
+    if (threadIdx.x < 32) tmem_alloc<512>(&S.tmem_base);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = S.tmem_base;
+    const uint32_t tmem_grp = tmem_base + (uint32_t)g * 64u;
+    const uint32_t tmem_lane = tmem_grp + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0;
+    const RowShare rs = row_share(a.n_nodes, blockIdx.x * DG_GROUPS + g, gridDim.x * DG_GROUPS);
+    pdl_wait();                  // dP, dQ, d_h of the kernels before this one
+    pdl_launch_dependents();
+    for (int row0 = rs.begin; row0 < rs.end; row0 += rs.tile_rows) {
+        const int row_end = min(rs.end, row0 + rs.tile_rows);
+        nt_group_sync(g);
+        load_block<true>(A_hi, A_lo, a.dP, 64, 64, row0, row_end, tid);
+        fence_proxy_async();
+        tc_fence_before();
+        nt_group_sync(g);
+        if (tid == 0) {
+            tc_fence_after();
+            issue_kblock<true>(tmem_grp, tc_idesc(64), A_hi, A_lo, S.Wa_hi, S.Wa_lo, 0);
+            umma_commit(&S.mbar[g]);
+        }
+        mbar_wait(&S.mbar[g], phase);
+        phase ^= 1;
+        load_block<true>(A_hi, A_lo, a.dQ, 64, 64, row0, row_end, tid);
+        fence_proxy_async();
+        tc_fence_before();
+        nt_group_sync(g);
+        if (tid == 0) {
+            tc_fence_after();
+            issue_kblock<true>(tmem_grp, tc_idesc(64), A_hi, A_lo, S.Wb_hi, S.Wb_lo, 1);
+            umma_commit(&S.mbar[g]);
+        }
+        mbar_wait(&S.mbar[g], phase);
+        phase ^= 1;
+        tc_fence_after();
+        // D -> fp32 staging (64 rows in each 16 KB A tile), then d_h += staged
+        // rows as full lines
+        {
+            const int r = tid;
+            float *st = reinterpret_cast<float *>(r < 64 ? A_hi : A_lo);
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                float acc[16];
+                tmem_ld16(tmem_lane + 16 * q, acc);
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4)
+                    *stage_ptr(st, r & 63, 4 * q + v4) =
+                        make_float4(acc[4 * v4], acc[4 * v4 + 1], acc[4 * v4 + 2], acc[4 * v4 + 3]);
+            }
+        }
+        tc_fence_before();
+        nt_group_sync(g);
+        {
+            const int c4 = tid & 15, slot = tid >> 4;
+            const bool vec = (k & 3) == 0;
+#pragma unroll 4
+            for (int p = 0; p < NT_ROWS / 8; ++p) {
+                const int row = p * 8 + slot;
+                if (row0 + row >= row_end) continue;
+                const float *sp = reinterpret_cast<const float *>(row < 64 ? A_hi : A_lo);
+                const float4 v = *stage_ptr(const_cast<float *>(sp), row & 63, c4);
+                float *d = a.d_h + (size_t)(row0 + row) * k + 4 * c4;
+                if (vec && 4 * c4 + 3 < k) {
+                    float4 o = *reinterpret_cast<float4 *>(d);
+                    o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+                    *reinterpret_cast<float4 *>(d) = o;
+                } else {
+                    if (4 * c4 < k) d[0] += v.x;
+                    if (4 * c4 + 1 < k) d[1] += v.y;
+                    if (4 * c4 + 2 < k) d[2] += v.z;
+                    if (4 * c4 + 3 < k) d[3] += v.w;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc<512>(tmem_base);
+}
+
+int launch_dgrad_pq_tc(const float *dP, const float *dQ, const float *edge_w1, float *d_h,
+                       int n_nodes, int k, int in_e, cudaStream_t st) {
+    DgradPqArgs a{dP, dQ, edge_w1, d_h, n_nodes, k, in_e};
+    const size_t smem = sizeof(DgSmem);
+    int grid = num_sms();
+    const int need = (n_nodes + 16 * DG_GROUPS - 1) / (16 * DG_GROUPS);
+    if (need < grid) grid = need;
+    if (grid < 1) grid = 1;
+    const int rc = ensure_smem(dgrad_pq_tc_kernel, smem);
+    if (rc) return rc;
+    launch_chained(dgrad_pq_tc_kernel, dim3(grid), dim3(DG_THREADS), smem, st, a);
+    return check_launch();
+}
+
 int launch_node_pre_tc(const float *h, const float *edge_w1, const float *edge_b1, float *P,
                        float *Q, int n_nodes, int k, int in_e, int perm, int mode,
                        cudaStream_t st) {
