@@ -370,26 +370,6 @@ mean_pool_bwd_kernel(const float *__restrict__ d_pooled, const int32_t *__restri
 // ---------------------------------------------------------------------------
 // node backward
 // ---------------------------------------------------------------------------
-struct NodeBwdArgs {
-    const float *h_in;      // [N][k]
-    const float *M;         // [N][64]
-    const float *d_h_out;   // [N][k]
-    float *d_h_in;          // [N][k]   residual part + Wn1 h-part
-    float *dM;              // [N][64]
-    float *DO, *U, *DV, *O; // [N][64]  factors of the node weight gradients
-    float *dzn, *gdot;      // [N]
-    const float *node_w1, *node_b1, *node_w2, *node_b2, *natt_w, *natt_b, *node_gate;
-    int n_nodes, k;
-    uint32_t flags;
-    int att_act;
-    // GraphNorm (phase 1: stop at dy = dL/d(gn output); phase 2: resume from dv)
-    int phase;                     // 0 = no GraphNorm
-    const float *V;                // [N][64] pre-activation (phase 1, 2)
-    const float *gn_a, *gn_b;      // y = a v + b
-    const float *gn_shift, *gn_invstd;   // c_hat = (v - shift) * invstd
-    float *DY, *DYC;               // [N][64] dy and dy * c_hat (phase 1 out, 2 in)
-    const float *coef;             // [3][64]: dv = c0 dy + c1 c_hat + c2 (phase 2)
-};
 
 __global__ void __launch_bounds__(BT)
 egnn_node_bwd_kernel(const NodeBwdArgs a) {
@@ -1388,7 +1368,13 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
         rc = ensure_smem(egnn_node_bwd_kernel, smem);
         if (rc) return rc;
         const int grid = persistent_grid((n + 15) / 16, 1);
-        if (!graphnorm) {
+        if (!graphnorm && cfg->math != PVS_MATH_FP32) {
+            // tcgen05 node backward (egnn_node_tc.cu): the four contractions as
+            // UMMA, row-per-thread epilogues
+            na.phase = 0;
+            rc = launch_node_bwd_tc(na, st);
+            if (rc) return rc;
+        } else if (!graphnorm) {
             na.phase = 0;
             launch_chained(egnn_node_bwd_kernel, dim3(grid), dim3(BT), smem, st, na);
             rc = check_launch();

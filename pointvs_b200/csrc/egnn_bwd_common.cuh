@@ -49,6 +49,29 @@ __host__ __device__ __forceinline__ int64_t dt1_at(int64_t dt1_rows, int64_t e, 
 bool edge_bwd_tc_supported(const EdgeBwdArgs &a);
 int launch_edge_bwd_tc(const EdgeBwdArgs &a, int grid, cudaStream_t st);
 
+struct NodeBwdArgs {
+    const float *h_in;      // [N][k]
+    const float *M;         // [N][64]
+    const float *d_h_out;   // [N][k]
+    float *d_h_in;          // [N][k]   residual part + Wn1 h-part
+    float *dM;              // [N][64]
+    float *DO, *U, *DV, *O; // [N][64]  factors of the node weight gradients
+    float *dzn, *gdot;      // [N]
+    const float *node_w1, *node_b1, *node_w2, *node_b2, *natt_w, *natt_b, *node_gate;
+    int n_nodes, k;
+    uint32_t flags;
+    int att_act;
+    // GraphNorm (phase 1: stop at dy = dL/d(gn output); phase 2: resume from dv)
+    int phase;                     // 0 = no GraphNorm
+    const float *V;                // [N][64] pre-activation (phase 1, 2)
+    const float *gn_a, *gn_b;      // y = a v + b
+    const float *gn_shift, *gn_invstd;   // c_hat = (v - shift) * invstd
+    float *DY, *DYC;               // [N][64] dy and dy * c_hat (phase 1 out, 2 in)
+    const float *coef;             // [3][64]: dv = c0 dy + c1 c_hat + c2 (phase 2)
+};
+// tcgen05 node backward (egnn_node_tc.cu), phase 0 (no GraphNorm) only.
+int launch_node_bwd_tc(const NodeBwdArgs &a, cudaStream_t st);
+
 // Grouped weight gradients: up to WG_MAX_JOBS products d_w += A^T B (+ column
 // sums of A into d_b) over the same rows, one launch + one reduce (egnn_bwd.cu:
 // FFMA; wgrad_tc.cu: tcgen05).  Per-CTA partial block: [64][128] products, then

@@ -17,6 +17,7 @@
 #include <cuda.h>       // CUtensorMap (types only: the encoder comes from the runtime)
 
 #include "egnn_common.cuh"
+#include "egnn_bwd_common.cuh"
 #include "tc_common.cuh"
 
 namespace pvs {
@@ -851,6 +852,301 @@ int launch_dgrad_pq_tc(const float *dP, const float *dQ, const float *edge_w1, f
     const int rc = ensure_smem(dgrad_pq_tc_kernel, smem);
     if (rc) return rc;
     launch_chained(dgrad_pq_tc_kernel, dim3(grid), dim3(DG_THREADS), smem, st, a);
+    return check_launch();
+}
+
+// ---------------------------------------------------------------------------
+// K3, node model backward (no GraphNorm) on tcgen05
+// ---------------------------------------------------------------------------
+// Autograd of node_model (egnn_satorras.py:134-166), same mathematics as
+// egnn_node_bwd_kernel (egnn_bwd.cu, FFMA) with its four contractions as UMMA
+// in bf16x3:
+//   V  = [h ; M] . W1^T          recompute    two K blocks, B = W1h, W1m (K-major)
+//   O  = U . W2^T                recompute    B = W2 (K-major)
+//   dU = dO . W2                 data grad    B = the SAME W2 tile read MN-major
+//   dh = dV . W1h, dM = dV . W1m data grads   B = the W1h / W1m tiles read MN-major
+// A weight tile image [out][in] serves both directions: K-major it is W^T as
+// the forward needs it, MN-major (rows = K) it is W.  Row-per-thread epilogues
+// as in node_tc: the attention logit, the gate products and d(attention) are
+// thread-local sums over the row; V stays in tensor memory and is re-read for
+// silu'(V).  The factors of the node weight gradients (U, O, dO, dV) go to HBM
+// for wgrad_group_tc_kernel as before.
+constexpr int NB_GROUPS = 4;
+constexpr int NB_THREADS = NB_GROUPS * NT_GROUP_THREADS;
+constexpr uint32_t NB_IDESC_BMN = tc_idesc(64) | (1u << 16);    // B MN-major
+
+struct __align__(1024) NbSmem {
+    uint8_t A_hi[NB_GROUPS][NT_ROWS * 128];
+    uint8_t A_lo[NB_GROUPS][NT_ROWS * 128];
+    uint8_t W1h_hi[64 * 128], W1h_lo[64 * 128];
+    uint8_t W1m_hi[64 * 128], W1m_lo[64 * 128];
+    uint8_t W2_hi[64 * 128], W2_lo[64 * 128];
+    float b1[64], b2[64], wn[64];
+    uint64_t mbar[NB_GROUPS];
+    uint32_t tmem_base;
+};
+
+// D[128 x 64] (+)= A . B with A K-major and B read MN-major (tile rows = K)
+__device__ __forceinline__ void issue_kblock_bmn(uint32_t tmem_d, const uint8_t *a_hi,
+                                                 const uint8_t *a_lo, const uint8_t *b_hi,
+                                                 const uint8_t *b_lo, uint32_t acc) {
+    const uint64_t ah = make_desc(smem_u32(a_hi)), al = make_desc(smem_u32(a_lo));
+    const uint64_t bh = make_desc(smem_u32(b_hi)), bl = make_desc(smem_u32(b_lo));
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t aadv = (uint64_t)(ks * 2);              // 16 bf16 along a row
+        const uint64_t badv = (uint64_t)(ks * (2048 >> 4));    // 16 rows of 128 bytes
+        umma_bf16(tmem_d, ah + aadv, bh + badv, NB_IDESC_BMN, acc);
+        acc = 1;
+        umma_bf16(tmem_d, al + aadv, bh + badv, NB_IDESC_BMN, 1);
+        umma_bf16(tmem_d, ah + aadv, bl + badv, NB_IDESC_BMN, 1);
+    }
+}
+
+// 16 floats [c0, c0 + 16) of a row with `kv` valid columns (zeros beyond / !ok)
+__device__ __forceinline__ void row_load16(const float *row, int kv, int c0, bool ok, bool vec,
+                                           float (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+    if (!ok || c0 >= kv) return;
+    if (vec && c0 + 16 <= kv) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(row + c0) + j);
+            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (c0 + i < kv) v[i] = __ldg(row + c0 + i);
+    }
+}
+__device__ __forceinline__ void row_store16(float *row, int kv, int c0, bool ok, bool vec,
+                                            const float (&v)[16]) {
+    if (!ok || c0 >= kv) return;
+    if (vec && c0 + 16 <= kv) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            reinterpret_cast<float4 *>(row + c0)[j] =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (c0 + i < kv) row[c0 + i] = v[i];
+    }
+}
+
+__global__ void __launch_bounds__(NB_THREADS, 1)
+node_bwd_tc_kernel(const NodeBwdArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    NbSmem &S = *reinterpret_cast<NbSmem *>(smem_dyn);
+    if ((smem_u32(smem_dyn) & 1023u) != 0u) __trap();
+    const int g = threadIdx.x / NT_GROUP_THREADS, tid = threadIdx.x % NT_GROUP_THREADS;
+    const int warp = tid >> 5;
+    uint8_t *A_hi = S.A_hi[g], *A_lo = S.A_lo[g];
+    const int k = a.k;
+    load_weight_tiles<true>(S.W1h_hi, S.W1h_lo, a.node_w1, 2 * k, k, k);
+    load_weight_tiles<true>(S.W1m_hi, S.W1m_lo, a.node_w1 + k, 2 * k, k, k);
+    load_weight_tiles<true>(S.W2_hi, S.W2_lo, a.node_w2, k, k, k);
+    for (int n = threadIdx.x; n < 64; n += NB_THREADS) {
+        S.b1[n] = n < k ? a.node_b1[n] : 0.0f;
+        S.b2[n] = n < k ? a.node_b2[n] : 0.0f;
+        S.wn[n] = (n < k && a.natt_w) ? a.natt_w[n] : 0.0f;
+    }
+    if (tid == 0) mbar_init(&S.mbar[g], 1);
+    if (threadIdx.x < 32) tmem_alloc<512>(&S.tmem_base);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = S.tmem_base;
+    const uint32_t tmem_grp = tmem_base + (uint32_t)g * 128u;     // V: +0, work: +64
+    const uint32_t tl = tmem_grp + ((uint32_t)(warp * 32) << 16);
+    constexpr uint32_t C_V = 0, C_W = 64;
+    uint32_t phase = 0;
+    const bool f_natt = (a.flags & PVS_F_NODE_ATTENTION) && a.natt_w != nullptr;
+    const bool f_res = a.flags & PVS_F_RESIDUAL;
+    const bool f_rez = f_res && (a.flags & PVS_F_REZERO);
+    const bool f_gat = f_res && (a.flags & PVS_F_GATED_RESIDUAL);
+    const float natt_b = (f_natt && a.natt_b) ? a.natt_b[0] : 0.0f;
+    const float gate = a.node_gate ? a.node_gate[0] : 1.0f;
+    const float G = fmaxf(gate, 0.0f);
+    const bool vec = (k & 3) == 0;
+    auto publish = [&]() {
+        fence_proxy_async();
+        tc_fence_before();
+        nt_group_sync(g);
+    };
+    auto commit_wait = [&]() {
+        if (tid == 0) umma_commit(&S.mbar[g]);
+        mbar_wait(&S.mbar[g], phase);
+        phase ^= 1;
+        tc_fence_after();
+    };
+    // 16 values of this thread's row -> chunks 2 q, 2 q + 1 of the A tiles
+    auto to_tile = [&](int q, const float (&v)[16]) {
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+            float u8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u8[i] = v[8 * hlf + i];
+            uint4 hi, lo;
+            split8<true>(u8, hi, lo);
+            *reinterpret_cast<uint4 *>(A_hi + swz(tid, 2 * q + hlf)) = hi;
+            *reinterpret_cast<uint4 *>(A_lo + swz(tid, 2 * q + hlf)) = lo;
+        }
+    };
+    const RowShare rs = row_share(a.n_nodes, blockIdx.x * NB_GROUPS + g, gridDim.x * NB_GROUPS);
+    pdl_wait();                  // chain kernel (backward order): see pvs_common.cuh
+    pdl_launch_dependents();
+    for (int row0 = rs.begin; row0 < rs.end; row0 += rs.tile_rows) {
+        const int row_end = min(rs.end, row0 + rs.tile_rows);
+        const int r = tid;
+        const bool ok = row0 + r < row_end;
+        const size_t row = (size_t)(row0 + (ok ? r : 0));
+        nt_group_sync(g);
+        // ---- V = [h ; M] . W1^T ----
+        load_block<true>(A_hi, A_lo, a.h_in, k, k, row0, row_end, tid);
+        publish();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_kblock<true>(tmem_grp + C_V, tc_idesc(64), A_hi, A_lo, S.W1h_hi, S.W1h_lo, 0);
+        }
+        commit_wait();
+        load_block<true>(A_hi, A_lo, a.M, 64, 64, row0, row_end, tid);
+        publish();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_kblock<true>(tmem_grp + C_V, tc_idesc(64), A_hi, A_lo, S.W1m_hi, S.W1m_lo, 1);
+        }
+        commit_wait();
+        // ---- U = silu(V + b1) -> A tiles, HBM ----
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            float v[16];
+            tmem_ld16(tl + C_V + 16 * q, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = siluf_(v[i] + S.b1[16 * q + i]);
+            to_tile(q, v);
+            row_store16(a.U + row * 64, 64, 16 * q, ok, true, v);
+        }
+        tc_fence_before();
+        publish();
+        // ---- O = U . W2^T ----
+        if (tid == 0) {
+            tc_fence_after();
+            issue_kblock<true>(tmem_grp + C_W, tc_idesc(64), A_hi, A_lo, S.W2_hi, S.W2_lo, 0);
+        }
+        commit_wait();
+        // ---- attention, residual variants and their backward down to dO ----
+        const float *ghrow = a.d_h_out + row * k;
+        const float *hrow = a.h_in + row * k;
+        float zdot = 0.0f, dsd = 0.0f, gho = 0.0f, ghh = 0.0f;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            float o[16], gh[16];
+            tmem_ld16(tl + C_W + 16 * q, o);
+            row_load16(ghrow, k, 16 * q, ok, vec, gh);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                o[i] += S.b2[16 * q + i];
+                zdot = fmaf(S.wn[16 * q + i], o[i], zdot);
+                const float do2 = f_rez ? gate * gh[i] : (f_gat ? G * gh[i] : gh[i]);
+                dsd = fmaf(do2, o[i], dsd);
+                gho = fmaf(gh[i], o[i], gho);
+            }
+            if (f_gat) {
+                float hv[16];
+                row_load16(hrow, k, 16 * q, ok, vec, hv);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) ghh = fmaf(gh[i], hv[i], ghh);
+            }
+            row_store16(a.O + row * 64, 64, 16 * q, ok, true, o);
+        }
+        float s = 1.0f, dz = 0.0f;
+        if (f_natt) {
+            const float zn = zdot + natt_b;
+            const bool soft = a.flags & PVS_F_SOFTMAX_ATTENTION;
+            s = soft ? zn : apply_act(zn, a.att_act);
+            dz = dsd * (soft ? 1.0f : act_grad(zn, s, a.att_act));
+        }
+        if (ok) {
+            a.dzn[row0 + r] = dz;
+            a.gdot[row0 + r] = f_rez ? s * gho : (f_gat ? (gate > 0.0f ? s * gho - ghh : 0.0f) : 0.0f);
+        }
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            float o[16], gh[16];
+            tmem_ld16(tl + C_W + 16 * q, o);
+            row_load16(ghrow, k, 16 * q, ok, vec, gh);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float do2 = f_rez ? gate * gh[i] : (f_gat ? G * gh[i] : gh[i]);
+                o[i] = fmaf(dz, S.wn[16 * q + i], do2 * s);     // dO
+            }
+            to_tile(q, o);
+            row_store16(a.DO + row * 64, 64, 16 * q, ok, true, o);
+        }
+        tc_fence_before();
+        publish();
+        // ---- dU = dO . W2 ----
+        if (tid == 0) {
+            tc_fence_after();
+            issue_kblock_bmn(tmem_grp + C_W, A_hi, A_lo, S.W2_hi, S.W2_lo, 0);
+        }
+        commit_wait();
+        // ---- dV = dU * silu'(V + b1) -> A tiles, HBM ----
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            float du[16], v[16];
+            tmem_ld16(tl + C_W + 16 * q, du);
+            tmem_ld16(tl + C_V + 16 * q, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                du[i] = (ok && 16 * q + i < k) ? du[i] * silu_gradf_(v[i] + S.b1[16 * q + i]) : 0.0f;
+            to_tile(q, du);
+            row_store16(a.DV + row * 64, 64, 16 * q, ok, true, du);
+        }
+        tc_fence_before();
+        publish();           // every thread is done with V in tensor memory
+        // ---- dh = dV . W1h -> work columns, dM = dV . W1m -> V's columns ----
+        if (tid == 0) {
+            tc_fence_after();
+            issue_kblock_bmn(tmem_grp + C_W, A_hi, A_lo, S.W1h_hi, S.W1h_lo, 0);
+            issue_kblock_bmn(tmem_grp + C_V, A_hi, A_lo, S.W1m_hi, S.W1m_lo, 0);
+        }
+        commit_wait();
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            float dh[16], gh[16], dm[16];
+            tmem_ld16(tl + C_W + 16 * q, dh);
+            tmem_ld16(tl + C_V + 16 * q, dm);
+            row_load16(ghrow, k, 16 * q, ok, vec, gh);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                // residual branch of dL/dh: gh (plain, rezero), (1 - G) gh (gated)
+                const float dres = !f_res ? 0.0f : (f_gat ? (1.0f - G) * gh[i] : gh[i]);
+                dh[i] += dres;
+            }
+            row_store16(a.d_h_in + row * k, k, 16 * q, ok, vec, dh);
+            row_store16(a.dM + row * 64, 64, 16 * q, ok, true, dm);
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc<512>(tmem_base);
+}
+
+int launch_node_bwd_tc(const NodeBwdArgs &a, cudaStream_t st) {
+    const size_t smem = sizeof(NbSmem);
+    int grid = num_sms();
+    const int need = (a.n_nodes + 16 * NB_GROUPS - 1) / (16 * NB_GROUPS);
+    if (need < grid) grid = need;
+    if (grid < 1) grid = 1;
+    const int rc = ensure_smem(node_bwd_tc_kernel, smem);
+    if (rc) return rc;
+    launch_chained(node_bwd_tc_kernel, dim3(grid), dim3(NB_THREADS), smem, st, a);
     return check_launch();
 }
 
