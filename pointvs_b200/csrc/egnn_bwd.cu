@@ -27,6 +27,10 @@
 
 namespace pvs {
 
+// Side stream of the stacked backward (egnn_model.cu) for the reductions into
+// the parameter gradients; null in per-layer calls.
+thread_local const BwdSide *g_bwd_side = nullptr;
+
 constexpr int BT = 256;           // threads
 constexpr int KB = 64;            // internal pitch of every [*, k] buffer here
 constexpr int LDT = KB + 4;       // smem tile pitch
@@ -1342,6 +1346,7 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
         return PVS_ERR_WORKSPACE;
 
     cudaStream_t st = (cudaStream_t)stream;
+    const BwdSide *side = g_bwd_side;
     // the backward kernels of a layer form a launch chain (pvs_common.cuh)
     struct ChainScope {
         bool prev;
@@ -1465,7 +1470,17 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
             if (rc) return rc;
             egnn_edge_bwd_kernel<<<w.edge_grid, BT, smem, st>>>(eb);
         }
-        launch_chained(edge_bwd_reduce_kernel, dim3((EP_STRIDE + 255) / 256), dim3(256), 0, st,
+        // The reductions into the parameter gradients are off the critical path
+        // (nothing later in the backward reads a parameter gradient): inside
+        // pvs_egnn_stack_bwd they run on a side stream, concurrently with the
+        // rest of this layer and the node backward of the next one.
+        cudaStream_t st_red = st;
+        if (side) {
+            cudaEventRecord(side->ev_a, st);
+            cudaStreamWaitEvent(side->stream, side->ev_a, 0);
+            st_red = side->stream;
+        }
+        launch_chained(edge_bwd_reduce_kernel, dim3((EP_STRIDE + 255) / 256), dim3(256), 0, st_red,
                        (const float *)w.edge_partial, w.edge_grid, *grads, k, in_e, col_r,
                        cfg->n_edge_classes);
         launch_chained(csc_gather_kernel, dim3((n + 7) / 8), dim3(256), 0, st, csc_ptr, csc_eid, n,
@@ -1505,7 +1520,13 @@ int pvs_egnn_layer_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
         wg.add(w.dQ, KB, k, h_in, k, k, grads->edge_w1 ? grads->edge_w1 + k : nullptr, in_e,
                nullptr);
     }
-    rc = wg.launch(n, w.wg_partial, st, cfg->math != PVS_MATH_FP32);
+    cudaStream_t st_wg = st;
+    if (side) {
+        cudaEventRecord(side->ev_b, st);
+        cudaStreamWaitEvent(side->stream, side->ev_b, 0);
+        st_wg = side->stream;
+    }
+    rc = wg.launch(n, w.wg_partial, st_wg, cfg->math != PVS_MATH_FP32);
     if (rc) return rc;
     return PVS_OK;
 }

@@ -72,6 +72,12 @@ struct NodeBwdArgs {
 // tcgen05 node backward (egnn_node_tc.cu), phase 0 (no GraphNorm) only.
 int launch_node_bwd_tc(const NodeBwdArgs &a, cudaStream_t st);
 
+struct BwdSide {
+    cudaStream_t stream;
+    cudaEvent_t ev_a, ev_b;     // fork points on the main stream
+};
+extern thread_local const BwdSide *g_bwd_side;
+
 // Grouped weight gradients: up to WG_MAX_JOBS products d_w += A^T B (+ column
 // sums of A into d_b) over the same rows, one launch + one reduce (egnn_bwd.cu:
 // FFMA; wgrad_tc.cu: tcgen05).  Per-CTA partial block: [64][128] products, then

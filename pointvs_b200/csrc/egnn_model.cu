@@ -4,6 +4,7 @@
 #include <cstdlib>
 
 #include "egnn_common.cuh"
+#include "egnn_bwd_common.cuh"
 
 using namespace pvs;
 
@@ -215,7 +216,9 @@ int64_t pvs_egnn_stack_bwd_workspace_bytes(int32_t n_nodes, int32_t n_edges, int
         if (v > lw) lw = v;
     }
     const int k = cfgs[0].k;
-    return align_up(lw, 256) + 2 * align_up((int64_t)n_nodes * k * 4, 256) +
+    // two layer workspaces: layer l's gradient reductions still read theirs on
+    // the side stream while layer l - 1 runs in the other one
+    return 2 * align_up(lw, 256) + 2 * align_up((int64_t)n_nodes * k * 4, 256) +
            2 * align_up((int64_t)n_nodes * 3 * 4, 256) + 256;
 }
 
@@ -238,24 +241,66 @@ int pvs_egnn_stack_bwd(const pvs_graph *g, const int32_t *csc_ptr, const int32_t
     float *dh[2], *dx[2];
     for (int i = 0; i < 2; ++i) { dh[i] = (float *)p; p += align_up((int64_t)n * k * 4, 256); }
     for (int i = 0; i < 2; ++i) { dx[i] = (float *)p; p += align_up((int64_t)n * 3 * 4, 256); }
-    void *lws = p;
-    const int64_t lws_bytes = workspace_bytes - (p - (char *)workspace);
+    const int64_t lws_bytes = ((workspace_bytes - (p - (char *)workspace)) / 2) & ~(int64_t)255;
+    void *lws[2] = {p, p + lws_bytes};
+    cudaStream_t st = (cudaStream_t)stream;
+    // Side stream for the reductions into the parameter gradients (per-CTA
+    // partials of the edge kernel, the grouped weight gradients): nothing later
+    // in the backward reads them, so they run beside the next layer's node and
+    // edge kernels.  Each layer uses the workspace the layer before the
+    // previous one has finished with (ev_done), and everything is joined to the
+    // caller's stream at the end.  PVS_NO_BWD_SIDE=1 keeps one stream.
+    static const bool no_side = getenv("PVS_NO_BWD_SIDE") != nullptr;
+    struct SideRes {
+        BwdSide s{};
+        cudaEvent_t ev_done[2]{};
+        bool ok = false;
+        SideRes() {
+            ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&s.ev_a, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&s.ev_b, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ev_done[0], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ev_done[1], cudaEventDisableTiming) == cudaSuccess;
+        }
+    };
+    static thread_local SideRes *res[16] = {};      // per device of this host thread
+    SideRes *sr = nullptr;
+    int dev = 0;
+    if (!no_side && n_layers > 1 && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 16) {
+        if (!res[dev]) res[dev] = new SideRes();
+        if (res[dev]->ok) sr = res[dev];
+    }
+    bool pending[2] = {false, false};
     const float *dh_cur = d_h_out, *dx_cur = d_x_out;
-    for (int l = n_layers - 1; l >= 0; --l) {
+    int rc = PVS_OK;
+    for (int l = n_layers - 1; l >= 0 && rc == PVS_OK; --l) {
         pvs_layer_config cfg = cfgs[l];
         if (layer_ws != nullptr)
             cfg.saved_fwd_workspace = (const char *)layer_ws + (size_t)l * layer_ws_stride;
         float *dh_next = l == 0 ? d_h_in : dh[l & 1];
         float *dx_next = l == 0 ? d_x_in : dx[l & 1];
-        int rc = pvs_egnn_layer_bwd(g, csc_ptr, csc_eid, &cfg, &params[l],
-                                    H + (size_t)l * n * k, X + (size_t)l * n * 3, nullptr,
-                                    dh_cur, dx_cur, nullptr, dh_next, dx_next, nullptr,
-                                    &grads[l], lws, lws_bytes, stream);
-        if (rc) return rc;
+        const int par = l & 1;
+        if (sr && pending[par]) {        // the reductions that read this workspace
+            cudaStreamWaitEvent(st, sr->ev_done[par], 0);
+            pending[par] = false;
+        }
+        g_bwd_side = sr ? &sr->s : nullptr;
+        rc = pvs_egnn_layer_bwd(g, csc_ptr, csc_eid, &cfg, &params[l],
+                                H + (size_t)l * n * k, X + (size_t)l * n * 3, nullptr,
+                                dh_cur, dx_cur, nullptr, dh_next, dx_next, nullptr,
+                                &grads[l], lws[sr ? par : 0], lws_bytes, stream);
+        g_bwd_side = nullptr;
+        if (sr) {
+            cudaEventRecord(sr->ev_done[par], sr->s.stream);
+            pending[par] = true;
+        }
         dh_cur = dh_next;
         dx_cur = dx_next;
     }
-    return PVS_OK;
+    if (sr)
+        for (int par = 0; par < 2; ++par)
+            if (pending[par]) cudaStreamWaitEvent(st, sr->ev_done[par], 0);
+    return rc;
 }
 
 }  // extern "C"
