@@ -86,6 +86,70 @@ linear_fwd_kernel(const float *__restrict__ in, int ld_in, int rows, int ki,
 }
 
 // ---------------------------------------------------------------------------
+// linear with a short input (the atom-feature embedding: ki = 13..32 -> 64):
+// streaming, one thread per (row, four output columns), 64 rows per block; the
+// weights sit in shared memory, a row's inputs are broadcast loads.  The
+// generic kernel stages 64-row tiles for a K = 13 product and spent 33 us on
+// what is a 40 MB copy.  Same accumulation order (k ascending, bias last).
+// ---------------------------------------------------------------------------
+constexpr int LSK_MAX_KI = 32;
+__global__ void __launch_bounds__(256)
+linear_smallk_kernel(const float *__restrict__ in, int ld_in, int rows, int ki,
+                     const float *__restrict__ W, int ld_w, const float *__restrict__ b,
+                     int ko, int act, float *__restrict__ out, int ld_out) {
+    pdl_wait();                  // chain kernel: see pvs_common.cuh
+    pdl_launch_dependents();
+    __shared__ __align__(16) float Ws[LSK_MAX_KI][64];
+    __shared__ __align__(16) float bs[64];
+    for (int idx = threadIdx.x; idx < ki * 64; idx += blockDim.x) {
+        const int kk = idx >> 6, n = idx & 63;
+        Ws[kk][n] = n < ko ? W[(size_t)n * ld_w + kk] : 0.0f;
+    }
+    if (threadIdx.x < 64) bs[threadIdx.x] = (b != nullptr && threadIdx.x < ko) ? b[threadIdx.x] : 0.0f;
+    __syncthreads();
+    const int cg = threadIdx.x & 15, rg = threadIdx.x >> 4;
+    const bool vec = (ld_out & 3) == 0 && (ko & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    // the 16 lanes of a row fetch its inputs once (one or two coalesced loads)
+    // and pass them round by shuffle; a weight vector read from shared memory
+    // serves the thread's four rows
+    float xa[4], xb[4], acc[4][4] = {};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = blockIdx.x * 64 + rg + 16 * i;
+        const bool ok = r < rows;
+        const float *x = in + (size_t)(ok ? r : 0) * ld_in;
+        xa[i] = (ok && cg < ki) ? __ldg(x + cg) : 0.0f;
+        xb[i] = (ok && 16 + cg < ki) ? __ldg(x + 16 + cg) : 0.0f;
+    }
+    for (int kk = 0; kk < ki; ++kk) {
+        const float4 w4 = *reinterpret_cast<const float4 *>(&Ws[kk][4 * cg]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float xv = __shfl_sync(0xffffffffu, kk < 16 ? xa[i] : xb[i], kk & 15, 16);
+            acc[i][0] = fmaf(xv, w4.x, acc[i][0]); acc[i][1] = fmaf(xv, w4.y, acc[i][1]);
+            acc[i][2] = fmaf(xv, w4.z, acc[i][2]); acc[i][3] = fmaf(xv, w4.w, acc[i][3]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = blockIdx.x * 64 + rg + 16 * i;
+        if (r >= rows) continue;
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = apply_act(acc[i][c] + bs[4 * cg + c], act);
+        float *dst = out + (size_t)r * ld_out + 4 * cg;
+        if (vec && 4 * cg + 3 < ko) {
+            *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (4 * cg + c < ko) dst[c] = v[c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // mean pool: one CTA per graph
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -613,6 +677,11 @@ int launch_linear(const float *in, int ld_in, int rows, int ki,
                   int act, float *out, int ld_out, cudaStream_t st,
                   int w_in_major, int accumulate) {
     if (rows == 0) return PVS_OK;
+    if (ki <= LSK_MAX_KI && ko <= 64 && !w_in_major && !accumulate && rows >= 4096) {
+        launch_chained(linear_smallk_kernel, dim3((rows + 63) / 64), dim3(256), 0, st, in, ld_in,
+                       rows, ki, w, ld_w, b, ko, act, out, ld_out);
+        return check_launch();
+    }
     const int kip = (ki + 3) & ~3;
     const int nj4 = ko <= 64 ? 1 : 2;
     const int ldw = 64 * nj4;
