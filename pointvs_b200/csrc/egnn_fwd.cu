@@ -156,8 +156,37 @@ __global__ void __launch_bounds__(256)
 mean_pool_kernel(const float *__restrict__ h, const int32_t *__restrict__ ptr,
                  int k, float *__restrict__ pooled) {
     __shared__ float part[4][64];
+    __shared__ __align__(16) float part16[16][64];
     const int g = blockIdx.x;
     const int lo = ptr[g], hi = ptr[g + 1];
+    if (k == 64 && (reinterpret_cast<uintptr_t>(h) & 15) == 0) {
+        // 16 lanes x float4 per row, 16 rows in flight per step, two steps
+        // unrolled; partials added in a fixed order
+        const int c4 = threadIdx.x & 15, rgp = threadIdx.x >> 4;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s;
+        int r = lo + rgp;
+        for (; r + 16 < hi; r += 32) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(h + (size_t)r * 64) + c4);
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(h + (size_t)(r + 16) * 64) + c4);
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+            s2.x += b.x; s2.y += b.y; s2.z += b.z; s2.w += b.w;
+        }
+        if (r < hi) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(h + (size_t)r * 64) + c4);
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        }
+        *reinterpret_cast<float4 *>(&part16[rgp][4 * c4]) =
+            make_float4(s.x + s2.x, s.y + s2.y, s.z + s2.z, s.w + s2.w);
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            float tot = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) tot += part16[q][threadIdx.x];
+            const int cnt = hi - lo;
+            pooled[(size_t)g * 64 + threadIdx.x] = tot / (float)(cnt > 0 ? cnt : 1);
+        }
+        return;
+    }
     const int cl = threadIdx.x & 63, grp = threadIdx.x >> 6;
     for (int c0 = 0; c0 < k; c0 += 64) {
         const int c = c0 + cl;
