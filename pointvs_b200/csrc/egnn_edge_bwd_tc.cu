@@ -59,6 +59,10 @@ constexpr int WG_ISSUER = 128;    // thread that issues the weight-gradient MMAs
 constexpr int KB = 64;
 // TMEM columns
 constexpr uint32_t C_D1 = 0, C_D2 = 64, C_D3 = 128, C_D4 = 192, C_DW2 = 256, C_DWC1 = 320;
+// m = silu(t2 + b2) and silu'(t2 + b2), parked by E1 for E3 (fp32, the thread's
+// own lane and columns): E3 reads them back instead of evaluating 32 SiLU pairs
+// per thread again
+constexpr uint32_t C_M = 384, C_G2 = 448;
 
 struct BwdTcSmem {
     // activation tiles, bf16 hi [0] / lo [1], 1024-byte aligned
@@ -261,6 +265,15 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
             tmem_ld16(tmem_lane + col + 16 * b, t16);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[16 * b + i] = t16[i];
+        }
+    };
+    auto st32 = [&](uint32_t col, const float (&v)[CW]) {
+#pragma unroll
+        for (int b = 0; b < CW / 16; ++b) {
+            float t16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t16[i] = v[16 * b + i];
+            tmem_st16(tmem_lane + col + 16 * b, t16);
         }
     };
     // CW channels of this thread's row -> bf16 hi / lo tile (16-byte chunks
@@ -487,18 +500,20 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
             // ---- E1: m = silu(t2 + b2) -> M tile; attention logit partial ----
             BPH(3);
             {
-                float v[CW];
+                float v[CW], g2[CW];
                 ld32(C_D1, v);
                 float dot = 0.0f;
 #pragma unroll
                 for (int i = 0; i < CW; ++i) {
                     const int n = CW * cq + i;
-                    float s, g;
-                    silu_pair(v[i] + S.b2[n], s, g);
+                    float s;
+                    silu_pair(v[i] + S.b2[n], s, g2[i]);
                     v[i] = s;
                     dot = fmaf(S.wa[n], s, dot);
                 }
                 store_row(S.Mt, v);
+                st32(C_M, v);
+                st32(C_G2, g2);
                 S.p_za[cq][erow] = dot;
             }
             publish();
@@ -608,14 +623,11 @@ egnn_edge_bwd_tc_kernel(const EdgeBwdArgs a) {
             {
                 float m[CW], sg2[CW];
                 {
-                    float v[CW];
-                    ld32(C_D1, v);
+                    ld32(C_M, m);
+                    ld32(C_G2, sg2);
                     float dot = 0.0f;
 #pragma unroll
-                    for (int i = 0; i < CW; ++i) {
-                        silu_pair(v[i] + S.b2[CW * cq + i], m[i], sg2[i]);
-                        dot = fmaf(dMv[i], m[i], dot);
-                    }
+                    for (int i = 0; i < CW; ++i) dot = fmaf(dMv[i], m[i], dot);
                     S.p_za[cq][erow] = dot;
                 }
                 __syncthreads();

@@ -77,6 +77,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ... and the store (the thread's own lane; completes before it returns)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    uint32_t r[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[i]);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]),
+          "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
+          "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // Shared-memory matrix descriptor, K-major, SWIZZLE_128B, 128-byte rows:
 // start address [0,14) (>>4), LBO [16,30) = 1 (unused for swizzled K-major),
 // SBO [32,46) = 1024 B between 8-row groups, version [46,48) = 1,
