@@ -508,3 +508,42 @@ def test_edge_dropout_matches_published_dropout_adj_semantics():
         sd, cfgs, graph.x.cpu(), thin.edge_index('csr').cpu(), pos0.cpu(),
         thin.edge_attr_onehot('csr').cpu())
     assert helpers.scaled_err(h_want.cpu().numpy(), h_ref.numpy()) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('ki,ko,act', [(13, 64, 'none'), (20, 48, 'silu'),
+                                       (32, 64, 'none'), (7, 30, 'sigmoid')])
+def test_streaming_small_k_linear_equals_tiled_linear(ki, ko, act):
+    """The streaming form of the linear (short inputs, >= 4096 rows: the
+    atom-feature embedding) against fp64 PyTorch (1e-6) and, bit for bit,
+    against the tiled kernel that smaller row counts take (same accumulation
+    order); and the vectorised mean pool against PyTorch."""
+    import torch
+    from pointvs_b200 import dense
+    gen = torch.Generator().manual_seed(ki * 100 + ko)
+    x = torch.randn(5003, ki, generator=gen).cuda()
+    w = (torch.randn(ko, ki, generator=gen) * 0.3).cuda()
+    b = torch.randn(ko, generator=gen).cuda()
+    big = dense.linear(x, w, b, act)                       # streaming kernel
+    small = torch.cat([dense.linear(x[i:i + 1000], w, b, act)    # tiled kernel
+                       for i in range(0, 5003, 1000)])
+    assert torch.equal(big, small)
+    ref = x.double() @ w.double().t() + b.double()
+    ref = {'none': ref, 'silu': torch.nn.functional.silu(ref),
+           'sigmoid': torch.sigmoid(ref)}[act]
+    assert float((big.double() - ref).abs().max()) < 2e-6 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.gpu
+def test_mean_pool_matches_torch():
+    import torch
+    from pointvs_b200 import dense
+    gen = torch.Generator().manual_seed(3)
+    sizes = [1, 17, 1000, 33, 512, 5]
+    ptr_ = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int32).cuda()
+    for k in (64, 40):
+        h = torch.randn(int(ptr_[-1]), k, generator=gen).cuda()
+        got = dense.mean_pool(h, None, len(sizes), graph_ptr=ptr_)
+        want = torch.stack([h[int(ptr_[i]):int(ptr_[i + 1])].double().mean(0)
+                            for i in range(len(sizes))])
+        assert float((got.double() - want).abs().max()) < 1e-6
